@@ -1,0 +1,234 @@
+/* taknative.h -- C ABI of the B200-native AlphaTak self-play engine (libtaknative.so).
+ *
+ * This is the drop-in boundary for the ONE hot path of ViliamVadocz/tak:
+ *   tak::Game::{possible_moves, play, result}   (reference: tak/src/move_gen.rs:7-102, game.rs:121-267)
+ *   alpha_tak::Node::{virtual_rollout, devirtualize_path, rollout, improved_policy, pick_move, play}
+ *                                               (reference: alpha-tak/src/search/mcts.rs:16-125, play.rs:13-67)
+ *   alpha_tak::Network::policy_eval             (reference: alpha-tak/src/model/network.rs:34, net6.rs:124-138)
+ *   train::self_play_parallel                   (reference: train/src/self_play.rs:96-262)
+ * The reference has no FFI layer of its own (it is a pure-Rust workspace); each entry point below names
+ * the Rust item a `extern "C"` shim crate would forward to it (INTEGRATION.md shows that shim).
+ *
+ * Conventions
+ *   - every function returns int32_t: TAK_OK (0) or a negative tak_status code; nothing aborts.
+ *   - output buffers are caller-allocated, with a capacity argument and a returned count.
+ *   - a tak_engine_t owns all device memory and one CUDA stream; use one engine from one host thread at a
+ *     time (engines are independent, thread-per-GPU is fine).  Calls that return host data synchronise the
+ *     engine's stream before returning; calls documented "async" only enqueue work.
+ *   - there is NO CPU fallback: every compute entry point fails with TAK_ERR_CUDA if the device is missing.
+ *
+ * Move encoding (uint16_t), shared by every entry point:
+ *   bits 0-5   square index = row * N + col          (col = file a.., row = rank 1..)
+ *   bits 6-7   placement: piece 0 Flat, 1 Wall, 2 Cap | spread: direction 0 Up(+) 1 Down(-) 2 Left(<) 3 Right(>)
+ *   bits 8-15  spread pattern mask (0 => the move is a placement).  MSB-first: each drop of c pieces is
+ *              c-1 zero bits followed by a one bit (takparse 0.5.5 `Pattern::mask`), e.g. "3a1>21" -> 0b0110_0000.
+ */
+#ifndef TAKNATIVE_H
+#define TAKNATIVE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum tak_status {
+    TAK_OK = 0,
+    /* tak::PlayError (reference: tak/src/error.rs:4-15) */
+    TAK_ERR_OUT_OF_BOUNDS = -1,
+    TAK_ERR_ALREADY_OCCUPIED = -2,
+    TAK_ERR_NO_CAPSTONE = -3,
+    TAK_ERR_NO_STONES = -4,
+    TAK_ERR_OPENING_NON_FLAT = -5,
+    TAK_ERR_EMPTY_SQUARE = -6,
+    TAK_ERR_STACK_NOT_OWNED = -7,
+    TAK_ERR_STACK_WALL = -8,         /* StackError::Wall */
+    TAK_ERR_STACK_CAP = -9,          /* StackError::Cap */
+    TAK_ERR_TAKE_ZERO = -10,         /* TakeError::Zero */
+    TAK_ERR_TAKE_CARRY_LIMIT = -11,  /* TakeError::CarryLimit */
+    TAK_ERR_TAKE_STACK_SIZE = -12,   /* TakeError::StackSize */
+    TAK_ERR_SPREAD_OUT_OF_BOUNDS = -13,
+    /* boundary errors */
+    TAK_ERR_BAD_ARG = -32,
+    TAK_ERR_CUDA = -33,
+    TAK_ERR_CAPACITY = -34,          /* caller buffer or device pool too small */
+    TAK_ERR_PARSE = -35,
+    TAK_ERR_NO_NETWORK = -36,
+    TAK_ERR_INVALID_MOVE = -37       /* e.g. mcts_play of a move that is not a child (reference panics) */
+} tak_status;
+
+/* tak::GameResult (reference: tak/src/game_result.rs:4-8), one byte:
+ *   0 Ongoing | 1 Winner{White} | 2 Winner{Black} | 3 Draw ; bit 4 (0x10) = road / reversible_plies flag */
+enum {
+    TAK_RESULT_ONGOING = 0,
+    TAK_RESULT_WHITE = 1,
+    TAK_RESULT_BLACK = 2,
+    TAK_RESULT_DRAW = 3,
+    TAK_RESULT_FLAG = 0x10
+};
+
+/* POD mirror of tak::Game<N> (reference: tak/src/game.rs:25-35, board.rs:8-10, tile.rs:7-10) for N = 3..8.
+ * Square index = row * n + col.  Stack colours bottom -> top, bit i set = Black. */
+typedef struct tak_state {
+    uint8_t n;
+    uint8_t to_move; /* 0 White, 1 Black */
+    uint16_t ply;
+    uint8_t white_stones, white_caps, black_stones, black_caps;
+    int8_t half_komi;
+    uint8_t reversible_plies;
+    uint8_t _pad[6];
+    uint8_t height[64];
+    uint8_t top[64];        /* kind of the top piece: 0 Flat, 1 Wall, 2 Cap (0 on an empty square) */
+    uint64_t stack_lo[64];  /* pieces 0..63 */
+    uint64_t stack_hi[64];  /* pieces 64..127 (only reachable for N >= 7) */
+} tak_state_t;
+
+typedef struct tak_engine tak_engine_t;
+
+typedef struct tak_engine_config {
+    int32_t device;            /* CUDA ordinal */
+    int32_t n;                 /* board size 3..8 */
+    int32_t max_games;         /* concurrent games (and search trees) */
+    int32_t nodes_per_game;    /* MCTS node-pool capacity per game and per half (0 => default) */
+    int32_t max_batch;         /* max leaves per network call (0 => max_games) */
+    int32_t reserved[3];
+} tak_engine_config_t;
+
+/* ---- engine ------------------------------------------------------------------------------------- */
+int32_t tak_engine_create(const tak_engine_config_t* cfg, tak_engine_t** out);
+int32_t tak_engine_destroy(tak_engine_t* e);
+int32_t tak_engine_sync(tak_engine_t* e);
+const char* tak_last_error(void);      /* thread-local text for the last failing call */
+int32_t tak_version(void);
+
+/* ---- tak::Game -----------------------------------------------------------------------------------
+ * tak_games_reset        Game::with_half_komi (game.rs:57-71)              games [first, first+count)
+ * tak_games_upload/...   host <-> device copy of whole states
+ * tak_possible_moves     Game::possible_moves (move_gen.rs:7-30), same order; out_offsets has n+1 entries
+ * tak_play               Game::play (game.rs:121-130); out_status[i] = TAK_OK or the PlayError code.  As in
+ *                        the reference a failed play may leave that game in an invalid state.
+ * tak_result             Game::result (game.rs:220-267)
+ * tak_perft              perf_count (tak/tests/perft.rs:3-18): same counting rule, breadth-first on device  */
+int32_t tak_games_reset(tak_engine_t* e, int32_t first, int32_t count, int32_t half_komi);
+int32_t tak_games_upload(tak_engine_t* e, const int32_t* ids, int32_t n, const tak_state_t* states);
+int32_t tak_games_download(tak_engine_t* e, const int32_t* ids, int32_t n, tak_state_t* states);
+int32_t tak_possible_moves(tak_engine_t* e, const int32_t* ids, int32_t n, uint16_t* out_moves, int32_t* out_offsets,
+                           int32_t cap);
+int32_t tak_play(tak_engine_t* e, const int32_t* ids, const uint16_t* moves, int32_t n, int32_t* out_status);
+int32_t tak_result(tak_engine_t* e, const int32_t* ids, int32_t n, uint8_t* out_results);
+int32_t tak_perft(tak_engine_t* e, const tak_state_t* root, int32_t depth, uint64_t* out_nodes);
+/* timing hook for bench.py: device milliseconds (CUDA events on the engine stream) of the last tak_perft, and
+ * the number of child states it materialised / kernels it launched */
+int32_t tak_perft_stats(tak_engine_t* e, double* out_ms, uint64_t* out_materialised, uint64_t* out_launches);
+
+/* ---- host-side (cold) helpers: takparse surface ---------------------------------------------------
+ * tak_move_index         alpha_tak::search::move_index (move_map.rs:19-48)
+ * tak_ptn_parse/format   takparse Move FromStr / Display
+ * tak_tps_format/parse   From<Game> for Tps / From<Tps> for Game (tak/src/tps.rs:7-96)                */
+int32_t tak_move_index(int32_t n, uint16_t move, int32_t* out_index);
+int32_t tak_policy_size(int32_t n, int32_t* out_size);
+int32_t tak_ptn_parse(int32_t n, const char* text, uint16_t* out_move);
+int32_t tak_ptn_format(int32_t n, uint16_t move, char* out, int32_t cap);
+int32_t tak_tps_format(const tak_state_t* s, char* out, int32_t cap);
+int32_t tak_tps_parse(int32_t n, const char* text, tak_state_t* out);
+int32_t tak_state_init(int32_t n, int32_t half_komi, tak_state_t* out);
+
+/* ---- alpha_tak::Network ---------------------------------------------------------------------------
+ * net_create             Net5::default / Net6::default shapes (net5.rs:29-73, net6.rs:29-68); arch = 5 or 6, or
+ *                        0 for the DummyNet of search/tests.rs:6-35 (policy all ones, eval 0; any N)
+ * net_load_weights       fp32 host blob, tensors concatenated in the order documented in DESIGN.md
+ *                        (conv weight [co][ci][3][3], conv bias, bn gamma/beta/mean/var ...); BN is folded here
+ * net_load_weights_device  same blob already resident on this device (e.g. after an NCCL broadcast)
+ * net_weights_size       number of fp32 elements of that blob
+ * net_game_repr          alpha_tak::repr::game_repr (repr/game.rs:19-51) as fp32 [C][N][N] per state
+ * net_policy_eval        Network::policy_eval (net6.rs:124-138): out_policy[B][policy_size] softmax over ALL
+ *                        outputs (no legality mask), out_value[B] = tanh(fc)                              */
+int32_t net_create(tak_engine_t* e, int32_t arch);
+int32_t net_weights_size(tak_engine_t* e, int64_t* out_elems);
+int32_t net_load_weights(tak_engine_t* e, const float* blob, int64_t elems);
+int32_t net_load_weights_device(tak_engine_t* e, const void* device_blob, int64_t elems);
+int32_t net_input_channels(int32_t n, int32_t* out_channels);
+int32_t net_game_repr(tak_engine_t* e, const tak_state_t* states, int32_t b, float* out);
+int32_t net_policy_eval(tak_engine_t* e, const tak_state_t* states, int32_t b, float* out_policy, float* out_value);
+/* device-resident variant used by bench.py `value`: evaluates the states of games [first, first+count) in place;
+ * returns device milliseconds for `reps` forward passes */
+int32_t net_forward_timed(tak_engine_t* e, int32_t first, int32_t count, int32_t reps, double* out_ms);
+
+/* ---- alpha_tak::Node (one search tree per game id) --------------------------------------------------
+ * mcts_tree_reset        Node::default()
+ * mcts_virtual_rollout   Node::virtual_rollout x k per game (mcts.rs:26-65), leaves queued in order
+ * mcts_pending           number of queued leaves + their states (what the reference hands to policy_eval)
+ * mcts_devirtualize      Node::devirtualize_path for every queued leaf, in queue order (mcts.rs:67-91), with
+ *                        priors/evals computed on device by the engine's network
+ * mcts_devirtualize_with same, but with caller-supplied network outputs [pending][policy_size], [pending]
+ * mcts_rollouts          fused loop == Node::rollout x n (mcts.rs:16-23) for every listed game in lock step
+ * mcts_children          children of the root: moves (movegen order), visits, priors, expected rewards
+ * mcts_root              root visits / virtual visits / expected reward
+ * mcts_pick_move         Node::pick_move(exploitation=true) (play.rs:49-58): last child with max visits
+ * mcts_play              Node::play (play.rs:26-43): re-root on the child (tree reuse)
+ * mcts_apply_dirichlet   Node::apply_dirichlet (noise.rs:6-16) with a counter-based RNG (seeded)            */
+int32_t mcts_tree_reset(tak_engine_t* e, const int32_t* ids, int32_t n);
+int32_t mcts_virtual_rollout(tak_engine_t* e, const int32_t* ids, int32_t n, int32_t k);
+int32_t mcts_pending(tak_engine_t* e, int32_t* out_count, int32_t* out_game_ids, tak_state_t* out_states,
+                     int32_t cap);
+int32_t mcts_devirtualize(tak_engine_t* e);
+int32_t mcts_devirtualize_with(tak_engine_t* e, const float* policy, const float* value, int32_t count);
+int32_t mcts_rollouts(tak_engine_t* e, const int32_t* ids, int32_t n, int32_t n_rollouts);
+int32_t mcts_children(tak_engine_t* e, int32_t id, uint16_t* out_moves, uint32_t* out_visits, float* out_priors,
+                      float* out_rewards, int32_t cap, int32_t* out_count);
+int32_t mcts_root(tak_engine_t* e, int32_t id, uint32_t* out_visits, uint32_t* out_virtual, float* out_reward);
+int32_t mcts_pick_move(tak_engine_t* e, const int32_t* ids, int32_t n, uint16_t* out_moves);
+int32_t mcts_play(tak_engine_t* e, const int32_t* ids, const uint16_t* moves, int32_t n);
+int32_t mcts_apply_dirichlet(tak_engine_t* e, const int32_t* ids, int32_t n, float alpha, float ratio,
+                             uint64_t seed);
+
+/* ---- train::self_play_parallel ----------------------------------------------------------------------
+ * One call plays `moves` lock-step plies for every game of the engine (games that end are recorded and
+ * restarted, as self_play.rs:148-152,236-240 does).  Replay records are fixed-size and device-resident until
+ * drained; selfplay_drain copies them out (this is the payload bench.py / the trainer all-gathers). */
+typedef struct tak_selfplay_config {
+    int32_t rollouts;        /* ROLLOUTS (self_play.rs:12); 800 for the headline metric */
+    int32_t half_komi;       /* Game::with_komi(2) => 4 */
+    int32_t instant_win;     /* 1 = "play winning moves if there are any" shortcut (self_play.rs:119-171) */
+    int32_t exploit_ply;     /* EXPLOIT_PLIES (40); plies below it sample ~ visits, others argmax */
+    int32_t noise_ply;       /* NOISE_PLIES (80); 0 disables Dirichlet noise (parity runs) */
+    float noise_alpha;       /* 0.2 */
+    float noise_ratio;       /* 0.3 */
+    uint64_t seed;           /* counter-based RNG key (openings, sampling, noise) */
+    int32_t max_plies;       /* safety cap per game (0 => none) */
+    int32_t game_id_base;    /* global id of local game 0 (rank sharding: openings/seeds use global ids) */
+    int32_t reserved[4];
+} tak_selfplay_config_t;
+
+typedef struct tak_selfplay_stats {
+    uint64_t plies_played;       /* searched plies (excludes the two forced opening plies) */
+    uint64_t games_completed;
+    uint64_t rollouts;           /* virtual rollouts started */
+    uint64_t evals;              /* leaves sent to the network */
+    uint64_t kernel_launches;
+    uint64_t records;            /* replay records produced */
+    double device_ms;            /* CUDA-event time of the whole call */
+    double net_ms;               /* CUDA-event time spent in network kernels */
+} tak_selfplay_stats_t;
+
+/* fixed-size replay record == alpha_tak::Example (example.rs:28-33) */
+#define TAK_REPLAY_MAX_CHILDREN 256
+typedef struct tak_replay_record {
+    int32_t game_id;            /* global game id */
+    int32_t game_serial;        /* how many games this slot had completed before */
+    float result;               /* +1 / 0 / -1 from the mover's perspective; NaN while the game is unfinished */
+    int32_t n_children;
+    tak_state_t state;
+    uint16_t moves[TAK_REPLAY_MAX_CHILDREN];
+    uint32_t visits[TAK_REPLAY_MAX_CHILDREN];
+} tak_replay_record_t;
+
+int32_t selfplay_begin(tak_engine_t* e, const tak_selfplay_config_t* cfg);
+int32_t selfplay_step(tak_engine_t* e, int32_t moves, tak_selfplay_stats_t* out_stats);
+int32_t selfplay_drain(tak_engine_t* e, tak_replay_record_t* out, int32_t cap, int32_t* out_count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TAKNATIVE_H */
