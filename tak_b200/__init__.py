@@ -1,0 +1,14 @@
+"""tak_b200: B200-native AlphaTak self-play engine (hot path of ViliamVadocz/tak) behind a C ABI.
+
+The package is a thin host-side mirror of the reference interface over libtaknative.so (CUDA, sm_100a).
+Importing it never touches oracle/ and never falls back to a CPU path: without the built library or a
+CUDA device every compute call raises.
+"""
+from ._lib import LIB_PATH, ReplayRecord, SelfplayStats, TakNativeError, TakState, load  # noqa: F401
+from .engine import (  # noqa: F401
+    RESULT_BLACK, RESULT_DRAW, RESULT_FLAG, RESULT_ONGOING, RESULT_WHITE, Engine, Game, format_move,
+    input_channels, move_index, parse_move, policy_size, state_init, tps_format, tps_parse,
+)
+
+__all__ = ["Engine", "Game", "TakState", "TakNativeError", "parse_move", "format_move", "move_index",
+           "policy_size", "input_channels", "state_init", "tps_format", "tps_parse", "load", "LIB_PATH"]

@@ -77,7 +77,7 @@ __device__ __forceinline__ bool conv_slot_valid(int slot, int pitch, int n_board
     return rel >= 0 && board < n_boards && y >= 1 && x < pitch - 1;
 }
 
-__global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_tc_kernel(const ConvParams p) {
+static __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_tc_kernel(const ConvParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* a_buf = smem;                                        // 2 x CONV_A_BYTES
     uint8_t* w_buf = smem + 2 * CONV_A_BYTES;                     // CONV_W_STAGES x 16 KiB

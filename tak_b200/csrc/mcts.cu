@@ -1,0 +1,436 @@
+// alpha_tak::Node part of the C ABI: batched device MCTS (one tree per game).
+// Reference: alpha-tak/src/search/{node,mcts,play,noise}.rs; schedule of train/src/self_play.rs:181-210.
+#include "mcts.hpp"
+
+#include <cmath>
+
+#include "game_kernels.cuh"
+#include "net.hpp"
+
+namespace tb {
+
+MctsView MctsState::view() const {
+    MctsView v{};
+    v.stat = stat.as<uint4>();
+    v.link = link.as<uint2>();
+    v.half = half.as<int>();
+    v.top = top.as<uint32_t>();
+    v.pend_cnt = pend_cnt.as<int>();
+    v.pend_leaf = pend_leaf.as<uint32_t>();
+    v.pend_plen = pend_plen.as<int>();
+    v.pend_path = pend_path.as<uint32_t>();
+    v.leaf_states = leaf_states.as<uint8_t>();
+    v.explo = explo.as<float>();
+    v.move_table = move_table.as<uint16_t>();
+    v.err = err.as<int>();
+    v.counters = counters.as<unsigned long long>();
+    v.cap = cap;
+    v.kcap = kcap;
+    return v;
+}
+
+static inline int warp_blocks(int warps) { return (warps + GAME_WARPS_PER_BLOCK - 1) / GAME_WARPS_PER_BLOCK; }
+
+int mcts_ensure(tak_engine* e, int k) {
+    const int G = e->max_games;
+    if (!e->mcts) {
+        MctsState* m = new MctsState();
+        e->mcts = m;
+        m->cap = e->nodes_per_game > 0 ? e->nodes_per_game : (1 << 17);
+        TB_CHECK(m->cap >= 64 && m->cap <= (1 << 24), TAK_ERR_BAD_ARG, "nodes_per_game %d out of range", m->cap);
+        const size_t nodes = size_t(G) * 2 * m->cap;
+        TB_CUDA(m->stat.ensure(nodes * 16));
+        TB_CUDA(m->link.ensure(nodes * 8));
+        TB_CUDA(m->half.ensure(size_t(G) * 4));
+        TB_CUDA(m->top.ensure(size_t(G) * 4));
+        TB_CUDA(m->pend_cnt.ensure(size_t(G) * 4));
+        TB_CUDA(m->eval_count.ensure(16));
+        TB_CUDA(m->err.ensure(16));
+        TB_CUDA(m->counters.ensure(64));
+        TB_CUDA(cudaMemsetAsync(m->half.p, 0, size_t(G) * 4, e->stream));
+        TB_CUDA(cudaMemsetAsync(m->pend_cnt.p, 0, size_t(G) * 4, e->stream));
+        TB_CUDA(cudaMemsetAsync(m->err.p, 0, 16, e->stream));
+        TB_CUDA(cudaMemsetAsync(m->counters.p, 0, 64, e->stream));
+        TB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&m->h_pinned), 64));
+        // exploration_rate(n) = ln((1 + n + 500) / 500) + 4 in f32 (mcts.rs:7-12), tabulated with the host libm
+        std::vector<float> tab(MCTS_EXPLO_TABLE);
+        for (int i = 0; i < MCTS_EXPLO_TABLE; ++i) {
+            volatile float nf = float(i);
+            volatile float a = 1.0f + nf;
+            volatile float b = a + 500.0f;
+            volatile float c = b / 500.0f;
+            volatile float d = logf(c);
+            tab[i] = d + 4.0f;
+        }
+        TB_CUDA(m->explo.ensure(tab.size() * 4));
+        TB_CUDA(cudaMemcpyAsync(m->explo.p, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice, e->stream));
+        const std::vector<uint16_t>& mt = host_move_index_table(e->n);
+        TB_CUDA(m->move_table.ensure(mt.size() * 2));
+        TB_CUDA(cudaMemcpyAsync(m->move_table.p, mt.data(), mt.size() * 2, cudaMemcpyHostToDevice, e->stream));
+        TB_CUDA(cudaStreamSynchronize(e->stream));
+        m->kcap = 0;
+        if (int r = mcts_ensure(e, k)) return r;
+        return mcts_launch_tree_reset(e, nullptr, G);
+    }
+    MctsState& m = *e->mcts;
+    if (k > m.kcap) {
+        TB_CHECK(!m.queued, TAK_ERR_BAD_ARG, "cannot grow the pending queue (k=%d) while leaves are queued", k);
+        const size_t slots = size_t(G) * k;
+        TB_CUDA(m.pend_leaf.ensure(slots * 4));
+        TB_CUDA(m.pend_plen.ensure(slots * 4));
+        TB_CUDA(m.pend_path.ensure(slots * MCTS_MAX_DEPTH * 4));
+        TB_CUDA(m.leaf_states.ensure(slots * e->state_bytes));
+        TB_CUDA(m.eval_index.ensure(slots * 4));
+        TB_CUDA(m.eval_slot.ensure(slots * 4));
+        m.kcap = k;
+    }
+    return TAK_OK;
+}
+
+int mcts_launch_tree_reset(tak_engine* e, const int* d_ids, int n) {
+    k_mcts_tree_reset<<<(n + 255) / 256, 256, 0, e->stream>>>(e->mcts->view(), d_ids, n);
+    e->launches++;
+    TB_CUDA(cudaGetLastError());
+    return TAK_OK;
+}
+
+int mcts_launch_rollout(tak_engine* e, const int* d_ids, int n, int k) {
+    MctsState& m = *e->mcts;
+    TB_DISPATCH_N(e->n, (k_mcts_rollout<N_><<<warp_blocks(n), GAME_THREADS, 0, e->stream>>>(
+                            m.view(), e->states.as<uint8_t>(), d_ids, n, k)));
+    e->launches++;
+    m.queued = true;
+    TB_CUDA(cudaGetLastError());
+    return TAK_OK;
+}
+
+int mcts_launch_compact(tak_engine* e) {
+    MctsState& m = *e->mcts;
+    k_mcts_compact<<<1, 1024, 0, e->stream>>>(m.pend_cnt.as<int>(), e->max_games, m.kcap, m.eval_index.as<int>(),
+                                              m.eval_slot.as<int>(), m.eval_count.as<int>());
+    e->launches++;
+    TB_CUDA(cudaGetLastError());
+    return TAK_OK;
+}
+
+int mcts_read_eval_count(tak_engine* e, int* out) {
+    MctsState& m = *e->mcts;
+    TB_CUDA(cudaMemcpyAsync(m.h_pinned, m.eval_count.p, 4, cudaMemcpyDeviceToHost, e->stream));
+    TB_CUDA(cudaStreamSynchronize(e->stream));
+    *out = m.h_pinned[0];
+    return TAK_OK;
+}
+
+int mcts_launch_backup(tak_engine* e, const PriorSource& ps) {
+    MctsState& m = *e->mcts;
+    TB_DISPATCH_N(e->n, (k_mcts_backup<N_><<<warp_blocks(e->max_games), GAME_THREADS, 0, e->stream>>>(
+                            m.view(), m.eval_slot.as<int>(), e->max_games, ps)));
+    e->launches++;
+    m.queued = false;
+    TB_CUDA(cudaGetLastError());
+    return TAK_OK;
+}
+
+int mcts_eval_and_backup(tak_engine* e) {
+    TB_CHECK(e->net, TAK_ERR_NO_NETWORK, "no network: call net_create first");
+    MctsState& m = *e->mcts;
+    NetState& ns = *e->net;
+    if (int r = mcts_launch_compact(e)) return r;
+    PriorSource ps{};
+    ps.arch = ns.arch;
+    ps.psz = ns.policy_out;
+    if (ns.arch != 0) {
+        int count = 0;
+        if (int r = mcts_read_eval_count(e, &count)) return r;
+        if (count > 0) {
+            // leaves are evaluated in chunks of max_batch; each chunk is backed up before the next one only when a
+            // single chunk suffices -- otherwise all chunks are evaluated first (queue order is preserved either way
+            // because the backup kernel walks each game's queue in order and outputs are indexed by compact slot).
+            TB_CHECK(count <= e->max_batch, TAK_ERR_CAPACITY, "%d queued leaves exceed max_batch %d", count,
+                     e->max_batch);
+            if (int r = net_forward(e, m.leaf_states.as<uint8_t>(), m.eval_index.as<int>(), count, nullptr)) return r;
+        }
+        ps.logits = ns.logits.as<float>();
+        ps.stats = ns.stats.as<float2>();
+        ps.values = ns.values.as<float>();
+        ps.S = ns.cap_S;
+    }
+    return mcts_launch_backup(e, ps);
+}
+
+int mcts_check_errors(tak_engine* e) {
+    MctsState& m = *e->mcts;
+    TB_CUDA(cudaMemcpyAsync(m.h_pinned + 1, m.err.p, 4, cudaMemcpyDeviceToHost, e->stream));
+    TB_CUDA(cudaStreamSynchronize(e->stream));
+    const int flags = m.h_pinned[1];
+    if (!flags) return TAK_OK;
+    TB_CUDA(cudaMemsetAsync(m.err.p, 0, 4, e->stream));
+    if (flags & MERR_POOL_FULL) {
+        set_error("MCTS node pool exhausted (nodes_per_game = %d): raise tak_engine_config.nodes_per_game", m.cap);
+        return TAK_ERR_CAPACITY;
+    }
+    if (flags & MERR_PENDING_FULL) {
+        set_error("more than %d leaves queued for one game", m.kcap);
+        return TAK_ERR_CAPACITY;
+    }
+    if (flags & MERR_DEPTH) {
+        set_error("search path deeper than %d plies", MCTS_MAX_DEPTH);
+        return TAK_ERR_CAPACITY;
+    }
+    if (flags & MERR_VISITS) {
+        set_error("visit count beyond the exploration table (%d)", MCTS_EXPLO_TABLE);
+        return TAK_ERR_CAPACITY;
+    }
+    if (flags & MERR_NAN) {
+        set_error("tried comparing nan (NaN upper confidence bound) or select on a node without children");
+        return TAK_ERR_BAD_ARG;
+    }
+    set_error("tried to play an invalid move / move without a policy index / noise before a visit");
+    return TAK_ERR_INVALID_MOVE;
+}
+
+int mcts_launch_pick(tak_engine* e, const int* d_ids, int n, const uint8_t* d_sample, uint64_t seed,
+                     const int* d_tags, uint16_t* d_out) {
+    k_mcts_pick<<<warp_blocks(n), GAME_THREADS, 0, e->stream>>>(e->mcts->view(), d_ids, n, d_sample, seed, d_tags,
+                                                               d_out);
+    e->launches++;
+    TB_CUDA(cudaGetLastError());
+    return TAK_OK;
+}
+int mcts_launch_reroot(tak_engine* e, const int* d_ids, const uint16_t* d_moves, int n) {
+    k_mcts_reroot<<<warp_blocks(n), GAME_THREADS, 0, e->stream>>>(e->mcts->view(), d_ids, d_moves, n);
+    e->launches++;
+    TB_CUDA(cudaGetLastError());
+    return TAK_OK;
+}
+int mcts_launch_dirichlet(tak_engine* e, const int* d_ids, int n, const uint8_t* d_enable, float alpha, float ratio,
+                          uint64_t seed, const int* d_tags) {
+    k_mcts_dirichlet<<<warp_blocks(n), GAME_THREADS, 0, e->stream>>>(e->mcts->view(), d_ids, n, d_enable, alpha,
+                                                                    ratio, seed, d_tags);
+    e->launches++;
+    TB_CUDA(cudaGetLastError());
+    return TAK_OK;
+}
+
+void mcts_destroy(tak_engine* e) {
+    if (!e->mcts) return;
+    MctsState& m = *e->mcts;
+    for (DevBuf* b : {&m.stat, &m.link, &m.half, &m.top, &m.pend_cnt, &m.pend_leaf, &m.pend_plen, &m.pend_path,
+                      &m.leaf_states, &m.eval_index, &m.eval_slot, &m.eval_count, &m.explo, &m.move_table, &m.err,
+                      &m.counters, &m.d_ids, &m.d_moves, &m.stage_policy, &m.stage_value, &m.stage_stat,
+                      &m.stage_link, &m.stage_count})
+        b->release();
+    if (m.h_pinned) cudaFreeHost(m.h_pinned);
+    delete e->mcts;
+    e->mcts = nullptr;
+}
+
+static int upload_ids(tak_engine* e, const int32_t* ids, int n, const int** d_ids) {
+    MctsState& m = *e->mcts;
+    for (int i = 0; i < n; ++i)
+        TB_CHECK(ids[i] >= 0 && ids[i] < e->max_games, TAK_ERR_BAD_ARG, "game id %d out of range", ids[i]);
+    TB_CUDA(m.d_ids.ensure(size_t(n) * 4 + 4));
+    TB_CUDA(cudaMemcpyAsync(m.d_ids.p, ids, size_t(n) * 4, cudaMemcpyHostToDevice, e->stream));
+    *d_ids = m.d_ids.as<int>();
+    return TAK_OK;
+}
+
+}  // namespace tb
+
+using namespace tb;
+
+extern "C" {
+
+int32_t mcts_tree_reset(tak_engine_t* e, const int32_t* ids, int32_t n) {
+    TB_CHECK(e && ids && n >= 0, TAK_ERR_BAD_ARG, "mcts_tree_reset: bad argument");
+    TB_CUDA(cudaSetDevice(e->device));
+    if (int r = mcts_ensure(e, 1)) return r;
+    if (n == 0) return TAK_OK;
+    const int* d_ids = nullptr;
+    if (int r = upload_ids(e, ids, n, &d_ids)) return r;
+    return mcts_launch_tree_reset(e, d_ids, n);
+}
+
+int32_t mcts_virtual_rollout(tak_engine_t* e, const int32_t* ids, int32_t n, int32_t k) {
+    TB_CHECK(e && ids && n >= 0 && k >= 1 && k <= 4096, TAK_ERR_BAD_ARG, "mcts_virtual_rollout: bad argument");
+    TB_CUDA(cudaSetDevice(e->device));
+    if (int r = mcts_ensure(e, k)) return r;
+    if (n == 0) return TAK_OK;
+    const int* d_ids = nullptr;
+    if (int r = upload_ids(e, ids, n, &d_ids)) return r;
+    if (int r = mcts_launch_rollout(e, d_ids, n, k)) return r;
+    return mcts_check_errors(e);
+}
+
+int32_t mcts_pending(tak_engine_t* e, int32_t* out_count, int32_t* out_game_ids, tak_state_t* out_states,
+                     int32_t cap) {
+    TB_CHECK(e && out_count, TAK_ERR_BAD_ARG, "mcts_pending: bad argument");
+    TB_CUDA(cudaSetDevice(e->device));
+    if (int r = mcts_ensure(e, 1)) return r;
+    MctsState& m = *e->mcts;
+    if (int r = mcts_launch_compact(e)) return r;
+    int count = 0;
+    if (int r = mcts_read_eval_count(e, &count)) return r;
+    *out_count = count;
+    if (!out_game_ids && !out_states) return TAK_OK;
+    TB_CHECK(count <= cap, TAK_ERR_CAPACITY, "%d queued leaves, caller buffer holds %d", count, cap);
+    std::vector<int> index(count);
+    TB_CUDA(cudaMemcpyAsync(index.data(), m.eval_index.p, size_t(count) * 4, cudaMemcpyDeviceToHost, e->stream));
+    TB_CUDA(cudaStreamSynchronize(e->stream));
+    std::vector<uint8_t> rec(e->state_bytes);
+    for (int i = 0; i < count; ++i) {
+        if (out_game_ids) out_game_ids[i] = index[i] / m.kcap;
+        if (out_states) {
+            TB_CUDA(cudaMemcpyAsync(rec.data(), m.leaf_states.as<uint8_t>() + size_t(index[i]) * e->state_bytes,
+                                    e->state_bytes, cudaMemcpyDeviceToHost, e->stream));
+            TB_CUDA(cudaStreamSynchronize(e->stream));
+            unpack_state(e->n, rec.data(), out_states[i]);
+        }
+    }
+    return TAK_OK;
+}
+
+int32_t mcts_devirtualize(tak_engine_t* e) {
+    TB_CHECK(e, TAK_ERR_BAD_ARG, "null engine");
+    TB_CUDA(cudaSetDevice(e->device));
+    if (int r = mcts_ensure(e, 1)) return r;
+    if (int r = mcts_eval_and_backup(e)) return r;
+    return mcts_check_errors(e);
+}
+
+int32_t mcts_devirtualize_with(tak_engine_t* e, const float* policy, const float* value, int32_t count) {
+    TB_CHECK(e && policy && value && count >= 0, TAK_ERR_BAD_ARG, "mcts_devirtualize_with: bad argument");
+    TB_CUDA(cudaSetDevice(e->device));
+    if (int r = mcts_ensure(e, 1)) return r;
+    MctsState& m = *e->mcts;
+    if (int r = mcts_launch_compact(e)) return r;
+    int queued = 0;
+    if (int r = mcts_read_eval_count(e, &queued)) return r;
+    TB_CHECK(queued == count, TAK_ERR_BAD_ARG, "%d leaves are queued but %d network outputs were supplied", queued,
+             count);
+    const int psz = host_policy_size(e->n);
+    TB_CUDA(m.stage_policy.ensure(size_t(count) * psz * 4 + 4));
+    TB_CUDA(m.stage_value.ensure(size_t(count) * 4 + 4));
+    TB_CUDA(cudaMemcpyAsync(m.stage_policy.p, policy, size_t(count) * psz * 4, cudaMemcpyHostToDevice, e->stream));
+    TB_CUDA(cudaMemcpyAsync(m.stage_value.p, value, size_t(count) * 4, cudaMemcpyHostToDevice, e->stream));
+    PriorSource ps{};
+    ps.arch = -1;
+    ps.logits = m.stage_policy.as<float>();
+    ps.values = m.stage_value.as<float>();
+    ps.psz = psz;
+    if (int r = mcts_launch_backup(e, ps)) return r;
+    return mcts_check_errors(e);
+}
+
+int32_t mcts_rollouts(tak_engine_t* e, const int32_t* ids, int32_t n, int32_t n_rollouts) {
+    TB_CHECK(e && ids && n >= 0 && n_rollouts >= 0, TAK_ERR_BAD_ARG, "mcts_rollouts: bad argument");
+    TB_CHECK(e->net, TAK_ERR_NO_NETWORK, "no network: call net_create first");
+    TB_CUDA(cudaSetDevice(e->device));
+    if (int r = mcts_ensure(e, 1)) return r;
+    if (n == 0) return TAK_OK;
+    const int* d_ids = nullptr;
+    if (int r = upload_ids(e, ids, n, &d_ids)) return r;
+    for (int i = 0; i < n_rollouts; ++i) {
+        if (int r = mcts_launch_rollout(e, d_ids, n, 1)) return r;
+        if (int r = mcts_eval_and_backup(e)) return r;
+    }
+    return mcts_check_errors(e);
+}
+
+static int export_root(tak_engine_t* e, int32_t id, std::vector<uint4>& st, std::vector<uint2>& lk, int* count) {
+    TB_CHECK(id >= 0 && id < e->max_games, TAK_ERR_BAD_ARG, "game id %d out of range", id);
+    if (int r = mcts_ensure(e, 1)) return r;
+    MctsState& m = *e->mcts;
+    const int cap = 4097;
+    TB_CUDA(m.stage_stat.ensure(size_t(cap) * 16));
+    TB_CUDA(m.stage_link.ensure(size_t(cap) * 8));
+    TB_CUDA(m.stage_count.ensure(16));
+    k_mcts_export_root<<<1, 256, 0, e->stream>>>(m.view(), id, m.stage_stat.as<uint4>(), m.stage_link.as<uint2>(), cap,
+                                                 m.stage_count.as<int>());
+    e->launches++;
+    TB_CUDA(cudaGetLastError());
+    TB_CUDA(cudaMemcpyAsync(m.h_pinned + 2, m.stage_count.p, 4, cudaMemcpyDeviceToHost, e->stream));
+    TB_CUDA(cudaStreamSynchronize(e->stream));
+    *count = m.h_pinned[2];
+    TB_CHECK(*count + 1 <= cap, TAK_ERR_CAPACITY, "root has %d children", *count);
+    st.resize(size_t(*count) + 1);
+    lk.resize(size_t(*count) + 1);
+    TB_CUDA(cudaMemcpyAsync(st.data(), m.stage_stat.p, st.size() * 16, cudaMemcpyDeviceToHost, e->stream));
+    TB_CUDA(cudaMemcpyAsync(lk.data(), m.stage_link.p, lk.size() * 8, cudaMemcpyDeviceToHost, e->stream));
+    TB_CUDA(cudaStreamSynchronize(e->stream));
+    return TAK_OK;
+}
+
+int32_t mcts_children(tak_engine_t* e, int32_t id, uint16_t* out_moves, uint32_t* out_visits, float* out_priors,
+                      float* out_rewards, int32_t cap, int32_t* out_count) {
+    TB_CHECK(e && out_count, TAK_ERR_BAD_ARG, "mcts_children: bad argument");
+    TB_CUDA(cudaSetDevice(e->device));
+    std::vector<uint4> st;
+    std::vector<uint2> lk;
+    int count = 0;
+    if (int r = export_root(e, id, st, lk, &count)) return r;
+    *out_count = count;
+    TB_CHECK(count <= cap, TAK_ERR_CAPACITY, "root has %d children, caller buffer holds %d", count, cap);
+    for (int i = 0; i < count; ++i) {
+        if (out_moves) out_moves[i] = uint16_t(lk[size_t(i) + 1].y & 0xFFFFu);
+        if (out_visits) out_visits[i] = st[size_t(i) + 1].z;
+        if (out_priors) std::memcpy(&out_priors[i], &st[size_t(i) + 1].x, 4);
+        if (out_rewards) std::memcpy(&out_rewards[i], &st[size_t(i) + 1].y, 4);
+    }
+    return TAK_OK;
+}
+
+int32_t mcts_root(tak_engine_t* e, int32_t id, uint32_t* out_visits, uint32_t* out_virtual, float* out_reward) {
+    TB_CHECK(e, TAK_ERR_BAD_ARG, "null engine");
+    TB_CUDA(cudaSetDevice(e->device));
+    std::vector<uint4> st;
+    std::vector<uint2> lk;
+    int count = 0;
+    if (int r = export_root(e, id, st, lk, &count)) return r;
+    if (out_visits) *out_visits = st[0].z;
+    if (out_virtual) *out_virtual = st[0].w;
+    if (out_reward) std::memcpy(out_reward, &st[0].y, 4);
+    return TAK_OK;
+}
+
+int32_t mcts_pick_move(tak_engine_t* e, const int32_t* ids, int32_t n, uint16_t* out_moves) {
+    TB_CHECK(e && ids && out_moves && n >= 0, TAK_ERR_BAD_ARG, "mcts_pick_move: bad argument");
+    TB_CUDA(cudaSetDevice(e->device));
+    if (int r = mcts_ensure(e, 1)) return r;
+    if (n == 0) return TAK_OK;
+    MctsState& m = *e->mcts;
+    const int* d_ids = nullptr;
+    if (int r = upload_ids(e, ids, n, &d_ids)) return r;
+    TB_CUDA(m.d_moves.ensure(size_t(n) * 2 + 2));
+    if (int r = mcts_launch_pick(e, d_ids, n, nullptr, 0, nullptr, m.d_moves.as<uint16_t>())) return r;
+    TB_CUDA(cudaMemcpyAsync(out_moves, m.d_moves.p, size_t(n) * 2, cudaMemcpyDeviceToHost, e->stream));
+    return mcts_check_errors(e);
+}
+
+int32_t mcts_play(tak_engine_t* e, const int32_t* ids, const uint16_t* moves, int32_t n) {
+    TB_CHECK(e && ids && moves && n >= 0, TAK_ERR_BAD_ARG, "mcts_play: bad argument");
+    TB_CUDA(cudaSetDevice(e->device));
+    if (int r = mcts_ensure(e, 1)) return r;
+    if (n == 0) return TAK_OK;
+    MctsState& m = *e->mcts;
+    TB_CHECK(!m.queued, TAK_ERR_BAD_ARG, "mcts_play while leaves are queued: call mcts_devirtualize first");
+    const int* d_ids = nullptr;
+    if (int r = upload_ids(e, ids, n, &d_ids)) return r;
+    TB_CUDA(m.d_moves.ensure(size_t(n) * 2 + 2));
+    TB_CUDA(cudaMemcpyAsync(m.d_moves.p, moves, size_t(n) * 2, cudaMemcpyHostToDevice, e->stream));
+    if (int r = mcts_launch_reroot(e, d_ids, m.d_moves.as<uint16_t>(), n)) return r;
+    return mcts_check_errors(e);
+}
+
+int32_t mcts_apply_dirichlet(tak_engine_t* e, const int32_t* ids, int32_t n, float alpha, float ratio, uint64_t seed) {
+    TB_CHECK(e && ids && n >= 0 && alpha > 0.f, TAK_ERR_BAD_ARG, "mcts_apply_dirichlet: bad argument");
+    TB_CUDA(cudaSetDevice(e->device));
+    if (int r = mcts_ensure(e, 1)) return r;
+    if (n == 0) return TAK_OK;
+    const int* d_ids = nullptr;
+    if (int r = upload_ids(e, ids, n, &d_ids)) return r;
+    if (int r = mcts_launch_dirichlet(e, d_ids, n, nullptr, alpha, ratio, seed, nullptr)) return r;
+    return mcts_check_errors(e);
+}
+
+}  // extern "C"

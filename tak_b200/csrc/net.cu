@@ -1,0 +1,369 @@
+// alpha_tak::Network for the engine: Net5 / Net6 forward (policy_eval / forward_mcts) on tcgen05 tensor cores.
+// Reference: alpha-tak/src/model/net6.rs:29-138, net5.rs:29-130, res_block.rs:13-23, network.rs:26-34.
+// DummyNet (alpha-tak/src/search/tests.rs:6-35) is arch 0.
+#include "net.hpp"
+
+#include <cmath>
+
+#include "net_kernels.cuh"
+
+namespace tb {
+
+static constexpr float BN_EPS = 1e-5f;  // tch nn::BatchNormConfig default
+
+int64_t net_blob_elems(const NetState& ns) {
+    const int64_t cin = ns.c_in, nsq = int64_t(ns.n) * ns.n;
+    int64_t total = 128 * cin * 9 + 128 + 4 * 128;
+    total += int64_t(ns.blocks) * (2 * (128 * 128 * 9 + 128) + 8 * 128);
+    if (ns.arch == 6) total += int64_t(ns.policy_ch) * 128 * 9 + ns.policy_ch;
+    else total += int64_t(ns.policy_out) * 128 * nsq + ns.policy_out;
+    total += 128 * nsq + 1;
+    return total;
+}
+
+// fold BN(eval) into conv weight/bias and pack for conv_tc: [stage = tap*2+half][kchunk 8][c_out 128][8 c_in]
+static void pack_conv(const float* w /*[co][ci][3][3]*/, const float* b, const float* bn /*gamma,beta,mean,var or null*/,
+                      int c_out, int c_in, int co_base, std::vector<__nv_bfloat16>& packed, std::vector<float>& bias) {
+    packed.assign(size_t(18) * 8 * 128 * 8, __float2bfloat16(0.f));
+    bias.assign(128, 0.f);
+    for (int col = 0; col < 128; ++col) {
+        const int co = co_base + col;
+        if (co >= c_out) continue;
+        double scale = 1.0, shift = 0.0;
+        if (bn) {
+            const double gamma = bn[co], beta = bn[c_out + co], mean = bn[2 * c_out + co], var = bn[3 * c_out + co];
+            scale = gamma / std::sqrt(var + double(BN_EPS));
+            shift = beta - mean * scale;
+        }
+        bias[col] = float(double(b[co]) * scale + shift);
+        for (int ci = 0; ci < c_in; ++ci)
+            for (int tap = 0; tap < 9; ++tap) {
+                const float v = float(double(w[(size_t(co) * c_in + ci) * 9 + tap]) * scale);
+                const int half = ci >> 6, kc = (ci & 63) >> 3, j = ci & 7;
+                packed[(((size_t(tap * 2 + half) * 8 + kc) * 128) + col) * 8 + j] = __float2bfloat16(v);
+            }
+    }
+}
+
+static int upload_layer(tak_engine* e, ConvLayer& L, const std::vector<__nv_bfloat16>& packed,
+                        const std::vector<float>& bias) {
+    TB_CUDA(L.w.ensure(packed.size() * 2));
+    TB_CUDA(L.bias.ensure(bias.size() * 4));
+    TB_CUDA(cudaMemcpyAsync(L.w.p, packed.data(), packed.size() * 2, cudaMemcpyHostToDevice, e->stream));
+    TB_CUDA(cudaMemcpyAsync(L.bias.p, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice, e->stream));
+    TB_CUDA(cudaStreamSynchronize(e->stream));
+    return TAK_OK;
+}
+
+int net_load_blob(tak_engine* e, const float* blob, int64_t elems) {
+    NetState& ns = *e->net;
+    TB_CHECK(ns.arch != 0, TAK_ERR_BAD_ARG, "the DummyNet has no weights");
+    TB_CHECK(elems == net_blob_elems(ns), TAK_ERR_BAD_ARG, "weight blob has %lld elements, architecture needs %lld",
+             (long long)elems, (long long)net_blob_elems(ns));
+    const int nsq = ns.n * ns.n;
+    const float* p = blob;
+    std::vector<__nv_bfloat16> packed;
+    std::vector<float> bias;
+    // initial conv + BN (net6.rs:39-40)
+    {
+        const float* w = p; p += size_t(128) * ns.c_in * 9;
+        const float* b = p; p += 128;
+        const float* bn = p; p += 4 * 128;
+        pack_conv(w, b, bn, 128, ns.c_in, 0, packed, bias);
+        if (int r = upload_layer(e, ns.layers[0], packed, bias)) return r;
+    }
+    // residual blocks: conv1, conv2, bn1, bn2 in creation order (net6.rs:43-54)
+    for (int blk = 0; blk < ns.blocks; ++blk) {
+        const float* w1 = p; p += size_t(128) * 128 * 9;
+        const float* b1 = p; p += 128;
+        const float* w2 = p; p += size_t(128) * 128 * 9;
+        const float* b2 = p; p += 128;
+        const float* bn1 = p; p += 4 * 128;
+        const float* bn2 = p; p += 4 * 128;
+        pack_conv(w1, b1, bn1, 128, 128, 0, packed, bias);
+        if (int r = upload_layer(e, ns.layers[1 + 2 * blk], packed, bias)) return r;
+        pack_conv(w2, b2, bn2, 128, 128, 0, packed, bias);
+        if (int r = upload_layer(e, ns.layers[2 + 2 * blk], packed, bias)) return r;
+    }
+    if (ns.arch == 6) {
+        const float* w = p; p += size_t(ns.policy_ch) * 128 * 9;
+        const float* b = p; p += ns.policy_ch;
+        for (int grp = 0; grp < ns.policy_groups; ++grp) {
+            pack_conv(w, b, nullptr, ns.policy_ch, 128, grp * 128, packed, bias);
+            if (int r = upload_layer(e, ns.policy_layers[grp], packed, bias)) return r;
+        }
+    } else {
+        // FC policy: W[j][k] -> bf16 Wt[k][j]
+        const int K = 128 * nsq, J = ns.policy_out;
+        const float* w = p; p += size_t(J) * K;
+        const float* b = p; p += J;
+        std::vector<__nv_bfloat16> wt(size_t(K) * J);
+        for (int j = 0; j < J; ++j)
+            for (int k = 0; k < K; ++k) wt[size_t(k) * J + j] = __float2bfloat16(w[size_t(j) * K + k]);
+        TB_CUDA(ns.fc_policy_w.ensure(wt.size() * 2));
+        TB_CUDA(ns.fc_policy_b.ensure(size_t(J) * 4));
+        TB_CUDA(cudaMemcpyAsync(ns.fc_policy_w.p, wt.data(), wt.size() * 2, cudaMemcpyHostToDevice, e->stream));
+        TB_CUDA(cudaMemcpyAsync(ns.fc_policy_b.p, b, size_t(J) * 4, cudaMemcpyHostToDevice, e->stream));
+        TB_CUDA(cudaStreamSynchronize(e->stream));
+    }
+    {
+        const float* w = p; p += size_t(128) * nsq;
+        ns.value_bias = *p; p += 1;
+        TB_CUDA(ns.value_w.ensure(size_t(128) * nsq * 4));
+        TB_CUDA(cudaMemcpyAsync(ns.value_w.p, w, size_t(128) * nsq * 4, cudaMemcpyHostToDevice, e->stream));
+        TB_CUDA(cudaStreamSynchronize(e->stream));
+    }
+    TB_CHECK(p - blob == elems, TAK_ERR_BAD_ARG, "internal: blob walk mismatch");
+    ns.loaded = true;
+    return TAK_OK;
+}
+
+int net_ensure_capacity(tak_engine* e, int boards) {
+    NetState& ns = *e->net;
+    if (boards <= ns.cap_boards) return TAK_OK;
+    const int P = ns.n + 1;
+    const int tiles = (boards * P * P + P + 1 + CONV_TILE_M - 1) / CONV_TILE_M;
+    const int S = CONV_GUARD + tiles * CONV_TILE_M + CONV_GUARD;
+    for (int i = 0; i < 3; ++i) {
+        TB_CUDA(ns.act[i].ensure(size_t(S) * 256));
+        TB_CUDA(cudaMemsetAsync(ns.act[i].p, 0, size_t(S) * 256, e->stream));
+    }
+    if (ns.arch == 6) TB_CUDA(ns.logits.ensure(size_t(ns.policy_groups) * 128 * S * 4));
+    else if (ns.arch == 5) TB_CUDA(ns.logits.ensure(size_t(boards) * ns.policy_out * 4));
+    TB_CUDA(ns.stats.ensure(size_t(boards) * 8));
+    TB_CUDA(ns.values.ensure(size_t(boards) * 4));
+    ns.cap_boards = boards;
+    ns.cap_S = S;
+    return TAK_OK;
+}
+
+template <int N>
+static int forward_t(tak_engine* e, const uint8_t* d_states, const int* d_index, int boards, float* d_policy_out) {
+    NetState& ns = *e->net;
+    if (int r = net_ensure_capacity(e, boards)) return r;
+    const int P = N + 1;
+    const int tiles = (boards * P * P + P + 1 + CONV_TILE_M - 1) / CONV_TILE_M;
+    const int S = ns.cap_S;  // plane stride is fixed by the allocation
+    __nv_bfloat16* x = ns.act[0].as<__nv_bfloat16>();
+    __nv_bfloat16* t = ns.act[1].as<__nv_bfloat16>();
+    __nv_bfloat16* y = ns.act[2].as<__nv_bfloat16>();
+    const int wblocks = (boards + 7) / 8;
+    k_encode<N><<<(boards + 1 + 7) / 8, 256, 0, e->stream>>>(d_states, d_index, boards, x, S);
+    e->launches++;
+    TB_CUDA(cudaGetLastError());
+    auto conv = [&](const ConvLayer& L, const __nv_bfloat16* in, const __nv_bfloat16* res, __nv_bfloat16* out,
+                    int mode, float* out_f32, int ch_off, int ch_valid) -> int {
+        ConvParams p{};
+        p.in = in; p.res = res; p.out = out; p.out_f32 = out_f32;
+        p.w = L.w.as<__nv_bfloat16>(); p.bias = L.bias.as<float>();
+        p.S = S; p.tiles = tiles; p.n_boards = boards; p.pitch = P; p.mode = mode;
+        p.out_ch_offset = ch_off; p.out_ch_valid = ch_valid;
+        TB_CUDA(conv3x3_tc_launch(p, e->num_sms, e->stream));
+        e->launches++;
+        return TAK_OK;
+    };
+    // initial conv + BN + ReLU (net6.rs:72-76)
+    if (int r = conv(ns.layers[0], x, nullptr, y, CONV_RELU, nullptr, 0, 128)) return r;
+    std::swap(x, y);
+    // residual tower (res_block.rs:14-22)
+    for (int blk = 0; blk < ns.blocks; ++blk) {
+        if (int r = conv(ns.layers[1 + 2 * blk], x, nullptr, t, CONV_RELU, nullptr, 0, 128)) return r;
+        if (int r = conv(ns.layers[2 + 2 * blk], t, x, y, CONV_RES_RELU, nullptr, 0, 128)) return r;
+        std::swap(x, y);
+    }
+    ns.trunk_out = x;
+    // heads
+    if (ns.arch == 6) {
+        for (int grp = 0; grp < ns.policy_groups; ++grp) {
+            const int valid = std::min(128, ns.policy_ch - grp * 128);
+            if (int r = conv(ns.policy_layers[grp], x, nullptr, nullptr, CONV_LOGITS_F32, ns.logits.as<float>(),
+                             grp * 128, valid))
+                return r;
+        }
+        k_policy_stats_conv<N><<<boards, 256, 0, e->stream>>>(ns.logits.as<float>(), S, ns.policy_ch, boards,
+                                                              ns.stats.as<float2>(), d_policy_out);
+    } else {
+        k_policy_fc<N><<<boards, 256, 0, e->stream>>>(x, S, ns.fc_policy_w.as<__nv_bfloat16>(),
+                                                      ns.fc_policy_b.as<float>(), ns.policy_out,
+                                                      ns.logits.as<float>());
+        e->launches++;
+        k_policy_stats_dense<<<boards, 256, 0, e->stream>>>(ns.logits.as<float>(), ns.policy_out,
+                                                            ns.stats.as<float2>(), d_policy_out);
+    }
+    e->launches++;
+    TB_CUDA(cudaGetLastError());
+    k_value<N><<<wblocks, 256, 0, e->stream>>>(x, S, ns.value_w.as<float>(), ns.value_bias, boards,
+                                               ns.values.as<float>());
+    e->launches++;
+    TB_CUDA(cudaGetLastError());
+    return TAK_OK;
+}
+
+int net_forward(tak_engine* e, const uint8_t* d_states, const int* d_index, int boards, float* d_policy_out) {
+    TB_CHECK(e->net, TAK_ERR_NO_NETWORK, "no network: call net_create first");
+    NetState& ns = *e->net;
+    TB_CHECK(ns.arch != 0, TAK_ERR_BAD_ARG, "internal: forward on the DummyNet");
+    TB_CHECK(ns.loaded, TAK_ERR_NO_NETWORK, "network weights not loaded");
+    if (boards == 0) return TAK_OK;
+    int r = TAK_ERR_BAD_ARG;
+    if (e->n == 5) r = forward_t<5>(e, d_states, d_index, boards, d_policy_out);
+    if (e->n == 6) r = forward_t<6>(e, d_states, d_index, boards, d_policy_out);
+    return r;
+}
+
+void net_destroy(tak_engine* e) {
+    if (!e->net) return;
+    NetState& ns = *e->net;
+    for (auto& L : ns.layers) { L.w.release(); L.bias.release(); }
+    for (auto& L : ns.policy_layers) { L.w.release(); L.bias.release(); }
+    for (DevBuf* b : {&ns.fc_policy_w, &ns.fc_policy_b, &ns.value_w, &ns.act[0], &ns.act[1], &ns.act[2], &ns.logits,
+                      &ns.stats, &ns.values, &ns.stage_states, &ns.stage_policy, &ns.stage_repr})
+        b->release();
+    delete e->net;
+    e->net = nullptr;
+}
+
+}  // namespace tb
+
+using namespace tb;
+
+extern "C" {
+
+int32_t net_input_channels(int32_t n, int32_t* out_channels) {
+    TB_CHECK(n >= 3 && n <= 8 && out_channels, TAK_ERR_BAD_ARG, "net_input_channels: bad argument");
+    *out_channels = input_channels_c(n);
+    return TAK_OK;
+}
+
+int32_t net_create(tak_engine_t* e, int32_t arch) {
+    TB_CHECK(e, TAK_ERR_BAD_ARG, "null engine");
+    TB_CHECK(arch == 0 || arch == 5 || arch == 6, TAK_ERR_BAD_ARG, "arch must be 0 (DummyNet), 5 (Net5) or 6 (Net6)");
+    TB_CHECK(arch == 0 || arch == e->n, TAK_ERR_BAD_ARG, "Net%d needs a %dx%d engine (engine is %dx%d)", arch, arch,
+             arch, e->n, e->n);
+    TB_CUDA(cudaSetDevice(e->device));
+    net_destroy(e);
+    NetState* ns = new NetState();
+    ns->arch = arch;
+    ns->n = e->n;
+    ns->c_in = input_channels_c(e->n);
+    ns->policy_out = host_policy_size(e->n);
+    if (arch == 6) {
+        ns->blocks = 16;                         // net6.rs:16
+        ns->policy_ch = 3 + 4 * ((1 << 6) - 2);  // move_channels(6) = 251
+        ns->policy_groups = 2;
+    } else if (arch == 5) {
+        ns->blocks = 8;                          // net5.rs:16
+    }
+    ns->layers.resize(arch ? 1 + 2 * ns->blocks : 0);
+    ns->policy_layers.resize(ns->policy_groups);
+    e->net = ns;
+    return TAK_OK;
+}
+
+int32_t net_weights_size(tak_engine_t* e, int64_t* out_elems) {
+    TB_CHECK(e && e->net && out_elems, TAK_ERR_NO_NETWORK, "no network");
+    *out_elems = e->net->arch ? net_blob_elems(*e->net) : 0;
+    return TAK_OK;
+}
+
+int32_t net_load_weights(tak_engine_t* e, const float* blob, int64_t elems) {
+    TB_CHECK(e && e->net && blob, TAK_ERR_NO_NETWORK, "no network / null blob");
+    TB_CUDA(cudaSetDevice(e->device));
+    return net_load_blob(e, blob, elems);
+}
+
+int32_t net_load_weights_device(tak_engine_t* e, const void* device_blob, int64_t elems) {
+    TB_CHECK(e && e->net && device_blob, TAK_ERR_NO_NETWORK, "no network / null blob");
+    TB_CHECK(elems == net_blob_elems(*e->net), TAK_ERR_BAD_ARG, "weight blob size mismatch");
+    TB_CUDA(cudaSetDevice(e->device));
+    std::vector<float> host(static_cast<size_t>(elems));
+    // the caller's tensor may live on another stream (torch / NCCL): a blocking copy orders after prior device work
+    TB_CUDA(cudaMemcpy(host.data(), device_blob, size_t(elems) * 4, cudaMemcpyDeviceToHost));
+    return net_load_blob(e, host.data(), elems);
+}
+
+static int stage_states(tak_engine_t* e, const tak_state_t* states, int b) {
+    NetState& ns = *e->net;
+    std::vector<uint8_t> packed(size_t(b) * e->state_bytes);
+    for (int i = 0; i < b; ++i) {
+        TB_CHECK(states[i].n == e->n, TAK_ERR_BAD_ARG, "state %d has board size %d, engine has %d", i, states[i].n,
+                 e->n);
+        pack_state(e->n, states[i], packed.data() + size_t(i) * e->state_bytes);
+    }
+    TB_CUDA(ns.stage_states.ensure(packed.size()));
+    TB_CUDA(cudaMemcpyAsync(ns.stage_states.p, packed.data(), packed.size(), cudaMemcpyHostToDevice, e->stream));
+    TB_CUDA(cudaStreamSynchronize(e->stream));
+    return TAK_OK;
+}
+
+int32_t net_game_repr(tak_engine_t* e, const tak_state_t* states, int32_t b, float* out) {
+    TB_CHECK(e && states && out && b >= 0, TAK_ERR_BAD_ARG, "net_game_repr: bad argument");
+    if (b == 0) return TAK_OK;
+    TB_CUDA(cudaSetDevice(e->device));
+    if (!e->net) {
+        int r = net_create(e, 0);
+        if (r) return r;
+    }
+    if (int r = stage_states(e, states, b)) return r;
+    NetState& ns = *e->net;
+    const size_t elems = size_t(b) * input_channels_c(e->n) * e->nsq;
+    TB_CUDA(ns.stage_repr.ensure(elems * 4));
+    TB_DISPATCH_N(e->n, (k_repr_f32<N_><<<(b + 7) / 8, 256, 0, e->stream>>>(ns.stage_states.as<uint8_t>(), b,
+                                                                           ns.stage_repr.as<float>())));
+    e->launches++;
+    TB_CUDA(cudaGetLastError());
+    TB_CUDA(cudaMemcpyAsync(out, ns.stage_repr.p, elems * 4, cudaMemcpyDeviceToHost, e->stream));
+    TB_CUDA(cudaStreamSynchronize(e->stream));
+    return TAK_OK;
+}
+
+int32_t net_policy_eval(tak_engine_t* e, const tak_state_t* states, int32_t b, float* out_policy, float* out_value) {
+    TB_CHECK(e && states && out_policy && out_value && b >= 0, TAK_ERR_BAD_ARG, "net_policy_eval: bad argument");
+    TB_CHECK(e->net, TAK_ERR_NO_NETWORK, "no network: call net_create first");
+    if (b == 0) return TAK_OK;
+    TB_CUDA(cudaSetDevice(e->device));
+    NetState& ns = *e->net;
+    const int psz = ns.policy_out;
+    if (ns.arch == 0) {  // DummyNet: policy all ones, eval 0 (search/tests.rs:29-34)
+        for (size_t i = 0; i < size_t(b) * psz; ++i) out_policy[i] = 1.0f;
+        for (int i = 0; i < b; ++i) out_value[i] = 0.0f;
+        return TAK_OK;
+    }
+    const int chunk = e->max_batch;
+    for (int done = 0; done < b; done += chunk) {
+        const int cur = std::min(chunk, b - done);
+        if (int r = stage_states(e, states + done, cur)) return r;
+        TB_CUDA(ns.stage_policy.ensure(size_t(cur) * psz * 4));
+        if (int r = net_forward(e, ns.stage_states.as<uint8_t>(), nullptr, cur, ns.stage_policy.as<float>())) return r;
+        TB_CUDA(cudaMemcpyAsync(out_policy + size_t(done) * psz, ns.stage_policy.p, size_t(cur) * psz * 4,
+                                cudaMemcpyDeviceToHost, e->stream));
+        TB_CUDA(cudaMemcpyAsync(out_value + done, ns.values.p, size_t(cur) * 4, cudaMemcpyDeviceToHost, e->stream));
+        TB_CUDA(cudaStreamSynchronize(e->stream));
+    }
+    return TAK_OK;
+}
+
+int32_t net_forward_timed(tak_engine_t* e, int32_t first, int32_t count, int32_t reps, double* out_ms) {
+    TB_CHECK(e && out_ms && reps > 0 && first >= 0 && count > 0 && first + count <= e->max_games, TAK_ERR_BAD_ARG,
+             "net_forward_timed: bad argument");
+    TB_CHECK(e->net && e->net->arch != 0, TAK_ERR_NO_NETWORK, "no network");
+    TB_CUDA(cudaSetDevice(e->device));
+    const uint8_t* st = e->states.as<uint8_t>() + size_t(first) * e->state_bytes;
+    if (int r = net_forward(e, st, nullptr, count, nullptr)) return r;  // warm-up + allocation
+    cudaEvent_t e0, e1;
+    TB_CUDA(cudaEventCreate(&e0));
+    TB_CUDA(cudaEventCreate(&e1));
+    TB_CUDA(cudaEventRecord(e0, e->stream));
+    for (int i = 0; i < reps; ++i)
+        if (int r = net_forward(e, st, nullptr, count, nullptr)) return r;
+    TB_CUDA(cudaEventRecord(e1, e->stream));
+    TB_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    TB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *out_ms = ms;
+    return TAK_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,46 @@
+// Network state of an engine (weights packed for conv_tc, activation slot planes, head outputs).
+#pragma once
+#include <cuda_bf16.h>
+
+#include "engine.hpp"
+
+namespace tb {
+
+struct ConvLayer {
+    DevBuf w;     // bf16 [18][8][128][8]
+    DevBuf bias;  // fp32 [128]
+};
+
+struct NetState {
+    int arch = 0;          // 0 DummyNet, 5 Net5, 6 Net6
+    int n = 0;
+    int c_in = 0;          // input_channels(n)
+    int blocks = 0;        // residual blocks
+    int policy_ch = 0;     // Net6: move_channels(6) = 251
+    int policy_groups = 0; // Net6: 2 groups of 128 output channels
+    int policy_out = 0;    // policy vector length (1575 / 9036)
+    bool loaded = false;
+    std::vector<ConvLayer> layers;         // initial conv + 2 per block (BN folded)
+    std::vector<ConvLayer> policy_layers;  // Net6 policy conv, one per group
+    DevBuf fc_policy_w, fc_policy_b;       // Net5 policy FC: bf16 Wt[k][j], fp32 bias
+    DevBuf value_w;                        // fp32 [128*NSQ] (NCHW flatten order)
+    float value_bias = 0.f;
+    // activations
+    int cap_boards = 0, cap_S = 0;
+    DevBuf act[3];                         // bf16 slot planes
+    DevBuf logits;                         // Net6: fp32 [256][S]; Net5: fp32 [B][1575]
+    DevBuf stats;                          // float2 {max, sum exp} per board
+    DevBuf values;                         // fp32 [B]
+    const __nv_bfloat16* trunk_out = nullptr;
+    // staging for the host-facing API
+    DevBuf stage_states, stage_policy, stage_repr;
+};
+
+// Evaluate `boards` packed states (d_states[index[i]] or d_states[i] if index == nullptr) on the engine stream.
+// Leaves logits / stats / values on device; optionally writes the full softmax policy [boards][policy_out].
+int net_forward(tak_engine* e, const uint8_t* d_states, const int* d_index, int boards, float* d_policy_out);
+int net_ensure_capacity(tak_engine* e, int boards);
+int net_load_blob(tak_engine* e, const float* blob, int64_t elems);
+int64_t net_blob_elems(const NetState& ns);
+
+}  // namespace tb

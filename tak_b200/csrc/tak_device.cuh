@@ -1,0 +1,418 @@
+// Warp-cooperative Tak game state for sm_100a: one warp holds one game, lane l owns squares l and l+32.
+//
+// Device-side replacement for tak::Game<N> / Board<N> / Tile (reference: tak/src/game.rs:25-35, board.rs:8-10,
+// tile.rs:7-10) and the three hot functions possible_moves (move_gen.rs:7-102), play (game.rs:121-209) and
+// result (game.rs:220-267, board.rs:61-113).
+//
+// HBM record ("packed state", S bytes, S = 288/384/1120 for N = 5/6/8):
+//   cols[NSQ]   stack colours per square, bit i = piece i is Black (bit 0 = bottom); u64 for N<=6, u128 above
+//   hts[NSQ]    stack heights (u8)
+//   walls,caps  bitboards of the top-piece kind
+//   scalars     to_move, ply, reserves, half_komi, reversible_plies
+// Squares are stored in MOVE-GENERATION order o = col*N + row (the reference enumerates `for x {for y}`),
+// so a warp prefix sum over per-square move counts yields the reference's move order directly, and a
+// warp's loads/stores of cols[] are one coalesced 256-byte access.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include <type_traits>
+
+namespace tb {
+
+constexpr unsigned FULL = 0xFFFFFFFFu;
+
+__host__ __device__ constexpr int tak_stones(int n) {
+    return n == 3 ? 10 : n == 4 ? 15 : n == 5 ? 21 : n == 6 ? 30 : n == 7 ? 40 : 50;
+}
+__host__ __device__ constexpr int tak_caps(int n) { return n <= 4 ? 0 : n <= 6 ? 1 : 2; }
+
+template <int N>
+struct StateLayout {
+    static constexpr int NSQ = N * N;
+    using Col = std::conditional_t<(N <= 6), uint64_t, unsigned __int128>;
+    static constexpr int COLS_BYTES = NSQ * int(sizeof(Col));
+    static constexpr int HTS_OFF = (COLS_BYTES + 15) / 16 * 16;
+    static constexpr int HTS_BYTES = (NSQ + 15) / 16 * 16;
+    static constexpr int BB_OFF = HTS_OFF + HTS_BYTES;   // walls, caps
+    static constexpr int SC_OFF = BB_OFF + 16;           // 16 bytes of scalars
+    static constexpr int RAW = SC_OFF + 16;
+    static constexpr int S = (RAW + 31) / 32 * 32;
+};
+
+struct StateScalars {  // 16 bytes
+    uint8_t to_move;   // 0 White 1 Black
+    uint8_t ws, wc, bs, bc;
+    int8_t half_komi;
+    uint8_t reversible;
+    uint8_t _pad;
+    uint16_t ply;
+    uint16_t _pad2[3];
+};
+static_assert(sizeof(StateScalars) == 16, "scalars must be 16 bytes");
+
+// number of compositions of p into at most f parts / into exactly f+1 parts whose last part is 1
+static __constant__ uint8_t c_comp_le[9][8] = {
+    {0, 0, 0, 0, 0, 0, 0, 0},      {0, 1, 1, 1, 1, 1, 1, 1},       {0, 1, 2, 2, 2, 2, 2, 2},
+    {0, 1, 3, 4, 4, 4, 4, 4},      {0, 1, 4, 7, 8, 8, 8, 8},       {0, 1, 5, 11, 15, 16, 16, 16},
+    {0, 1, 6, 16, 26, 31, 32, 32}, {0, 1, 7, 22, 42, 57, 63, 64},  {0, 1, 8, 29, 64, 99, 120, 127}};
+static __constant__ uint8_t c_comp_flat[9][8] = {
+    // [p][f] = C(p-2, f-1) for f>=1 (p-1 >= f), and [p][0] = (p == 1)
+    {0, 0, 0, 0, 0, 0, 0, 0}, {1, 0, 0, 0, 0, 0, 0, 0},  {0, 1, 0, 0, 0, 0, 0, 0},
+    {0, 1, 1, 0, 0, 0, 0, 0}, {0, 1, 2, 1, 0, 0, 0, 0},  {0, 1, 3, 3, 1, 0, 0, 0},
+    {0, 1, 4, 6, 4, 1, 0, 0}, {0, 1, 5, 10, 10, 5, 1, 0}, {0, 1, 6, 15, 20, 15, 6, 1}};
+
+// GameResult byte (include/taknative.h): 0 ongoing, 1 white, 2 black, 3 draw, |0x10 road / reversible
+enum : uint8_t { RES_ONGOING = 0, RES_WHITE = 1, RES_BLACK = 2, RES_DRAW = 3, RES_FLAG = 0x10 };
+
+template <int N>
+struct WarpGame {
+    using L = StateLayout<N>;
+    using Col = typename L::Col;
+    static constexpr int NSQ = L::NSQ;
+    static constexpr bool TWO = NSQ > 32;
+    static constexpr uint64_t ALL = NSQ == 64 ? ~0ull : ((1ull << NSQ) - 1);
+
+    Col c0, c1;        // colours of squares lane / lane+32
+    int h0, h1;        // heights
+    uint64_t walls, caps;  // uniform
+    int to_move, ply, ws, wc, bs, bc, half_komi, reversible;  // uniform
+
+    __device__ __forceinline__ static int lane() { return threadIdx.x & 31; }
+    __device__ __forceinline__ static int row_of(int o) { return o % N; }
+    __device__ __forceinline__ static int col_of(int o) { return o / N; }
+
+    __device__ __forceinline__ void load(const uint8_t* rec) {
+        const int l = lane();
+        const Col* cols = reinterpret_cast<const Col*>(rec);
+        const uint8_t* hts = rec + L::HTS_OFF;
+        c0 = 0; c1 = 0; h0 = 0; h1 = 0;
+        if (l < NSQ) { c0 = cols[l]; h0 = hts[l]; }
+        if (TWO && l + 32 < NSQ) { c1 = cols[l + 32]; h1 = hts[l + 32]; }
+        const uint64_t* bb = reinterpret_cast<const uint64_t*>(rec + L::BB_OFF);
+        walls = bb[0];
+        caps = bb[1];
+        const uint4 sv = *reinterpret_cast<const uint4*>(rec + L::SC_OFF);
+        StateScalars sc;
+        *reinterpret_cast<uint4*>(&sc) = sv;
+        to_move = sc.to_move; ply = sc.ply; ws = sc.ws; wc = sc.wc; bs = sc.bs; bc = sc.bc;
+        half_komi = sc.half_komi; reversible = sc.reversible;
+    }
+    __device__ __forceinline__ void store(uint8_t* rec) const {
+        const int l = lane();
+        Col* cols = reinterpret_cast<Col*>(rec);
+        uint8_t* hts = rec + L::HTS_OFF;
+        if (l < NSQ) { cols[l] = c0; hts[l] = uint8_t(h0); }
+        if (TWO && l + 32 < NSQ) { cols[l + 32] = c1; hts[l + 32] = uint8_t(h1); }
+        if (l == 0) {
+            uint64_t* bb = reinterpret_cast<uint64_t*>(rec + L::BB_OFF);
+            bb[0] = walls;
+            bb[1] = caps;
+            StateScalars sc{};
+            sc.to_move = uint8_t(to_move); sc.ply = uint16_t(ply);
+            sc.ws = uint8_t(ws); sc.wc = uint8_t(wc); sc.bs = uint8_t(bs); sc.bc = uint8_t(bc);
+            sc.half_komi = int8_t(half_komi); sc.reversible = uint8_t(reversible);
+            *reinterpret_cast<uint4*>(rec + L::SC_OFF) = *reinterpret_cast<uint4*>(&sc);
+        }
+    }
+    __device__ __forceinline__ void reset(int hk) {
+        c0 = 0; c1 = 0; h0 = 0; h1 = 0; walls = 0; caps = 0;
+        to_move = 0; ply = 0; ws = bs = tak_stones(N); wc = bc = tak_caps(N); half_komi = hk; reversible = 0;
+    }
+
+    // bitboard from per-lane predicates of the two owned squares
+    __device__ __forceinline__ uint64_t bb(bool p0, bool p1) const {
+        uint64_t lo = __ballot_sync(FULL, p0);
+        if (!TWO) return lo & ALL;
+        uint64_t hi = __ballot_sync(FULL, p1);
+        return (lo | (hi << 32)) & ALL;
+    }
+    __device__ __forceinline__ static bool top_black(Col c, int h) { return h > 0 && ((c >> (h - 1)) & 1); }
+    __device__ __forceinline__ uint64_t occupied() const { return bb(h0 > 0, h1 > 0); }
+    __device__ __forceinline__ uint64_t black_tops() const { return bb(top_black(c0, h0), top_black(c1, h1)); }
+
+    // ---- Game::result (game.rs:220-267) ----------------------------------------------------------------
+    __device__ __forceinline__ static bool has_road(uint64_t road) {
+        // o = col*N + row: +1 is Up (row+1), +N is Right (col+1)
+        uint64_t row0 = 0, rowL = 0;
+#pragma unroll
+        for (int c = 0; c < N; ++c) { row0 |= 1ull << (c * N); rowL |= 1ull << (c * N + N - 1); }
+        const uint64_t col0 = (1ull << N) - 1, colL = col0 << (N * (N - 1));
+        // vertical: from row 0 to row N-1 (board.rs:79-86); horizontal: col 0 to col N-1 (board.rs:88-93)
+        uint64_t reach = road & row0, reach2 = road & col0;
+        for (;;) {
+            uint64_t a = reach | ((reach << 1) & ~row0) | ((reach >> 1) & ~rowL) | (reach << N) | (reach >> N);
+            uint64_t b = reach2 | ((reach2 << 1) & ~row0) | ((reach2 >> 1) & ~rowL) | (reach2 << N) | (reach2 >> N);
+            a &= road; b &= road;
+            if (a == reach && b == reach2) break;
+            reach = a; reach2 = b;
+        }
+        return (reach & rowL) != 0 || (reach2 & colL) != 0;
+    }
+    __device__ __forceinline__ uint8_t result() const {
+        const uint64_t occ = occupied();
+        const uint64_t blk = black_tops();
+        const uint64_t wht = occ & ~blk;
+        const uint64_t road_w = wht & ~walls, road_b = blk & ~walls;
+        const uint64_t road_prev = to_move == 0 ? road_b : road_w;  // player who just moved
+        const uint64_t road_cur = to_move == 0 ? road_w : road_b;
+        if (has_road(road_prev)) return uint8_t((to_move == 0 ? RES_BLACK : RES_WHITE) | RES_FLAG);
+        if (has_road(road_cur)) return uint8_t((to_move == 0 ? RES_WHITE : RES_BLACK) | RES_FLAG);
+        if ((wc == 0 && ws == 0) || (bc == 0 && bs == 0) || occ == ALL) {
+            const uint64_t flat = ~(walls | caps);
+            const int fd = __popcll(wht & flat) - __popcll(blk & flat);
+            const int k = half_komi / 2;  // truncating, as i8 division
+            if (fd > k) return RES_WHITE;
+            if (fd < k) return RES_BLACK;
+            return (half_komi % 2 == 0) ? RES_DRAW : RES_BLACK;
+        }
+        if (reversible >= 50) return uint8_t(RES_DRAW | RES_FLAG);
+        return RES_ONGOING;
+    }
+    __device__ __forceinline__ int flat_diff() const {
+        const uint64_t occ = occupied();
+        const uint64_t blk = black_tops();
+        const uint64_t flat = ~(walls | caps);
+        return __popcll(occ & ~blk & flat) - __popcll(blk & flat);
+    }
+
+    // ---- move generation (move_gen.rs:7-102) -----------------------------------------------------------
+    // free run of droppable squares from o in direction d (0 Up 1 Down 2 Left 3 Right); wall_after = the
+    // run is ended by a wall (a capstone on top of the moving stack may flatten it)
+    __device__ __forceinline__ void free_run(int o, int d, int& free, bool& wall_after) const {
+        const int r = row_of(o), c = col_of(o);
+        const int dist = d == 0 ? N - 1 - r : d == 1 ? r : d == 2 ? c : N - 1 - c;
+        const int delta = d == 0 ? 1 : d == 1 ? -1 : d == 2 ? -N : N;
+        const uint64_t blockers = walls | caps;
+        free = 0;
+        wall_after = false;
+        int q = o;
+        for (int s = 0; s < dist; ++s) {
+            q += delta;
+            if ((blockers >> q) & 1) {
+                wall_after = (walls >> q) & 1;
+                break;
+            }
+            ++free;
+        }
+    }
+    __device__ __forceinline__ int my_stones() const { return to_move == 0 ? ws : bs; }
+    __device__ __forceinline__ int my_caps() const { return to_move == 0 ? wc : bc; }
+    __device__ __forceinline__ bool mover_black() const { return ply < 2 ? (to_move == 0) : (to_move == 1); }
+
+    __device__ __forceinline__ int count_square(int o, Col c, int h) const {
+        if (o >= NSQ) return 0;
+        if (ply < 2) return h == 0 ? 1 : 0;
+        if (h == 0) return (my_stones() > 0 ? 2 : 0) + (my_caps() > 0 ? 1 : 0);
+        if (top_black(c, h) != (to_move == 1)) return 0;
+        const bool is_cap = (caps >> o) & 1;
+        const int maxp = h < N ? h : N;
+        int total = 0;
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+            int free;
+            bool wall_after;
+            free_run(o, d, free, wall_after);
+            const bool flatten = wall_after && is_cap;
+            for (int p = 1; p <= maxp; ++p) total += c_comp_le[p][free] + (flatten ? c_comp_flat[p][free] : 0);
+        }
+        return total;
+    }
+    // per-lane move counts of its two squares
+    __device__ __forceinline__ void count_moves(int& n0, int& n1) const {
+        n0 = count_square(lane(), c0, h0);
+        n1 = TWO ? count_square(lane() + 32, c1, h1) : 0;
+    }
+    __device__ __forceinline__ static uint16_t abi_square(int o) { return uint16_t(row_of(o) * N + col_of(o)); }
+
+    template <class Emit>
+    __device__ __forceinline__ void emit_square(int o, Col c, int h, int base, Emit&& emit) const {
+        if (o >= NSQ) return;
+        const uint16_t sq = abi_square(o);
+        int k = base;
+        if (ply < 2) {
+            if (h == 0) emit(k, sq);
+            return;
+        }
+        if (h == 0) {
+            if (my_stones() > 0) { emit(k++, sq); emit(k++, uint16_t(sq | (1u << 6))); }
+            if (my_caps() > 0) emit(k++, uint16_t(sq | (2u << 6)));
+            return;
+        }
+        if (top_black(c, h) != (to_move == 1)) return;
+        const bool is_cap = (caps >> o) & 1;
+        const int maxp = h < N ? h : N;
+        for (int d = 0; d < 4; ++d) {
+            int free;
+            bool wall_after;
+            free_run(o, d, free, wall_after);
+            const bool flatten = wall_after && is_cap;
+            if (free == 0 && !flatten) continue;
+            for (int p = 1; p <= maxp; ++p) {
+                // drop sequences in descending lexicographic order == odd p-bit patterns in ascending order
+                for (unsigned v = 1; v < (1u << p); v += 2) {
+                    const int parts = __popc(v);
+                    const bool ok = parts <= free || (flatten && parts == free + 1 && (p == 1 || (v & 2)));
+                    if (ok) emit(k++, uint16_t(sq | (unsigned(d) << 6) | ((v << (8 - p)) << 8)));
+                }
+            }
+        }
+    }
+    // total number of legal moves; emit(k, move) is called for move k in reference order
+    template <class Emit>
+    __device__ __forceinline__ int generate(Emit&& emit) const {
+        int n0, n1;
+        count_moves(n0, n1);
+        // exclusive scan over squares 0..31 then 32..63
+        int inc0 = n0;
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) {
+            int t = __shfl_up_sync(FULL, inc0, s);
+            if (lane() >= s) inc0 += t;
+        }
+        const int tot0 = __shfl_sync(FULL, inc0, 31);
+        emit_square(lane(), c0, h0, inc0 - n0, emit);
+        int total = tot0;
+        if (TWO) {
+            int inc1 = n1;
+#pragma unroll
+            for (int s = 1; s < 32; s <<= 1) {
+                int t = __shfl_up_sync(FULL, inc1, s);
+                if (lane() >= s) inc1 += t;
+            }
+            total += __shfl_sync(FULL, inc1, 31);
+            emit_square(lane() + 32, c1, h1, tot0 + inc1 - n1, emit);
+        }
+        return total;
+    }
+    __device__ __forceinline__ int count_total() const {
+        int n0, n1;
+        count_moves(n0, n1);
+        int s = n0 + n1;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+        return s;
+    }
+
+    // ---- Game::play (game.rs:121-209) ---------------------------------------------------------------------
+    // CHECK = validate like the reference and return its PlayError code; without CHECK the move must be legal.
+    template <bool CHECK>
+    __device__ __forceinline__ int play(uint16_t mv) {
+        const int sq = mv & 63;
+        const unsigned mask = mv >> 8;
+        const int kind = (mv >> 6) & 3;
+        if (CHECK && sq >= NSQ) return -1;  // OutOfBounds
+        const int o = (sq % N) * N + (sq / N);
+        const int l = lane();
+        const bool swapped = ply < 2;
+        if (mask == 0) {
+            // ---- execute_place (game.rs:147-169)
+            if (CHECK) {
+                const uint64_t occ = occupied();
+                if ((occ >> o) & 1) return -2;
+                if (kind == 2 && my_caps() == 0) return -3;
+                if (kind <= 1 && my_stones() == 0) return -4;
+                if (kind == 3) return -32;
+                if (swapped && kind != 0) return -5;
+            }
+            const bool black = mover_black();
+            if (l == (o & 31)) {
+                if (o < 32) { c0 = black ? 1 : 0; h0 = 1; }
+                else { c1 = black ? 1 : 0; h1 = 1; }
+            }
+            if (kind == 1) walls |= 1ull << o;
+            if (kind == 2) caps |= 1ull << o;
+            if (kind <= 1) {
+                if ((to_move == 0) != swapped) ws -= 1; else bs -= 1;
+            } else {
+                if (to_move == 0) wc -= 1; else bc -= 1;
+            }
+            reversible = 0;
+        } else {
+            // ---- execute_spread (game.rs:171-209)
+            const int p = 8 - (__ffs(mask) - 1);   // pattern.count_pieces()
+            const int drops = __popc(mask);
+            const int d = kind;
+            const int r = row_of(o), cc = col_of(o);
+            const int delta = d == 0 ? 1 : d == 1 ? -1 : d == 2 ? -N : N;
+            // source column / height, broadcast from the owning lane
+            const int src_lane = o & 31;
+            Col sc = (o < 32) ? c0 : c1;
+            int sh = (o < 32) ? h0 : h1;
+            if constexpr (sizeof(Col) == 8) {
+                sc = __shfl_sync(FULL, sc, src_lane);
+            } else {
+                uint64_t lo = uint64_t(sc), hi = uint64_t(sc >> 64);
+                lo = __shfl_sync(FULL, lo, src_lane);
+                hi = __shfl_sync(FULL, hi, src_lane);
+                sc = (Col(hi) << 64) | lo;
+            }
+            sh = __shfl_sync(FULL, sh, src_lane);
+            const bool src_cap = (caps >> o) & 1, src_wall = (walls >> o) & 1;
+            if (CHECK) {
+                if (sh == 0) return -6;                                      // EmptySquare
+                if (top_black(sc, sh) != mover_black()) return -7;           // StackNotOwned
+                if (p > N) return -11;                                       // TakeError::CarryLimit
+                if (p > sh) return -12;                                      // TakeError::StackSize
+                const int dist = d == 0 ? N - 1 - r : d == 1 ? r : d == 2 ? cc : N - 1 - cc;
+                // walk the drops in order and report the first error the reference would hit
+                int q = o;
+                unsigned m = mask;
+                for (int t = 1; t <= drops; ++t) {
+                    if (t > dist) return -13;                                // SpreadOutOfBounds
+                    q += delta;
+                    const int lead = __clz(m << 24);                         // zeros before this drop's one bit
+                    const int dt = lead + 1;
+                    m = (m << dt) & 0xFF;
+                    const bool last_single_cap = (t == drops) && dt == 1 && src_cap;
+                    if ((caps >> q) & 1) return -9;                          // StackError::Cap
+                    if (((walls >> q) & 1) && !last_single_cap) return -8;   // StackError::Wall
+                }
+            }
+            const Col carry = (sc >> (sh - p)) & ((Col(1) << p) - 1);  // bit 0 = bottom-most carried piece
+            // my squares: am I the source, or at distance t along the direction?
+#pragma unroll
+            for (int half = 0; half < (TWO ? 2 : 1); ++half) {
+                const int q = l + 32 * half;
+                if (q >= NSQ) continue;
+                Col& qc = half ? c1 : c0;
+                int& qh = half ? h1 : h0;
+                if (q == o) {
+                    qh = sh - p;
+                    qc = sc & ((Col(1) << qh) - 1);
+                    continue;
+                }
+                const int diff = q - o;
+                int t = 0;
+                if (d == 0 && col_of(q) == cc && diff > 0) t = diff;
+                if (d == 1 && col_of(q) == cc && diff < 0) t = -diff;
+                if (d == 2 && row_of(q) == r && diff < 0) t = -diff / N;
+                if (d == 3 && row_of(q) == r && diff > 0) t = diff / N;
+                if (t == 0 || t > drops) continue;
+                // offset/length of drop t inside the carried pieces
+                unsigned m = mask;
+                int off = 0, dt = 0;
+                for (int i = 1; i <= t; ++i) {
+                    off += dt;
+                    dt = __clz(m << 24) + 1;
+                    m = (m << dt) & 0xFF;
+                }
+                const Col seg = (carry >> off) & ((Col(1) << dt) - 1);
+                qc |= seg << qh;
+                qh += dt;
+            }
+            // top-piece kinds: the source loses its kind; the last drop square takes it
+            const int last = o + delta * drops;
+            walls &= ~(1ull << o);
+            caps &= ~(1ull << o);
+            walls &= ~(1ull << last);  // a flattened wall
+            if (src_wall) walls |= 1ull << last;
+            if (src_cap) caps |= 1ull << last;
+            reversible = (reversible + 1) & 0xFF;
+        }
+        ply += 1;
+        to_move ^= 1;
+        return 0;
+    }
+};
+
+}  // namespace tb

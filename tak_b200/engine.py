@@ -1,0 +1,384 @@
+"""Host-side mirror of the reference's interface for the hot path, over the C ABI (include/taknative.h).
+
+`Engine` is the batched device object (thousands of games / search trees per GPU); `Game`, `Node` and `Network`
+mirror `tak::Game<N>`, `alpha_tak::Node` and `alpha_tak::Network::policy_eval` one-to-one so the parity tests read
+like the reference's own tests (tak/tests/*.rs, alpha-tak/src/search/tests.rs).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import EngineConfig, ReplayRecord, SelfplayConfig, SelfplayStats, TakNativeError, TakState, check
+
+RESULT_ONGOING, RESULT_WHITE, RESULT_BLACK, RESULT_DRAW, RESULT_FLAG = 0, 1, 2, 3, 0x10
+
+
+def _ids(ids) -> Tuple[C.Array, int]:
+    arr = np.ascontiguousarray(ids, dtype=np.int32)
+    return arr.ctypes.data_as(C.POINTER(C.c_int32)), int(arr.size), arr
+
+
+# ---- cold host helpers (takparse surface) -----------------------------------------------------------------
+def parse_move(text: str, n: int) -> int:
+    """takparse `Move::from_str` -> u16 move."""
+    out = C.c_uint16()
+    check(_lib.load().tak_ptn_parse(n, text.encode(), C.byref(out)))
+    return out.value
+
+
+def format_move(move: int, n: int) -> str:
+    buf = C.create_string_buffer(32)
+    check(_lib.load().tak_ptn_format(n, move, buf, 32))
+    return buf.value.decode()
+
+
+def move_index(move: int, n: int) -> int:
+    """alpha_tak::search::move_index (move_map.rs:19-48)."""
+    out = C.c_int32()
+    check(_lib.load().tak_move_index(n, move, C.byref(out)))
+    return out.value
+
+
+def policy_size(n: int) -> int:
+    out = C.c_int32()
+    check(_lib.load().tak_policy_size(n, C.byref(out)))
+    return out.value
+
+
+def input_channels(n: int) -> int:
+    out = C.c_int32()
+    check(_lib.load().net_input_channels(n, C.byref(out)))
+    return out.value
+
+
+def state_init(n: int, half_komi: int = 0) -> TakState:
+    s = TakState()
+    check(_lib.load().tak_state_init(n, half_komi, C.byref(s)))
+    return s
+
+
+def tps_format(state: TakState) -> str:
+    buf = C.create_string_buffer(8192)
+    check(_lib.load().tak_tps_format(C.byref(state), buf, 8192))
+    return buf.value.decode()
+
+
+def tps_parse(n: int, text: str) -> TakState:
+    s = TakState()
+    check(_lib.load().tak_tps_parse(n, text.encode(), C.byref(s)))
+    return s
+
+
+class Engine:
+    """Owns one GPU's game states, search trees and network (`tak_engine_t`)."""
+
+    def __init__(self, n: int, max_games: int, device: int = 0, nodes_per_game: int = 0, max_batch: int = 0):
+        self.lib = _lib.load()
+        self.n = n
+        self.max_games = max_games
+        cfg = EngineConfig(device=device, n=n, max_games=max_games, nodes_per_game=nodes_per_game,
+                           max_batch=max_batch)
+        h = C.c_void_p()
+        check(self.lib.tak_engine_create(C.byref(cfg), C.byref(h)))
+        self._h = h
+        self.policy_size = policy_size(n)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.tak_engine_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        check(self.lib.tak_engine_sync(self._h))
+
+    # ---- tak::Game, batched -----------------------------------------------------------------------------
+    def reset(self, first: int = 0, count: Optional[int] = None, half_komi: int = 0):
+        check(self.lib.tak_games_reset(self._h, first, self.max_games - first if count is None else count, half_komi))
+
+    def upload(self, ids, states: Sequence[TakState]):
+        p, k, _keep = _ids(ids)
+        arr = (TakState * k)(*states)
+        check(self.lib.tak_games_upload(self._h, p, k, arr))
+
+    def download(self, ids) -> List[TakState]:
+        p, k, _keep = _ids(ids)
+        arr = (TakState * k)()
+        check(self.lib.tak_games_download(self._h, p, k, arr))
+        return list(arr)
+
+    def possible_moves(self, ids) -> List[np.ndarray]:
+        """`Game::possible_moves` for each listed game, in the reference's order."""
+        p, k, _keep = _ids(ids)
+        cap = max(1024, 512 * k)
+        while True:
+            moves = np.zeros(cap, dtype=np.uint16)
+            offs = np.zeros(k + 1, dtype=np.int32)
+            r = self.lib.tak_possible_moves(self._h, p, k, moves.ctypes.data_as(C.POINTER(C.c_uint16)),
+                                            offs.ctypes.data_as(C.POINTER(C.c_int32)), cap)
+            if r == -34 and cap < (1 << 26):
+                cap *= 4
+                continue
+            check(r)
+            return [moves[offs[i]:offs[i + 1]].copy() for i in range(k)]
+
+    def play(self, ids, moves) -> np.ndarray:
+        """`Game::play`; returns per-game status (0 or the PlayError code)."""
+        p, k, _keep = _ids(ids)
+        mv = np.ascontiguousarray(moves, dtype=np.uint16)
+        assert mv.size == k
+        st = np.zeros(k, dtype=np.int32)
+        check(self.lib.tak_play(self._h, p, mv.ctypes.data_as(C.POINTER(C.c_uint16)), k,
+                                st.ctypes.data_as(C.POINTER(C.c_int32))))
+        return st
+
+    def result(self, ids) -> np.ndarray:
+        p, k, _keep = _ids(ids)
+        out = np.zeros(k, dtype=np.uint8)
+        check(self.lib.tak_result(self._h, p, k, out.ctypes.data_as(C.POINTER(C.c_uint8))))
+        return out
+
+    def perft(self, root: TakState, depth: int) -> int:
+        out = C.c_uint64()
+        check(self.lib.tak_perft(self._h, C.byref(root), depth, C.byref(out)))
+        return out.value
+
+    def perft_stats(self):
+        ms, mat, launches = C.c_double(), C.c_uint64(), C.c_uint64()
+        check(self.lib.tak_perft_stats(self._h, C.byref(ms), C.byref(mat), C.byref(launches)))
+        return {"ms": ms.value, "materialised": mat.value, "launches": launches.value}
+
+    # ---- alpha_tak::Network --------------------------------------------------------------------------------
+    def net_create(self, arch: int):
+        check(self.lib.net_create(self._h, arch))
+
+    def net_weights_size(self) -> int:
+        out = C.c_int64()
+        check(self.lib.net_weights_size(self._h, C.byref(out)))
+        return out.value
+
+    def net_load_weights(self, blob: np.ndarray):
+        blob = np.ascontiguousarray(blob, dtype=np.float32)
+        check(self.lib.net_load_weights(self._h, blob.ctypes.data_as(C.POINTER(C.c_float)), blob.size))
+
+    def net_load_weights_device(self, ptr: int, elems: int):
+        check(self.lib.net_load_weights_device(self._h, C.c_void_p(ptr), elems))
+
+    def game_repr(self, states: Sequence[TakState]) -> np.ndarray:
+        b = len(states)
+        c = input_channels(self.n)
+        out = np.zeros((b, c, self.n, self.n), dtype=np.float32)
+        arr = (TakState * b)(*states)
+        check(self.lib.net_game_repr(self._h, arr, b, out.ctypes.data_as(C.POINTER(C.c_float))))
+        return out
+
+    def policy_eval(self, states: Sequence[TakState]) -> Tuple[np.ndarray, np.ndarray]:
+        """`Network::policy_eval(&[Game])` -> (policy [B, policy_size], eval [B])."""
+        b = len(states)
+        pol = np.zeros((b, self.policy_size), dtype=np.float32)
+        val = np.zeros(b, dtype=np.float32)
+        if b == 0:
+            return pol, val
+        arr = (TakState * b)(*states)
+        check(self.lib.net_policy_eval(self._h, arr, b, pol.ctypes.data_as(C.POINTER(C.c_float)),
+                                       val.ctypes.data_as(C.POINTER(C.c_float))))
+        return pol, val
+
+    def net_forward_timed(self, first: int, count: int, reps: int) -> float:
+        ms = C.c_double()
+        check(self.lib.net_forward_timed(self._h, first, count, reps, C.byref(ms)))
+        return ms.value
+
+    # ---- alpha_tak::Node, batched -------------------------------------------------------------------------------
+    def tree_reset(self, ids):
+        p, k, _keep = _ids(ids)
+        check(self.lib.mcts_tree_reset(self._h, p, k))
+
+    def virtual_rollout(self, ids, k_per_game: int = 1):
+        p, k, _keep = _ids(ids)
+        check(self.lib.mcts_virtual_rollout(self._h, p, k, k_per_game))
+
+    def pending(self, with_states: bool = True):
+        cnt = C.c_int32()
+        check(self.lib.mcts_pending(self._h, C.byref(cnt), None, None, 0))
+        k = cnt.value
+        gids = np.zeros(max(k, 1), dtype=np.int32)
+        states = (TakState * max(k, 1))()
+        if k:
+            check(self.lib.mcts_pending(self._h, C.byref(cnt), gids.ctypes.data_as(C.POINTER(C.c_int32)),
+                                        states if with_states else None, k))
+        return gids[:k].copy(), list(states)[:k]
+
+    def devirtualize(self):
+        check(self.lib.mcts_devirtualize(self._h))
+
+    def devirtualize_with(self, policy: np.ndarray, value: np.ndarray):
+        policy = np.ascontiguousarray(policy, dtype=np.float32)
+        value = np.ascontiguousarray(value, dtype=np.float32)
+        check(self.lib.mcts_devirtualize_with(self._h, policy.ctypes.data_as(C.POINTER(C.c_float)),
+                                              value.ctypes.data_as(C.POINTER(C.c_float)), value.size))
+
+    def rollouts(self, ids, n_rollouts: int):
+        p, k, _keep = _ids(ids)
+        check(self.lib.mcts_rollouts(self._h, p, k, n_rollouts))
+
+    def children(self, gid: int):
+        cap = 4096
+        mv = np.zeros(cap, dtype=np.uint16)
+        vis = np.zeros(cap, dtype=np.uint32)
+        pri = np.zeros(cap, dtype=np.float32)
+        rew = np.zeros(cap, dtype=np.float32)
+        cnt = C.c_int32()
+        check(self.lib.mcts_children(self._h, gid, mv.ctypes.data_as(C.POINTER(C.c_uint16)),
+                                     vis.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                     pri.ctypes.data_as(C.POINTER(C.c_float)),
+                                     rew.ctypes.data_as(C.POINTER(C.c_float)), cap, C.byref(cnt)))
+        k = cnt.value
+        return mv[:k].copy(), vis[:k].copy(), pri[:k].copy(), rew[:k].copy()
+
+    def root(self, gid: int):
+        v, vv, r = C.c_uint32(), C.c_uint32(), C.c_float()
+        check(self.lib.mcts_root(self._h, gid, C.byref(v), C.byref(vv), C.byref(r)))
+        return v.value, vv.value, r.value
+
+    def pick_move(self, ids) -> np.ndarray:
+        p, k, _keep = _ids(ids)
+        out = np.zeros(k, dtype=np.uint16)
+        check(self.lib.mcts_pick_move(self._h, p, k, out.ctypes.data_as(C.POINTER(C.c_uint16))))
+        return out
+
+    def tree_play(self, ids, moves):
+        p, k, _keep = _ids(ids)
+        mv = np.ascontiguousarray(moves, dtype=np.uint16)
+        check(self.lib.mcts_play(self._h, p, mv.ctypes.data_as(C.POINTER(C.c_uint16)), k))
+
+    def apply_dirichlet(self, ids, alpha: float, ratio: float, seed: int):
+        p, k, _keep = _ids(ids)
+        check(self.lib.mcts_apply_dirichlet(self._h, p, k, alpha, ratio, seed))
+
+    # ---- train::self_play_parallel ----------------------------------------------------------------------------
+    def selfplay_begin(self, **kw):
+        cfg = SelfplayConfig(rollouts=kw.get("rollouts", 800), half_komi=kw.get("half_komi", 4),
+                             instant_win=kw.get("instant_win", 1), exploit_ply=kw.get("exploit_ply", 40),
+                             noise_ply=kw.get("noise_ply", 0), noise_alpha=kw.get("noise_alpha", 0.2),
+                             noise_ratio=kw.get("noise_ratio", 0.3), seed=kw.get("seed", 0x7A4B),
+                             max_plies=kw.get("max_plies", 0), game_id_base=kw.get("game_id_base", 0))
+        check(self.lib.selfplay_begin(self._h, C.byref(cfg)))
+
+    def selfplay_step(self, moves: int = 1) -> SelfplayStats:
+        st = SelfplayStats()
+        check(self.lib.selfplay_step(self._h, moves, C.byref(st)))
+        return st
+
+    def selfplay_drain(self, cap: int = 4096) -> List[ReplayRecord]:
+        arr = (ReplayRecord * cap)()
+        cnt = C.c_int32()
+        check(self.lib.selfplay_drain(self._h, arr, cap, C.byref(cnt)))
+        return list(arr)[:cnt.value]
+
+
+# ---- single-object mirrors of the Rust types --------------------------------------------------------------------
+class _Slots:
+    """Lazily created per-board-size engines whose game slots back `Game` objects."""
+
+    engines = {}
+    free = {}
+    SLOTS = 256
+
+    @classmethod
+    def acquire(cls, n: int):
+        if n not in cls.engines:
+            cls.engines[n] = Engine(n, cls.SLOTS)
+            cls.free[n] = list(range(cls.SLOTS - 1, -1, -1))
+        if not cls.free[n]:
+            raise RuntimeError("out of Game slots")
+        return cls.engines[n], cls.free[n].pop()
+
+    @classmethod
+    def release(cls, n: int, slot: int):
+        if n in cls.free:
+            cls.free[n].append(slot)
+
+
+class Game:
+    """Mirror of `tak::Game<N>` (reference: tak/src/game.rs) whose state lives on the GPU.
+
+    >>> g = Game.from_ptn_moves(5, ["d3", "c3", "c4", "1d3<", "1c4-", "Sc4"])
+    >>> len(g.possible_moves())   # tak/tests/perft.rs:21-24
+    87
+    """
+
+    def __init__(self, n: int = 5, half_komi: int = 0):
+        self.n = n
+        self.engine, self.slot = _Slots.acquire(n)
+        self.engine.reset(self.slot, 1, half_komi)
+
+    def __del__(self):
+        try:
+            _Slots.release(self.n, self.slot)
+        except Exception:
+            pass
+
+    @classmethod
+    def default(cls, n: int) -> "Game":
+        return cls(n, 0)
+
+    @classmethod
+    def with_komi(cls, n: int, komi: int) -> "Game":
+        return cls(n, komi * 2)
+
+    @classmethod
+    def with_half_komi(cls, n: int, half_komi: int) -> "Game":
+        return cls(n, half_komi)
+
+    @classmethod
+    def from_ptn_moves(cls, n: int, moves: Iterable[str], half_komi: int = 0) -> "Game":
+        g = cls(n, half_komi)
+        for m in moves:
+            st = g.play(m)
+            if st != 0:
+                raise TakNativeError(st, f"PlayError while playing {m}")
+        return g
+
+    @classmethod
+    def from_state(cls, state: TakState) -> "Game":
+        g = cls(state.n, state.half_komi)
+        g.engine.upload([g.slot], [state])
+        return g
+
+    def clone(self) -> "Game":
+        return Game.from_state(self.state())
+
+    def play(self, move) -> int:
+        if isinstance(move, str):
+            move = parse_move(move, self.n)
+        return int(self.engine.play([self.slot], [move])[0])
+
+    def possible_moves(self) -> List[int]:
+        return [int(m) for m in self.engine.possible_moves([self.slot])[0]]
+
+    def result(self) -> int:
+        return int(self.engine.result([self.slot])[0])
+
+    def state(self) -> TakState:
+        return self.engine.download([self.slot])[0]
+
+    def set_half_komi(self, half_komi: int):
+        s = self.state()
+        s.half_komi = half_komi
+        self.engine.upload([self.slot], [s])
+
+    def tps(self) -> str:
+        return tps_format(self.state())
+
+    def perft(self, depth: int) -> int:
+        return self.engine.perft(self.state(), depth)

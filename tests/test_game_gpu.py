@@ -1,0 +1,144 @@
+"""GPU parity of the tak::Game path (movegen order, play, result, perft) against the CPU oracle and the
+reference's known answers.  Everything goes through the C ABI (tak_b200 -> libtaknative.so)."""
+import numpy as np
+import pytest
+
+import oracle
+import tak_b200 as tb
+from util import random_positions, to_tb_state
+
+pytestmark = pytest.mark.gpu
+
+
+def splitmix(x):
+    x = (x + 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+    z = x
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+    return z ^ (z >> 31)
+
+
+def test_perft_known_answers(golden):
+    # reference: tak/tests/perft.rs:20-99 -- read like the reference's own test
+    for case in golden["perft"]:
+        game = tb.Game.from_ptn_moves(case["n"], case["moves"])
+        for depth, expect in case["expect"]:
+            assert game.perft(depth) == expect, (case["name"], depth)
+
+
+def test_perft_6x6_depth5():
+    # the value the reference keeps commented out (perft.rs:98)
+    assert tb.Game.default(6).perft(5) == 1_253_506_520
+
+
+def test_wins(golden):
+    # reference: tak/tests/wins.rs:5-67
+    for case in golden["wins"]:
+        game = tb.Game.from_ptn_moves(case["n"], case["moves"])
+        for chk in case["checks"]:
+            if chk["half_komi"] is not None:
+                game.set_half_komi(chk["half_komi"])
+            assert game.result() == chk["result"], case["name"]
+
+
+def test_golden_tps(golden):
+    # reference: tak/tests/tps.rs:5-24
+    t = golden["tps"]
+    assert tb.Game.from_ptn_moves(t["n"], t["moves"]).tps() == t["tps"]
+
+
+@pytest.mark.parametrize("n,games,komi", [(3, 64, 0), (4, 64, 1), (5, 256, 0), (6, 256, 4), (7, 32, 0), (8, 48, 4)])
+def test_random_playouts_match_oracle(n, games, komi):
+    """Lock-step random playouts: at every ply the GPU's move list (order included), the state after the move
+    and the result must equal the oracle's, bit for bit."""
+    eng = tb.Engine(n, games)
+    eng.reset(0, games, komi)
+    orc = [oracle.Game(n, komi) for _ in range(games)]
+    live = list(range(games))
+    ply = 0
+    max_moves = 0
+    while live and ply < 400:
+        lists = eng.possible_moves(live)
+        picks = []
+        for gid, mv in zip(live, lists):
+            want = orc[gid].possible_moves()
+            assert list(mv) == want, f"move list differs: n={n} game={gid} ply={ply}"
+            max_moves = max(max_moves, len(want))
+            picks.append(want[splitmix(gid * 1000003 + ply) % len(want)])
+        st = eng.play(live, picks)
+        assert not st.any()
+        for gid, mv in zip(live, picks):
+            assert orc[gid].play(mv) == 0
+        res = eng.result(live)
+        states = eng.download(live)
+        nxt = []
+        for gid, r, s in zip(live, res, states):
+            assert int(r) == orc[gid].result(), f"result differs: n={n} game={gid} ply={ply}"
+            assert s.key() == orc[gid].state().key(), f"state differs: n={n} game={gid} ply={ply}"
+            if r == 0:
+                nxt.append(gid)
+        live = nxt
+        ply += 1
+    assert max_moves > 3 * n
+    eng.close()
+
+
+def test_play_error_codes_fuzz():
+    """Game::play on arbitrary (mostly illegal) moves: the status must be the PlayError the reference would raise
+    (check order of tak/src/game.rs:147-209, tile.rs:28-63) and legal ones must produce the oracle's state."""
+    seen = set()
+    for n in (4, 5, 6, 8):
+        games = random_positions(n, 48, seed=40 + n, max_ply=70)
+        eng = tb.Engine(n, len(games))
+        ids = list(range(len(games)))
+        states = [to_tb_state(g.state()) for g in games]
+        for rnd in range(24):
+            eng.upload(ids, states)
+            moves = []
+            for gid in ids:
+                r = splitmix(gid * 7919 + rnd * 104729 + n)
+                sq = r % (n * n)
+                kind = (r >> 8) % 4
+                mask = (r >> 16) & 0xFF if (r >> 12) % 4 else 0
+                if mask == 0 and kind == 3:
+                    kind = 0
+                if (r >> 40) % 3 == 0:  # bias towards the mover's own stacks with plausible pickups
+                    legal = [m for m in games[gid].possible_moves() if m >> 8]
+                    if legal:
+                        base = legal[(r >> 44) % len(legal)]
+                        sq, kind = base & 63, (base >> 6) & 3
+                moves.append(sq | (kind << 6) | (mask << 8))
+            st = eng.play(ids, moves)
+            after = eng.download(ids)
+            for gid in ids:
+                o = games[gid].clone()
+                want = o.play(moves[gid])
+                assert int(st[gid]) == want, (n, gid, hex(moves[gid]), int(st[gid]), want)
+                seen.add(want)
+                if want == 0:
+                    assert after[gid].key() == o.state().key()
+        eng.close()
+    assert {0, -2, -6, -7, -8, -9, -11, -12, -13}.issubset(seen), seen
+
+
+def test_play_error_codes_opening():
+    g = tb.Game.default(5)
+    assert g.play("Sa1") == -5 and tb.Game.default(5).play("Ca1") == -5   # OpeningNonFlat
+    g = tb.Game.from_ptn_moves(5, ["a1"])
+    assert g.play("a1") == -2                                             # AlreadyOccupied
+    g = tb.Game.from_ptn_moves(5, ["a1", "b1", "Cc1", "d1"])
+    assert g.play("Ce1") == -3                                            # NoCapstone
+
+
+def test_ptn_tps_text_matches_oracle(golden_moves_5):
+    for i, text in enumerate(golden_moves_5):
+        mv = tb.parse_move(text, 5)
+        assert mv == oracle.parse_move(text, 5)
+        assert tb.format_move(mv, 5) == text
+        assert tb.move_index(mv, 5) == i
+    g = random_positions(6, 1, seed=77, min_ply=30, max_ply=60)[0]
+    for mv in g.possible_moves():
+        assert tb.move_index(mv, 6) == oracle.move_index(mv, 6)
+    s = tb.tps_parse(6, g.tps())
+    assert tb.tps_format(s) == g.tps()
+    assert s.key() == oracle.Game.from_tps(6, g.tps()).state().key()

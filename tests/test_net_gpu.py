@@ -1,0 +1,88 @@
+"""GPU parity of the network path: game_repr planes (bit-exact vs the oracle) and Net5/Net6 policy_eval
+(within the north-star tolerance, max abs 1e-2, vs the fp32 PyTorch restatement on seeded random weights)."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+import tak_b200 as tb
+from oracle.net_ref import RefNet
+from tak_b200 import weights as W
+from util import random_positions, to_tb_state
+
+pytestmark = pytest.mark.gpu
+
+POLICY_TOL = 1e-2   # north_star: "network policy logits and value agree within a stated bf16 tolerance (max abs 1e-2)"
+VALUE_TOL = 1e-2
+
+
+@pytest.mark.parametrize("n", [3, 4, 5, 6, 7, 8])
+def test_game_repr_bit_exact(n):
+    # reference: alpha-tak/src/repr/game.rs:19-51 (+ tests.rs:20-111 through the oracle, pinned on CPU)
+    games = random_positions(n, 24, seed=n, max_ply=90)
+    eng = tb.Engine(n, 8)
+    got = eng.game_repr([to_tb_state(g.state()) for g in games])
+    want = np.stack([g.repr() for g in games])
+    assert got.shape == want.shape == (24, tb.input_channels(n), n, n)
+    assert np.array_equal(got, want)
+    eng.close()
+
+
+def _check_net(arch, batch):
+    n = arch
+    blob = W.random_weights(arch, seed=0)
+    games = random_positions(n, batch, seed=11 + arch)
+    states = [to_tb_state(g.state()) for g in games]
+    eng = tb.Engine(n, 8, max_batch=4096)
+    eng.net_create(arch)
+    assert eng.net_weights_size() == blob.size == W.blob_size(arch)
+    eng.net_load_weights(blob)
+    pol, val = eng.policy_eval(states)
+    ref = RefNet(arch, blob, device="cuda")
+    x = torch.from_numpy(np.stack([g.repr() for g in games])).cuda()
+    rpol, rval, rlogits = ref.forward_mcts(x)
+    rpol, rval = rpol.cpu().numpy(), rval.cpu().numpy()
+    perr = np.abs(pol - rpol).max()
+    verr = np.abs(val - rval).max()
+    rel = np.abs(pol - rpol).max() / rpol.max()
+    print(f"Net{arch} B={batch}: policy max|err| {perr:.3e} (max p {rpol.max():.3e}, rel {rel:.3e}), "
+          f"value max|err| {verr:.3e}, |value| max {np.abs(rval).max():.3f}")
+    assert np.allclose(pol.sum(1), 1.0, atol=1e-3)
+    assert perr < POLICY_TOL and verr < VALUE_TOL
+    # the softmax must be tight in relative terms too, or the priors would be useless
+    assert rel < 0.1
+    # batch independence: the same position evaluates to the same bits wherever it sits in a batch
+    pol2, val2 = eng.policy_eval(states[::-1][: max(1, batch // 3)])
+    k = pol2.shape[0]
+    assert np.array_equal(pol2, pol[::-1][:k]) and np.array_equal(val2, val[::-1][:k])
+    eng.close()
+
+
+def test_net6_policy_eval():
+    _check_net(6, 96)
+
+
+def test_net5_policy_eval():
+    _check_net(5, 64)
+
+
+def test_net6_large_batch_matches_small():
+    blob = W.random_weights(6, seed=3)
+    games = random_positions(6, 700, seed=5)
+    states = [to_tb_state(g.state()) for g in games]
+    eng = tb.Engine(6, 8, max_batch=1024)
+    eng.net_create(6)
+    eng.net_load_weights(blob)
+    pol, val = eng.policy_eval(states)           # one 700-board pass (many tiles per CTA)
+    pol_s, val_s = eng.policy_eval(states[:5])   # 5-board pass
+    assert np.array_equal(pol[:5], pol_s) and np.array_equal(val[:5], val_s)
+    eng.close()
+
+
+def test_dummy_net():
+    # reference: alpha-tak/src/search/tests.rs:29-34
+    eng = tb.Engine(3, 4)
+    eng.net_create(0)
+    pol, val = eng.policy_eval([tb.state_init(3)])
+    assert pol.shape == (1, tb.policy_size(3)) and np.all(pol == 1.0) and val[0] == 0.0
+    eng.close()
