@@ -154,6 +154,9 @@ int32_t net_policy_eval(tak_engine_t* e, const tak_state_t* states, int32_t b, f
 /* device-resident variant used by bench.py `value`: evaluates the states of games [first, first+count) in place;
  * returns device milliseconds for `reps` forward passes */
 int32_t net_forward_timed(tak_engine_t* e, int32_t first, int32_t count, int32_t reps, double* out_ms);
+/* profiling variant: out[0] = ms per forward (all kernels), out[1] = ms per forward spent in the 3x3 conv kernel
+ * (CUDA events around each conv launch), out[2] = conv launches per forward, out[3] = algorithmic FLOP per forward */
+int32_t net_forward_profile(tak_engine_t* e, int32_t first, int32_t count, int32_t reps, double* out4);
 
 /* ---- alpha_tak::Node (one search tree per game id) --------------------------------------------------
  * mcts_tree_reset        Node::default()
@@ -177,6 +180,9 @@ int32_t mcts_devirtualize_with(tak_engine_t* e, const float* policy, const float
 int32_t mcts_rollouts(tak_engine_t* e, const int32_t* ids, int32_t n, int32_t n_rollouts);
 int32_t mcts_children(tak_engine_t* e, int32_t id, uint16_t* out_moves, uint32_t* out_visits, float* out_priors,
                       float* out_rewards, int32_t cap, int32_t* out_count);
+/* batched mcts_children: game i's children land in out_moves[i*stride ...] / out_visits[i*stride ...] */
+int32_t mcts_children_batch(tak_engine_t* e, const int32_t* ids, int32_t n, uint16_t* out_moves, uint32_t* out_visits,
+                            int32_t* out_counts, int32_t stride);
 int32_t mcts_root(tak_engine_t* e, int32_t id, uint32_t* out_visits, uint32_t* out_virtual, float* out_reward);
 int32_t mcts_pick_move(tak_engine_t* e, const int32_t* ids, int32_t n, uint16_t* out_moves);
 int32_t mcts_play(tak_engine_t* e, const int32_t* ids, const uint16_t* moves, int32_t n);

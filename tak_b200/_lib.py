@@ -118,6 +118,7 @@ SYMBOLS = {
     "net_game_repr": (_i32, [_vp, _P(TakState), _i32, _P(_f32)]),
     "net_policy_eval": (_i32, [_vp, _P(TakState), _i32, _P(_f32), _P(_f32)]),
     "net_forward_timed": (_i32, [_vp, _i32, _i32, _i32, _P(C.c_double)]),
+    "net_forward_profile": (_i32, [_vp, _i32, _i32, _i32, _P(C.c_double)]),
     "mcts_tree_reset": (_i32, [_vp, _P(_i32), _i32]),
     "mcts_virtual_rollout": (_i32, [_vp, _P(_i32), _i32, _i32]),
     "mcts_pending": (_i32, [_vp, _P(_i32), _P(_i32), _P(TakState), _i32]),
@@ -125,6 +126,7 @@ SYMBOLS = {
     "mcts_devirtualize_with": (_i32, [_vp, _P(_f32), _P(_f32), _i32]),
     "mcts_rollouts": (_i32, [_vp, _P(_i32), _i32, _i32]),
     "mcts_children": (_i32, [_vp, _i32, _P(_u16), _P(C.c_uint32), _P(_f32), _P(_f32), _i32, _P(_i32)]),
+    "mcts_children_batch": (_i32, [_vp, _P(_i32), _i32, _P(_u16), _P(C.c_uint32), _P(_i32), _i32]),
     "mcts_root": (_i32, [_vp, _i32, _P(C.c_uint32), _P(C.c_uint32), _P(_f32)]),
     "mcts_pick_move": (_i32, [_vp, _P(_i32), _i32, _P(_u16)]),
     "mcts_play": (_i32, [_vp, _P(_i32), _P(_u16), _i32]),

@@ -246,30 +246,45 @@ int32_t tak_games_reset(tak_engine_t* e, int32_t first, int32_t count, int32_t h
 int32_t tak_games_upload(tak_engine_t* e, const int32_t* ids, int32_t n, const tak_state_t* states) {
     if (int r = check_ids(e, ids, n)) return r;
     TB_CHECK(states, TAK_ERR_BAD_ARG, "null states");
+    if (n == 0) return TAK_OK;
     TB_CUDA(cudaSetDevice(e->device));
-    std::vector<uint8_t> rec(e->state_bytes);
+    const size_t S = e->state_bytes;
+    std::vector<uint8_t> rec(S * n);
     for (int i = 0; i < n; ++i) {
         TB_CHECK(states[i].n == e->n, TAK_ERR_BAD_ARG, "state %d has board size %d, engine has %d", i, states[i].n,
                  e->n);
-        pack_state(e->n, states[i], rec.data());
-        TB_CUDA(cudaMemcpyAsync(e->states.as<uint8_t>() + size_t(ids[i]) * e->state_bytes, rec.data(),
-                                e->state_bytes, cudaMemcpyHostToDevice, e->stream));
-        TB_CUDA(cudaStreamSynchronize(e->stream));
+        pack_state(e->n, states[i], rec.data() + S * i);
     }
+    // one H2D copy of the packed records + one scatter kernel
+    TB_CUDA(e->d_stage.ensure(S * n));
+    TB_CUDA(e->d_ids.ensure(size_t(n) * 4));
+    TB_CUDA(cudaMemcpyAsync(e->d_stage.p, rec.data(), S * n, cudaMemcpyHostToDevice, e->stream));
+    TB_CUDA(cudaMemcpyAsync(e->d_ids.p, ids, size_t(n) * 4, cudaMemcpyHostToDevice, e->stream));
+    k_scatter_records<<<(n * int(S / 16) + 255) / 256, 256, 0, e->stream>>>(
+        e->d_stage.as<uint4>(), e->states.as<uint4>(), e->d_ids.as<int>(), n, int(S / 16), 1);
+    e->launches++;
+    TB_CUDA(cudaGetLastError());
+    TB_CUDA(cudaStreamSynchronize(e->stream));
     return TAK_OK;
 }
 
 int32_t tak_games_download(tak_engine_t* e, const int32_t* ids, int32_t n, tak_state_t* states) {
     if (int r = check_ids(e, ids, n)) return r;
     TB_CHECK(states, TAK_ERR_BAD_ARG, "null states");
+    if (n == 0) return TAK_OK;
     TB_CUDA(cudaSetDevice(e->device));
-    std::vector<uint8_t> rec(size_t(e->state_bytes) * n);
-    for (int i = 0; i < n; ++i)
-        TB_CUDA(cudaMemcpyAsync(rec.data() + size_t(i) * e->state_bytes,
-                                e->states.as<uint8_t>() + size_t(ids[i]) * e->state_bytes, e->state_bytes,
-                                cudaMemcpyDeviceToHost, e->stream));
+    const size_t S = e->state_bytes;
+    std::vector<uint8_t> rec(S * n);
+    TB_CUDA(e->d_stage.ensure(S * n));
+    TB_CUDA(e->d_ids.ensure(size_t(n) * 4));
+    TB_CUDA(cudaMemcpyAsync(e->d_ids.p, ids, size_t(n) * 4, cudaMemcpyHostToDevice, e->stream));
+    k_scatter_records<<<(n * int(S / 16) + 255) / 256, 256, 0, e->stream>>>(
+        e->d_stage.as<uint4>(), e->states.as<uint4>(), e->d_ids.as<int>(), n, int(S / 16), 0);
+    e->launches++;
+    TB_CUDA(cudaGetLastError());
+    TB_CUDA(cudaMemcpyAsync(rec.data(), e->d_stage.p, S * n, cudaMemcpyDeviceToHost, e->stream));
     TB_CUDA(cudaStreamSynchronize(e->stream));
-    for (int i = 0; i < n; ++i) unpack_state(e->n, rec.data() + size_t(i) * e->state_bytes, states[i]);
+    for (int i = 0; i < n; ++i) unpack_state(e->n, rec.data() + S * i, states[i]);
     return TAK_OK;
 }
 

@@ -59,6 +59,16 @@ __global__ void __launch_bounds__(GAME_THREADS)
     if ((threadIdx.x & 31) == 0) out[w] = r;
 }
 
+// staging[i] <-> states[ids[i]] in 16-byte words (to_states = 1: scatter into the engine, 0: gather out of it)
+static __global__ void k_scatter_records(uint4* staging, uint4* states, const int* ids, int n, int words, int to_states) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * words) return;
+    const int i = t / words, w = t % words;
+    uint4* a = staging + size_t(i) * words + w;
+    uint4* b = states + size_t(ids[i]) * words + w;
+    if (to_states) *b = *a; else *a = *b;
+}
+
 // ---- perft -------------------------------------------------------------------------------------------------
 // counts[w] = number of children parent w contributes to the next frontier (0 for finished games);
 // `leaves` accumulates what perf_count returns for parents that stop here:

@@ -36,7 +36,7 @@ int mcts_ensure(tak_engine* e, int k) {
     if (!e->mcts) {
         MctsState* m = new MctsState();
         e->mcts = m;
-        m->cap = e->nodes_per_game > 0 ? e->nodes_per_game : (1 << 17);
+        m->cap = e->nodes_per_game > 0 ? e->nodes_per_game : (1 << 18);
         TB_CHECK(m->cap >= 64 && m->cap <= (1 << 24), TAK_ERR_BAD_ARG, "nodes_per_game %d out of range", m->cap);
         const size_t nodes = size_t(G) * 2 * m->cap;
         TB_CUDA(m->stat.ensure(nodes * 16));
@@ -94,10 +94,10 @@ int mcts_launch_tree_reset(tak_engine* e, const int* d_ids, int n) {
     return TAK_OK;
 }
 
-int mcts_launch_rollout(tak_engine* e, const int* d_ids, int n, int k) {
+int mcts_launch_rollout(tak_engine* e, const int* d_ids, int n, int k, const uint8_t* d_enable) {
     MctsState& m = *e->mcts;
     TB_DISPATCH_N(e->n, (k_mcts_rollout<N_><<<warp_blocks(n), GAME_THREADS, 0, e->stream>>>(
-                            m.view(), e->states.as<uint8_t>(), d_ids, n, k)));
+                            m.view(), e->states.as<uint8_t>(), d_ids, n, k, d_enable)));
     e->launches++;
     m.queued = true;
     TB_CUDA(cudaGetLastError());
@@ -377,6 +377,33 @@ int32_t mcts_children(tak_engine_t* e, int32_t id, uint16_t* out_moves, uint32_t
         if (out_priors) std::memcpy(&out_priors[i], &st[size_t(i) + 1].x, 4);
         if (out_rewards) std::memcpy(&out_rewards[i], &st[size_t(i) + 1].y, 4);
     }
+    return TAK_OK;
+}
+
+int32_t mcts_children_batch(tak_engine_t* e, const int32_t* ids, int32_t n, uint16_t* out_moves, uint32_t* out_visits,
+                            int32_t* out_counts, int32_t stride) {
+    TB_CHECK(e && ids && out_moves && out_visits && out_counts && n >= 0 && stride > 0, TAK_ERR_BAD_ARG,
+             "mcts_children_batch: bad argument");
+    TB_CUDA(cudaSetDevice(e->device));
+    if (int r = mcts_ensure(e, 1)) return r;
+    if (n == 0) return TAK_OK;
+    MctsState& m = *e->mcts;
+    const int* d_ids = nullptr;
+    if (int r = upload_ids(e, ids, n, &d_ids)) return r;
+    TB_CUDA(m.stage_stat.ensure(size_t(n) * stride * 4 + 16));
+    TB_CUDA(m.stage_link.ensure(size_t(n) * stride * 2 + 16));
+    TB_CUDA(m.stage_count.ensure(size_t(n) * 4 + 16));
+    k_mcts_export_children<<<(n + GAME_WARPS_PER_BLOCK - 1) / GAME_WARPS_PER_BLOCK, GAME_THREADS, 0, e->stream>>>(
+        m.view(), d_ids, n, m.stage_link.as<uint16_t>(), m.stage_stat.as<uint32_t>(), m.stage_count.as<int>(), stride);
+    e->launches++;
+    TB_CUDA(cudaGetLastError());
+    TB_CUDA(cudaMemcpyAsync(out_moves, m.stage_link.p, size_t(n) * stride * 2, cudaMemcpyDeviceToHost, e->stream));
+    TB_CUDA(cudaMemcpyAsync(out_visits, m.stage_stat.p, size_t(n) * stride * 4, cudaMemcpyDeviceToHost, e->stream));
+    TB_CUDA(cudaMemcpyAsync(out_counts, m.stage_count.p, size_t(n) * 4, cudaMemcpyDeviceToHost, e->stream));
+    TB_CUDA(cudaStreamSynchronize(e->stream));
+    for (int i = 0; i < n; ++i)
+        TB_CHECK(out_counts[i] <= stride, TAK_ERR_CAPACITY, "game %d has %d root children (> stride %d)", ids[i],
+                 out_counts[i], stride);
     return TAK_OK;
 }
 

@@ -19,7 +19,7 @@ struct MctsState {
 
 int mcts_ensure(tak_engine* e, int k);
 // d_ids == nullptr => games [0, n)
-int mcts_launch_rollout(tak_engine* e, const int* d_ids, int n, int k);
+int mcts_launch_rollout(tak_engine* e, const int* d_ids, int n, int k, const uint8_t* d_enable = nullptr);
 int mcts_launch_compact(tak_engine* e);                 // fills eval_index / eval_slot / eval_count (device)
 int mcts_read_eval_count(tak_engine* e, int* out);      // syncs the stream
 int mcts_launch_backup(tak_engine* e, const PriorSource& ps);

@@ -63,9 +63,10 @@ __device__ __forceinline__ void update_concrete(uint4& s, float reward) {
 // Node::virtual_rollout x k (mcts.rs:26-65) incl. select (mcts.rs:94-118); one warp per listed game
 template <int N>
 __global__ void __launch_bounds__(GAME_THREADS)
-    k_mcts_rollout(MctsView v, const uint8_t* states, const int* ids, int n, int k) {
+    k_mcts_rollout(MctsView v, const uint8_t* states, const int* ids, int n, int k, const uint8_t* enable) {
     const int w = warp_global_id();
     if (w >= n) return;
+    if (enable && !enable[w]) return;
     const int gid = ids ? ids[w] : w;
     const int l = threadIdx.x & 31;
     constexpr int S = StateLayout<N>::S;
@@ -478,6 +479,27 @@ static __global__ void k_mcts_export_root(MctsView v, int gid, uint4* out_stat, 
     for (int i = threadIdx.x; i < nchild && i + 1 < cap; i += blockDim.x) {
         out_stat[1 + i] = stat[base + i];
         out_link[1 + i] = link[base + i];
+    }
+}
+
+// Node::improved_policy (play.rs:13-22) for many games: moves / visits of the root children, `stride` per game
+static __global__ void __launch_bounds__(GAME_THREADS)
+    k_mcts_export_children(MctsView v, const int* ids, int n, uint16_t* out_moves, uint32_t* out_visits,
+                           int* out_counts, int stride) {
+    const int w = warp_global_id();
+    if (w >= n) return;
+    const int gid = ids ? ids[w] : w;
+    const int l = threadIdx.x & 31;
+    const int half = v.half[gid];
+    const uint4* stat = v.stat + arena_base(v, gid, half);
+    const uint2* link = v.link + arena_base(v, gid, half);
+    const uint2 lk = link[0];
+    const uint32_t base = lk.x & 0xFFFFFFu;
+    const int nchild = int(lk.y >> 16);
+    if (l == 0) out_counts[w] = nchild;
+    for (int i = l; i < nchild && i < stride; i += 32) {
+        out_moves[size_t(w) * stride + i] = uint16_t(link[base + i].y & 0xFFFFu);
+        out_visits[size_t(w) * stride + i] = stat[base + i].z;
     }
 }
 

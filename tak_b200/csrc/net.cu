@@ -153,6 +153,8 @@ static int forward_t(tak_engine* e, const uint8_t* d_states, const int* d_index,
     TB_CUDA(cudaGetLastError());
     auto conv = [&](const ConvLayer& L, const __nv_bfloat16* in, const __nv_bfloat16* res, __nv_bfloat16* out,
                     int mode, float* out_f32, int ch_off, int ch_valid) -> int {
+        NetProfile* prof = ns.profile;
+        if (prof) TB_CUDA(cudaEventRecord(prof->ev[2 * prof->n], e->stream));
         ConvParams p{};
         p.in = in; p.res = res; p.out = out; p.out_f32 = out_f32;
         p.w = L.w.as<__nv_bfloat16>(); p.bias = L.bias.as<float>();
@@ -160,6 +162,10 @@ static int forward_t(tak_engine* e, const uint8_t* d_states, const int* d_index,
         p.out_ch_offset = ch_off; p.out_ch_valid = ch_valid;
         TB_CUDA(conv3x3_tc_launch(p, e->num_sms, e->stream));
         e->launches++;
+        if (prof) {
+            TB_CUDA(cudaEventRecord(prof->ev[2 * prof->n + 1], e->stream));
+            prof->n++;
+        }
         return TAK_OK;
     };
     // initial conv + BN + ReLU (net6.rs:72-76)
@@ -340,6 +346,54 @@ int32_t net_policy_eval(tak_engine_t* e, const tak_state_t* states, int32_t b, f
         TB_CUDA(cudaMemcpyAsync(out_value + done, ns.values.p, size_t(cur) * 4, cudaMemcpyDeviceToHost, e->stream));
         TB_CUDA(cudaStreamSynchronize(e->stream));
     }
+    return TAK_OK;
+}
+
+int32_t net_forward_profile(tak_engine_t* e, int32_t first, int32_t count, int32_t reps, double* out4) {
+    TB_CHECK(e && out4 && reps > 0 && first >= 0 && count > 0 && first + count <= e->max_games, TAK_ERR_BAD_ARG,
+             "net_forward_profile: bad argument");
+    TB_CHECK(e->net && e->net->arch != 0 && e->net->loaded, TAK_ERR_NO_NETWORK, "no network");
+    TB_CUDA(cudaSetDevice(e->device));
+    NetState& ns = *e->net;
+    const uint8_t* st = e->states.as<uint8_t>() + size_t(first) * e->state_bytes;
+    if (int r = net_forward(e, st, nullptr, count, nullptr)) return r;
+    NetProfile prof;
+    for (auto& ev : prof.ev) TB_CUDA(cudaEventCreate(&ev));
+    cudaEvent_t t0, t1;
+    TB_CUDA(cudaEventCreate(&t0));
+    TB_CUDA(cudaEventCreate(&t1));
+    double conv_ms = 0, total_ms = 0;
+    int launches = 0;
+    for (int i = 0; i < reps; ++i) {
+        prof.n = 0;
+        ns.profile = &prof;
+        TB_CUDA(cudaEventRecord(t0, e->stream));
+        int r = net_forward(e, st, nullptr, count, nullptr);
+        ns.profile = nullptr;
+        if (r) return r;
+        TB_CUDA(cudaEventRecord(t1, e->stream));
+        TB_CUDA(cudaEventSynchronize(t1));
+        float ms = 0;
+        TB_CUDA(cudaEventElapsedTime(&ms, t0, t1));
+        total_ms += ms;
+        for (int k = 0; k < prof.n; ++k) {
+            TB_CUDA(cudaEventElapsedTime(&ms, prof.ev[2 * k], prof.ev[2 * k + 1]));
+            conv_ms += ms;
+        }
+        launches = prof.n;
+    }
+    for (auto& ev : prof.ev) cudaEventDestroy(ev);
+    cudaEventDestroy(t0);
+    cudaEventDestroy(t1);
+    const double nsq = double(e->nsq);
+    double flop = 2.0 * nsq * 128.0 * 9.0 * (double(ns.c_in) + 2.0 * ns.blocks * 128.0);   // trunk
+    if (ns.arch == 6) flop += 2.0 * nsq * double(ns.policy_ch) * 128.0 * 9.0;                // policy conv
+    else flop += 2.0 * 128.0 * nsq * double(ns.policy_out);                                   // policy FC
+    flop += 2.0 * 128.0 * nsq;                                                                // value FC
+    out4[0] = total_ms / reps;
+    out4[1] = conv_ms / reps;
+    out4[2] = launches;
+    out4[3] = flop * count;
     return TAK_OK;
 }
 

@@ -11,7 +11,13 @@ struct ConvLayer {
     DevBuf bias;  // fp32 [128]
 };
 
+struct NetProfile {
+    cudaEvent_t ev[160];
+    int n = 0;
+};
+
 struct NetState {
+    NetProfile* profile = nullptr;         // set only by net_forward_profile
     int arch = 0;          // 0 DummyNet, 5 Net5, 6 Net6
     int n = 0;
     int c_in = 0;          // input_channels(n)

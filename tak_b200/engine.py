@@ -198,6 +198,11 @@ class Engine:
         check(self.lib.net_forward_timed(self._h, first, count, reps, C.byref(ms)))
         return ms.value
 
+    def net_forward_profile(self, first: int, count: int, reps: int):
+        out = (C.c_double * 4)()
+        check(self.lib.net_forward_profile(self._h, first, count, reps, out))
+        return {"ms_forward": out[0], "ms_conv": out[1], "conv_launches": int(out[2]), "flop": out[3]}
+
     # ---- alpha_tak::Node, batched -------------------------------------------------------------------------------
     def tree_reset(self, ids):
         p, k, _keep = _ids(ids)
@@ -244,6 +249,17 @@ class Engine:
                                      rew.ctypes.data_as(C.POINTER(C.c_float)), cap, C.byref(cnt)))
         k = cnt.value
         return mv[:k].copy(), vis[:k].copy(), pri[:k].copy(), rew[:k].copy()
+
+    def children_batch(self, ids, stride: int = 256):
+        """`Node::improved_policy` of many roots at once: (moves [n, stride], visits [n, stride], counts [n])."""
+        p, k, _keep = _ids(ids)
+        mv = np.zeros((k, stride), dtype=np.uint16)
+        vis = np.zeros((k, stride), dtype=np.uint32)
+        cnt = np.zeros(k, dtype=np.int32)
+        check(self.lib.mcts_children_batch(self._h, p, k, mv.ctypes.data_as(C.POINTER(C.c_uint16)),
+                                           vis.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                           cnt.ctypes.data_as(C.POINTER(C.c_int32)), stride))
+        return mv, vis, cnt
 
     def root(self, gid: int):
         v, vv, r = C.c_uint32(), C.c_uint32(), C.c_float()
