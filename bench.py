@@ -1,0 +1,351 @@
+#!/usr/bin/env python3
+"""bench.py -- 6x6 batched self-play (800 rollouts/move, random-init Net6) on N B200s: moves/s.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--games G] [--rollouts R] [--impl reference]
+  torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W      (N > 1)
+
+A "step" is one searched ply of every concurrent game: forced opening / instant-win scan / Dirichlet noise /
+R x (virtual rollout of all G games -> one batched Net6 evaluation -> devirtualise) / pick / replay record /
+re-root + play (train/src/self_play.rs:96-262).  `value` = searched plies per second over all ranks with everything
+resident in HBM; `e2e` = the same 800-rollout searches driven through the host-buffer C ABI (host game states in,
+host visit counts + picked moves out, copies inside the timed region).
+`--impl reference` times the CPU restatement of the reference's loop (oracle/ + fp32 PyTorch Net6, all host threads)
+on a bounded sample of the same workload; it is the only place bench.py executes oracle/ besides `cpu_baseline`.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "self-play MCTS moves/sec (6x6, 800 rollouts)"
+UNIT = "moves/s"
+FLOP_PER_EVAL_NET6 = 368_197_632
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"bf16_burst": p["bf16_tflops"], "bf16_sustained": p["bf16_tflops_sustained"], "hbm": p["hbm_gbs"],
+                "source": "MEASURED_PEAKS.json (measured)"}
+    return {"bf16_burst": 1590.0, "bf16_sustained": 1400.0, "hbm": 6650.0, "source": "B200_PROFILING.md fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device = device
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i",
+                 str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU restatement of the reference loop (oracle + fp32 torch Net6): cpu_baseline and --impl reference
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_selfplay_sample(rollouts_sample: int, full_rollouts: int, workers: int = 32, seed: int = 0):
+    """32 lock-step games (WORKERS, self_play.rs:94), one leaf per tree per step, one batched policy_eval per step.
+    Runs `rollouts_sample` of the `full_rollouts` rollouts of one ply and scales."""
+    import torch
+
+    import oracle
+    from oracle.net_ref import RefNet
+    from tak_b200 import weights as W
+
+    n = 6
+    net = RefNet(6, W.random_weights(6, seed=seed), device="cpu")
+    games, searches = [], []
+    for i in range(workers):
+        g = oracle.Game.with_komi(n, 2)
+        g.play("a1")
+        g.play("a6" if i % 2 else "f6")
+        games.append(g)
+        searches.append(oracle.Search(n))
+    cores = torch.get_num_threads()
+    t0 = time.perf_counter()
+    evals = 0
+    for _ in range(rollouts_sample):
+        pend = [i for i in range(workers) if searches[i].virtual_rollout(games[i]) == 0]
+        if not pend:
+            continue
+        x = np.stack([oracle.Game.from_state(searches[i].pending_state(0)).repr() for i in pend])
+        pol, val, _ = net.forward_mcts(torch.from_numpy(x))
+        pol, val = pol.numpy(), val.numpy()
+        for j, i in enumerate(pend):
+            searches[i].devirtualize(pol[j], float(val[j]))
+        evals += len(pend)
+    dt = time.perf_counter() - t0
+    moves_per_s = workers / (dt * full_rollouts / rollouts_sample)
+    return {"value": moves_per_s, "seconds": dt, "cores": cores, "evals": evals,
+            "sample": f"{workers} lock-step games x {rollouts_sample} of {full_rollouts} rollouts of one ply "
+                      f"(oracle MCTS + fp32 PyTorch Net6, batch {workers}), scaled by {full_rollouts}/{rollouts_sample}"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = max(8, min(args.rollouts, 40))
+    cpu_selfplay_sample(4, args.rollouts)  # warm-up (thread pools, oneDNN primitives)
+    for _ in range(max(0, args.warmup - 1)):
+        cpu_selfplay_sample(4, args.rollouts)
+    t0 = time.perf_counter()
+    res = [cpu_selfplay_sample(sample, args.rollouts) for _ in range(args.steps)]
+    dt = time.perf_counter() - t0
+    value = float(np.mean([r["value"] for r in res]))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "6x6 batched self-play, 800 rollouts/move, random-init Net6 (CPU restatement of the "
+                               "reference loop: the Rust reference cannot be built here)",
+                   "games": 32, "rollouts": args.rollouts},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": res[0]["cores"], "kind": "port",
+                         "sample": res[0]["sample"]},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+
+    import tak_b200 as tb
+    from tak_b200 import weights as W
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+
+    G, R, n = args.games, args.rollouts, 6
+    eng = tb.Engine(n, G, device=local, nodes_per_game=args.nodes_per_game, max_batch=G)
+    eng.net_create(6)
+    # weights: rank 0 draws them, NCCL broadcasts the fp32 blob over NVLink, every rank folds/packs its own copy
+    elems = W.blob_size(6)
+    blob_dev = torch.empty(elems, dtype=torch.float32, device=dev)
+    if rank == 0:
+        blob_dev.copy_(torch.from_numpy(W.random_weights(6, seed=0)))
+    if dist:
+        dist.broadcast(blob_dev, src=0)
+    torch.cuda.synchronize()
+    eng.net_load_weights_device(blob_dev.data_ptr(), elems)
+
+    def barrier():
+        torch.cuda.synchronize()
+        eng.sync()
+        if dist:
+            dist.barrier()
+
+    def max_over_ranks(x: float) -> float:
+        if not dist:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x: float) -> float:
+        if not dist:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---------------- device-resident self-play: `value` ----------------
+    eng.selfplay_begin(rollouts=R, half_komi=4, instant_win=1, exploit_ply=40, noise_ply=80, noise_alpha=0.2,
+                       noise_ratio=0.3, seed=0x7A4B, game_id_base=rank * G)
+    replay_bytes = 0
+    for _ in range(args.warmup):
+        eng.selfplay_step(1)
+        eng.selfplay_drain(4 * G)
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    t_wall = time.perf_counter()
+    dev_ms, launches, evals, plies, games_done = 0.0, 0, 0, 0, 0
+    for _ in range(args.steps):
+        st = eng.selfplay_step(1)
+        dev_ms += st.device_ms
+        launches += st.kernel_launches
+        evals += st.evals
+        plies += st.plies_played
+        games_done += st.games_completed
+    barrier()
+    wall_ms = 1e3 * (time.perf_counter() - t_wall)
+    clocks = sampler.stop()
+    recs = eng.selfplay_drain(16 * G)
+    # replay gather: fixed-size records, all-gathered over NCCL (outside the timed rollouts, as the trainer would)
+    if dist:
+        cnt = torch.tensor([len(recs)], dtype=torch.int64, device=dev)
+        counts = [torch.zeros_like(cnt) for _ in range(world)]
+        dist.all_gather(counts, cnt)
+        mx = int(max(c.item() for c in counts))
+        rec_bytes = C.sizeof(tb.ReplayRecord)
+        payload = torch.zeros(max(mx, 1) * rec_bytes, dtype=torch.uint8, device=dev)
+        if recs:
+            raw = np.frombuffer(b"".join(bytes(r) for r in recs), dtype=np.uint8)
+            payload[: raw.size].copy_(torch.from_numpy(raw.copy()))
+        gathered = [torch.empty_like(payload) for _ in range(world)]
+        dist.all_gather(gathered, payload)
+        replay_bytes = int(sum(c.item() for c in counts)) * rec_bytes
+    t_max = max_over_ranks(max(dev_ms, 0.0))           # device time (CUDA events on the engine stream), max over ranks
+    total_plies = sum_over_ranks(float(plies))
+    value = total_plies / (t_max / 1e3)
+    total_launches = int(sum_over_ranks(float(launches)))
+
+    # ---------------- end to end through the host-buffer ABI: `e2e` ----------------
+    ids = np.arange(G, dtype=np.int32)
+    host_states = eng.download(ids)  # the positions the self-play run reached, now living in host memory
+    state_bytes = {5: 288, 6: 384}.get(n, 384)
+    h2d = G * state_bytes + G * 4
+    stride = 256
+    d2h = G * stride * 6 + G * 4 + G * 2
+
+    def e2e_step():
+        eng.upload(ids, host_states)           # H2D: packed game states from pinned staging
+        eng.tree_reset(ids)
+        eng.rollouts(ids, R)                   # select -> encode -> Net6 -> backup, R times
+        mv, vis, cnt = eng.children_batch(ids, stride)   # D2H: improved policy (visit counts) of every root
+        picks = eng.pick_move(ids)             # D2H: the moves to play
+        return int(vis.sum()), picks
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, 2))
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_t = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = world * G * e2e_steps / e2e_t
+
+    # ---------------- roofline of the dominant kernel (conv3x3_tc_kernel), measured live ----------------
+    prof = eng.net_forward_profile(0, G, 10)
+    pk = peaks()
+    conv_flop = prof["flop"] - G * (2.0 * 128 * 36)  # all but the value FC runs in the conv kernel
+    achieved = conv_flop / (prof["ms_conv"] * 1e-3) / 1e12
+    roofline = {
+        "bound": "tensor", "kernel": "conv3x3_tc_kernel", "achieved": achieved, "peak": pk["bf16_burst"],
+        "unit": "TFLOP/s", "frac": achieved / pk["bf16_burst"], "traffic": None,
+        "peak_kind": "burst bf16 (kernel timed alone, CUDA events around each launch), " + pk["source"],
+        "avg_launch_us": 1e3 * prof["ms_conv"] / prof["conv_launches"],
+        "algorithmic_flop_per_launch": conv_flop / prof["conv_launches"],
+        "step_frac_sustained": (value / world) * R * FLOP_PER_EVAL_NET6 / (pk["bf16_sustained"] * 1e12),
+        "forward_ms": prof["ms_forward"], "conv_share_of_forward": prof["ms_conv"] / prof["ms_forward"],
+    }
+
+    line = None
+    if rank == 0:
+        cpu = cpu_selfplay_sample(max(8, min(R, 24)), R)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": t_max / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "6x6 batched self-play, 800 rollouts/move, random-init Net6 (configs[2])",
+                       "games_per_gpu": G, "rollouts": R, "noise": "dirichlet(0.2) x0.3 below ply 80",
+                       "pick": "visit-weighted sample below ply 40, argmax after", "instant_win": True,
+                       "l2": "inputs larger than L2: per rollout step the net streams >1 GB of activations "
+                             "(G x 49 slots x 256 B x 2 x 35 layers) and 10 MB of weights",
+                       "parallelism": f"games sharded over {world} rank(s), no collective in the rollout loop"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "what": "host game states -> tak_games_upload -> mcts_rollouts(800) -> mcts_children_batch + "
+                            "mcts_pick_move -> host"},
+            "gpu_launches": total_launches,
+            "roofline": roofline,
+            "cpu_baseline": {"value": cpu["value"], "unit": UNIT, "cores": cpu["cores"], "kind": "port",
+                             "sample": cpu["sample"]},
+            "clocks": clocks,
+            "extra": {"wall_ms_per_step": wall_ms / args.steps, "evals_per_step": evals / max(1, args.steps),
+                      "games_completed": games_done, "replay_records_gathered_bytes": replay_bytes,
+                      "net_evals_per_s": evals / (dev_ms / 1e3) if dev_ms else None},
+        }
+    eng.close()
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--games", type=int, default=4096, help="concurrent games per GPU")
+    ap.add_argument("--rollouts", type=int, default=800)
+    ap.add_argument("--nodes-per-game", type=int, default=1 << 18)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

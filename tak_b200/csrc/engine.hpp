@@ -86,6 +86,17 @@ struct tak_engine {
     tb::DevBuf states;       // [max_games][S]
     // scratch for the batched Game API
     tb::DevBuf d_ids, d_moves, d_counts, d_status, d_results, d_stage;
+    void* h_stage = nullptr;  // pinned host staging for upload / download
+    size_t h_stage_bytes = 0;
+    cudaError_t ensure_pinned(size_t need) {
+        if (need <= h_stage_bytes) return cudaSuccess;
+        if (h_stage) cudaFreeHost(h_stage);
+        h_stage = nullptr;
+        h_stage_bytes = 0;
+        cudaError_t err = cudaMallocHost(&h_stage, need);
+        if (err == cudaSuccess) h_stage_bytes = need;
+        return err;
+    }
     // perft
     static constexpr int PF_LEVELS = 13;
     struct PerftLevel {

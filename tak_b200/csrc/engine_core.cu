@@ -219,6 +219,7 @@ int32_t tak_engine_destroy(tak_engine_t* e) {
         b->release();
     for (auto& lv : e->pf_level)
         for (DevBuf* b : {&lv.children, &lv.counts, &lv.offsets, &lv.moves}) b->release();
+    if (e->h_stage) cudaFreeHost(e->h_stage);
     cudaStreamDestroy(e->stream);
     delete e;
     return TAK_OK;
@@ -249,16 +250,17 @@ int32_t tak_games_upload(tak_engine_t* e, const int32_t* ids, int32_t n, const t
     if (n == 0) return TAK_OK;
     TB_CUDA(cudaSetDevice(e->device));
     const size_t S = e->state_bytes;
-    std::vector<uint8_t> rec(S * n);
+    TB_CUDA(e->ensure_pinned(S * n));
+    uint8_t* rec = static_cast<uint8_t*>(e->h_stage);
     for (int i = 0; i < n; ++i) {
         TB_CHECK(states[i].n == e->n, TAK_ERR_BAD_ARG, "state %d has board size %d, engine has %d", i, states[i].n,
                  e->n);
-        pack_state(e->n, states[i], rec.data() + S * i);
+        pack_state(e->n, states[i], rec + S * i);
     }
     // one H2D copy of the packed records + one scatter kernel
     TB_CUDA(e->d_stage.ensure(S * n));
     TB_CUDA(e->d_ids.ensure(size_t(n) * 4));
-    TB_CUDA(cudaMemcpyAsync(e->d_stage.p, rec.data(), S * n, cudaMemcpyHostToDevice, e->stream));
+    TB_CUDA(cudaMemcpyAsync(e->d_stage.p, rec, S * n, cudaMemcpyHostToDevice, e->stream));
     TB_CUDA(cudaMemcpyAsync(e->d_ids.p, ids, size_t(n) * 4, cudaMemcpyHostToDevice, e->stream));
     k_scatter_records<<<(n * int(S / 16) + 255) / 256, 256, 0, e->stream>>>(
         e->d_stage.as<uint4>(), e->states.as<uint4>(), e->d_ids.as<int>(), n, int(S / 16), 1);
@@ -274,7 +276,8 @@ int32_t tak_games_download(tak_engine_t* e, const int32_t* ids, int32_t n, tak_s
     if (n == 0) return TAK_OK;
     TB_CUDA(cudaSetDevice(e->device));
     const size_t S = e->state_bytes;
-    std::vector<uint8_t> rec(S * n);
+    TB_CUDA(e->ensure_pinned(S * n));
+    uint8_t* rec = static_cast<uint8_t*>(e->h_stage);
     TB_CUDA(e->d_stage.ensure(S * n));
     TB_CUDA(e->d_ids.ensure(size_t(n) * 4));
     TB_CUDA(cudaMemcpyAsync(e->d_ids.p, ids, size_t(n) * 4, cudaMemcpyHostToDevice, e->stream));
@@ -282,9 +285,9 @@ int32_t tak_games_download(tak_engine_t* e, const int32_t* ids, int32_t n, tak_s
         e->d_stage.as<uint4>(), e->states.as<uint4>(), e->d_ids.as<int>(), n, int(S / 16), 0);
     e->launches++;
     TB_CUDA(cudaGetLastError());
-    TB_CUDA(cudaMemcpyAsync(rec.data(), e->d_stage.p, S * n, cudaMemcpyDeviceToHost, e->stream));
+    TB_CUDA(cudaMemcpyAsync(rec, e->d_stage.p, S * n, cudaMemcpyDeviceToHost, e->stream));
     TB_CUDA(cudaStreamSynchronize(e->stream));
-    for (int i = 0; i < n; ++i) unpack_state(e->n, rec.data() + S * i, states[i]);
+    for (int i = 0; i < n; ++i) unpack_state(e->n, rec + S * i, states[i]);
     return TAK_OK;
 }
 
