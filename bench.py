@@ -289,7 +289,7 @@ def run_b200(args):
     conv_flop = prof["flop"] - G * (2.0 * 128 * 36)  # all but the value FC runs in the conv kernel
     achieved = conv_flop / (prof["ms_conv"] * 1e-3) / 1e12
     roofline = {
-        "bound": "tensor", "kernel": "conv3x3_tc_kernel", "achieved": achieved, "peak": pk["bf16_burst"],
+        "bound": "tensor", "kernel": "conv3x3_tc2_kernel", "achieved": achieved, "peak": pk["bf16_burst"],
         "unit": "TFLOP/s", "frac": achieved / pk["bf16_burst"], "traffic": None,
         "peak_kind": "burst bf16 (kernel timed alone, CUDA events around each launch), " + pk["source"],
         "avg_launch_us": 1e3 * prof["ms_conv"] / prof["conv_launches"],

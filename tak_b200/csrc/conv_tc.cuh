@@ -16,10 +16,12 @@
 // GEMM view per CTA tile: D[256 slots x 128 c_out] += A[256 x 1152] * W[128 x 1152]^T as two
 // M=128,N=128 accumulators in TMEM (fp32), 9 taps x 8 K-steps of K=16 each.
 //
-// Warp roles (320 threads, 1 persistent CTA per SM):
-//   warp 0     bulk-copy producer (activation tile + halo, weight stages)      -> mbarrier tx
+// Warp roles (352 threads, 1 persistent CTA per SM):
+//   warp 0     bulk-copy producer of the activation tile (+ halo)             -> mbarrier tx
+//   warp 10    bulk-copy producer of the weight stages                         -> mbarrier tx
 //   warp 1     TMEM allocator + single-thread tcgen05.mma issuer               -> tcgen05.commit
-//   warps 2-9  epilogue: tcgen05.ld -> +bias (+residual) -> ReLU -> pad mask -> bf16 slot planes
+//   warps 2-9  epilogue: residual prefetch, tcgen05.ld (software pipelined) -> +bias (+residual) -> ReLU ->
+//              pad mask -> bf16 slot planes
 // Double-buffered activation tiles and TMEM accumulators let the epilogue of tile i overlap the MMAs of
 // tile i+1; weights stream through a 5-stage ring (they stay L2 resident: 288 KiB per layer).
 #pragma once
@@ -42,7 +44,7 @@ constexpr int CONV_A_BYTES = CONV_ROWS * 16 * CONV_CHUNKS;  // 73728
 constexpr int CONV_W_STAGE_BYTES = 8 * 128 * 16;            // 16384: 64 c_in x 128 c_out
 constexpr int CONV_W_STAGES = 4;
 constexpr int CONV_STAGES_PER_LAYER = 18;                   // 9 taps x 2 K halves
-constexpr int CONV_THREADS = 320;
+constexpr int CONV_THREADS = 352;   // 11 warps: A producer, MMA, 8 epilogue, W producer
 constexpr int CONV_SMEM_BYTES = 2 * CONV_A_BYTES + CONV_W_STAGES * CONV_W_STAGE_BYTES + 1024;
 
 enum ConvMode : int {
@@ -77,6 +79,7 @@ __device__ __forceinline__ bool conv_slot_valid(int slot, int pitch, int n_board
     return rel >= 0 && board < n_boards && y >= 1 && x < pitch - 1;
 }
 
+template <int MODE>
 static __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_tc_kernel(const ConvParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* a_buf = smem;                                        // 2 x CONV_A_BYTES
@@ -118,13 +121,15 @@ static __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_tc_kernel(cons
     const size_t plane_bytes = static_cast<size_t>(p.S) * 16;
 
     if (warp == 0) {
-        // ===================== producer =====================
+        // ===================== activation-tile producer =====================
         if (lane == 0) {
-            uint32_t wcount = 0;
             int it = 0;
             for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
                 const int ab = it & 1;
                 const uint32_t aph = (it >> 1) & 1;
+#if defined(CONV_EXP) && (CONV_EXP & 4)
+                if (it >= 2) break;
+#endif
                 mbar_wait(BAR(2 + ab), aph ^ 1);
                 mbar_expect_tx(BAR(0 + ab), CONV_A_BYTES);
                 const int row0 = CONV_GUARD + tile * CONV_TILE_M - CONV_HALO_ROWS;  // >= 0
@@ -132,6 +137,16 @@ static __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_tc_kernel(cons
                 const uint32_t dst = smem_u32(a_buf + ab * CONV_A_BYTES);
                 for (int c = 0; c < CONV_CHUNKS; ++c)
                     bulk_g2s(dst + c * (CONV_ROWS * 16), src + c * plane_bytes, CONV_ROWS * 16, BAR(0 + ab));
+            }
+        }
+    } else if (warp == 10) {
+        // ===================== weight-stage producer =====================
+        if (lane == 0) {
+            uint32_t wcount = 0;
+#if defined(CONV_EXP) && (CONV_EXP & 1)
+            if (false)
+#endif
+            for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
                 for (int st = 0; st < CONV_STAGES_PER_LAYER; ++st, ++wcount) {
                     const int s = wcount % CONV_W_STAGES;
                     const uint32_t ph = (wcount / CONV_W_STAGES) & 1;
@@ -153,6 +168,9 @@ static __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_tc_kernel(cons
                 const int ab = it & 1;
                 const uint32_t ph2 = (it >> 1) & 1;
                 mbar_wait(BAR(14 + ab), ph2 ^ 1);  // accumulator stage drained by the epilogue
+#if defined(CONV_EXP) && (CONV_EXP & 4)
+                if (it < 2)
+#endif
                 mbar_wait(BAR(0 + ab), ph2);       // activation tile landed
                 tc_fence_after();
                 const uint32_t a_base = smem_u32(a_buf + ab * CONV_A_BYTES);
@@ -160,7 +178,9 @@ static __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_tc_kernel(cons
                 for (int st = 0; st < CONV_STAGES_PER_LAYER; ++st, ++wcount) {
                     const int s = wcount % CONV_W_STAGES;
                     const uint32_t ph = (wcount / CONV_W_STAGES) & 1;
+#if !(defined(CONV_EXP) && (CONV_EXP & 1))
                     mbar_wait(BAR(4 + s), ph);
+#endif
                     tc_fence_after();
                     const int tap = st >> 1, half = st & 1;
                     const int shift = (tap / 3 - 1) * p.pitch + (tap % 3 - 1);
@@ -177,13 +197,15 @@ static __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_tc_kernel(cons
                             umma_bf16(d_base + t * 128, adesc, bdesc, idesc, (st | j) != 0);
                         }
                     }
+#if !(defined(CONV_EXP) && (CONV_EXP & 1))
                     umma_commit(BAR(8 + s));  // weight stage free once these MMAs retire
+#endif
                 }
                 umma_commit(BAR(12 + ab));  // accumulators ready
                 umma_commit(BAR(2 + ab));   // activation tile free
             }
         }
-    } else {
+    } else if (warp >= 2 && warp < 10) {
         // ===================== epilogue (8 warps, one thread per slot row) =====================
         const int ew = warp - 2;          // 0..7
         const int t = ew >> 2;            // accumulator tile 0/1
@@ -195,20 +217,34 @@ static __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_tc_kernel(cons
             const uint32_t ph2 = (it >> 1) & 1;
             const int slot = CONV_GUARD + tile * CONV_TILE_M + row;
             const bool valid = conv_slot_valid(slot, p.pitch, p.n_boards);
+            // the residual does not depend on the MMAs: fetch the whole row before waiting for the accumulator
+            uint4 res[16];
+            if (MODE == CONV_RES_RELU) {
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    res[c] = make_uint4(0, 0, 0, 0);
+                    if (valid) res[c] = __ldg(reinterpret_cast<const uint4*>(p.res + (static_cast<size_t>(c) * p.S + slot) * 8));
+                }
+            }
             mbar_wait(BAR(12 + ab), ph2);
             tc_fence_after();
+#if defined(CONV_EXP) && (CONV_EXP & 2)
+            if (p.S != -12345) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(BAR(14 + ab)); continue; }
+#endif
             const uint32_t taddr = tmem_base + ab * 256 + t * 128 + (static_cast<uint32_t>(quarter * 32) << 16);
-#pragma unroll 1
+            uint32_t r[2][32];
+            tmem_ld32(taddr, r[0]);
+#pragma unroll
             for (int cc = 0; cc < 4; ++cc) {
-                uint32_t r[32];
-                tmem_ld32(taddr + cc * 32, r);
                 tmem_ld_wait();
-                if (p.mode == CONV_LOGITS_F32) {
+                if (cc < 3) tmem_ld32(taddr + (cc + 1) * 32, r[(cc + 1) & 1]);  // next chunk in flight while this one is processed
+                const uint32_t(&rc)[32] = r[cc & 1];
+                if (MODE == CONV_LOGITS_F32) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const int ch = cc * 32 + j;
                         if (ch < p.out_ch_valid) {
-                            float v = __uint_as_float(r[j]) + s_bias[ch];
+                            float v = __uint_as_float(rc[j]) + s_bias[ch];
                             p.out_f32[static_cast<size_t>(p.out_ch_offset + ch) * p.S + slot] = valid ? v : 0.0f;
                         }
                     }
@@ -218,12 +254,9 @@ static __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_tc_kernel(cons
                         const int chunk = cc * 4 + q;
                         float v[8];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[q * 8 + j]) + s_bias[chunk * 8 + j];
-                        const size_t off = (static_cast<size_t>(chunk) * p.S + slot) * 8;
-                        if (p.mode == CONV_RES_RELU) {
-                            uint4 rv = make_uint4(0, 0, 0, 0);
-                            if (valid) rv = *reinterpret_cast<const uint4*>(p.res + off);
-                            const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&rv);
+                        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(rc[q * 8 + j]) + s_bias[chunk * 8 + j];
+                        if (MODE == CONV_RES_RELU) {
+                            const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&res[chunk]);
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
                                 float2 f = __bfloat1622float2(rb[j]);
@@ -239,7 +272,7 @@ static __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_tc_kernel(cons
                             float b = valid ? fmaxf(v[2 * j + 1], 0.0f) : 0.0f;
                             ob[j] = __floats2bfloat162_rn(a, b);
                         }
-                        *reinterpret_cast<uint4*>(p.out + off) = ov;
+                        *reinterpret_cast<uint4*>(p.out + (static_cast<size_t>(chunk) * p.S + slot) * 8) = ov;
                     }
                 }
             }
@@ -258,14 +291,22 @@ static __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_tc_kernel(cons
 inline cudaError_t conv3x3_tc_launch(const ConvParams& p, int num_sms, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e =
-            cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV_SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(conv3x3_tc_kernel<CONV_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             CONV_SMEM_BYTES);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(conv3x3_tc_kernel<CONV_RES_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     CONV_SMEM_BYTES);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(conv3x3_tc_kernel<CONV_LOGITS_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     CONV_SMEM_BYTES);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
     int grid = p.tiles < num_sms ? p.tiles : num_sms;
     if (grid <= 0) return cudaSuccess;
-    conv3x3_tc_kernel<<<grid, CONV_THREADS, CONV_SMEM_BYTES, stream>>>(p);
+    if (p.mode == CONV_RELU) conv3x3_tc_kernel<CONV_RELU><<<grid, CONV_THREADS, CONV_SMEM_BYTES, stream>>>(p);
+    else if (p.mode == CONV_RES_RELU) conv3x3_tc_kernel<CONV_RES_RELU><<<grid, CONV_THREADS, CONV_SMEM_BYTES, stream>>>(p);
+    else conv3x3_tc_kernel<CONV_LOGITS_F32><<<grid, CONV_THREADS, CONV_SMEM_BYTES, stream>>>(p);
     return cudaGetLastError();
 }
 

@@ -5,6 +5,7 @@
 
 #include <cmath>
 
+#include "conv_tc2.cuh"
 #include "net_kernels.cuh"
 
 namespace tb {
@@ -21,7 +22,8 @@ int64_t net_blob_elems(const NetState& ns) {
     return total;
 }
 
-// fold BN(eval) into conv weight/bias and pack for conv_tc: [stage = tap*2+half][kchunk 8][c_out 128][8 c_in]
+// fold BN(eval) into conv weight/bias and pack for conv_tc2 (CTA pair, resident weights):
+//   [rank = c_out/64][stage = tap*2+half][kchunk 8][c_out%64][8 c_in]   (2 x 144 KiB)
 static void pack_conv(const float* w /*[co][ci][3][3]*/, const float* b, const float* bn /*gamma,beta,mean,var or null*/,
                       int c_out, int c_in, int co_base, std::vector<__nv_bfloat16>& packed, std::vector<float>& bias) {
     packed.assign(size_t(18) * 8 * 128 * 8, __float2bfloat16(0.f));
@@ -40,7 +42,8 @@ static void pack_conv(const float* w /*[co][ci][3][3]*/, const float* b, const f
             for (int tap = 0; tap < 9; ++tap) {
                 const float v = float(double(w[(size_t(co) * c_in + ci) * 9 + tap]) * scale);
                 const int half = ci >> 6, kc = (ci & 63) >> 3, j = ci & 7;
-                packed[(((size_t(tap * 2 + half) * 8 + kc) * 128) + col) * 8 + j] = __float2bfloat16(v);
+                packed[((((size_t(col >> 6) * 18 + (tap * 2 + half)) * 8 + kc) * 64) + (col & 63)) * 8 + j] =
+                    __float2bfloat16(v);
             }
     }
 }
@@ -160,7 +163,7 @@ static int forward_t(tak_engine* e, const uint8_t* d_states, const int* d_index,
         p.w = L.w.as<__nv_bfloat16>(); p.bias = L.bias.as<float>();
         p.S = S; p.tiles = tiles; p.n_boards = boards; p.pitch = P; p.mode = mode;
         p.out_ch_offset = ch_off; p.out_ch_valid = ch_valid;
-        TB_CUDA(conv3x3_tc_launch(p, e->num_sms, e->stream));
+        TB_CUDA(conv3x3_tc2_launch(p, e->num_sms, e->stream));
         e->launches++;
         if (prof) {
             TB_CUDA(cudaEventRecord(prof->ev[2 * prof->n + 1], e->stream));

@@ -6,7 +6,7 @@
 #pragma once
 #include <cuda_bf16.h>
 
-#include "conv_tc.cuh"
+#include "conv_tc2.cuh"
 #include "tak_device.cuh"
 
 namespace tb {

@@ -7,7 +7,7 @@
 #include <cstring>
 #include <vector>
 
-#include "conv_tc.cuh"
+#include "conv_tc2.cuh"
 
 using namespace tb;
 
@@ -72,7 +72,8 @@ int main(int argc, char** argv) {
                     h_res[((size_t)(ci >> 3) * S + slot) * 8 + (ci & 7)] = __float2bfloat16(urand() - 0.5f);
                 }
             }
-    std::vector<__nv_bfloat16> h_wplain((size_t)128 * 9 * 128), h_wpacked((size_t)18 * 8 * 128 * 8);
+    std::vector<__nv_bfloat16> h_wplain((size_t)128 * 9 * 128), h_wpacked((size_t)18 * 8 * 128 * 8),
+        h_wpacked2((size_t)18 * 8 * 128 * 8);
     std::vector<float> h_bias(128);
     for (auto& v : h_bias) v = urand() - 0.5f;
     for (int co = 0; co < 128; ++co)
@@ -82,15 +83,19 @@ int main(int argc, char** argv) {
                 h_wplain[((size_t)co * 9 + tap) * 128 + ci] = w;
                 int half = ci >> 6, kc = (ci & 63) >> 3, j = ci & 7;
                 h_wpacked[((((size_t)(tap * 2 + half) * 8 + kc) * 128) + co) * 8 + j] = w;
+                // CTA-pair layout: [rank = co/64][stage][kc][co%64][8]
+                h_wpacked2[(((((size_t)(co >> 6) * 18 + (tap * 2 + half)) * 8 + kc) * 64) + (co & 63)) * 8 + j] = w;
             }
 
-    __nv_bfloat16 *d_in, *d_res, *d_out, *d_wplain, *d_wpacked;
+    __nv_bfloat16 *d_in, *d_res, *d_out, *d_wplain, *d_wpacked, *d_wpacked2;
     float *d_bias, *d_ref, *d_logits;
     CK(cudaMalloc(&d_in, act_elems * 2));
     CK(cudaMalloc(&d_res, act_elems * 2));
     CK(cudaMalloc(&d_out, act_elems * 2));
     CK(cudaMalloc(&d_wplain, h_wplain.size() * 2));
     CK(cudaMalloc(&d_wpacked, h_wpacked.size() * 2));
+    CK(cudaMalloc(&d_wpacked2, h_wpacked2.size() * 2));
+    CK(cudaMemcpy(d_wpacked2, h_wpacked2.data(), h_wpacked2.size() * 2, cudaMemcpyHostToDevice));
     CK(cudaMalloc(&d_bias, 512));
     CK(cudaMalloc(&d_ref, (size_t)S * 128 * 4));
     CK(cudaMalloc(&d_logits, (size_t)128 * S * 4));
@@ -108,15 +113,19 @@ int main(int argc, char** argv) {
     CK(cudaMemcpy(h_ref.data(), d_ref, h_ref.size() * 4, cudaMemcpyDeviceToHost));
 
     int fails = 0;
+    const int impl_only = argc > 3 ? atoi(argv[3]) : 0;
+    for (int impl = 1; impl <= 2; ++impl)
     for (int sms : {prop.multiProcessorCount, 24}) {
+        if (impl_only && impl != impl_only) continue;
         for (int mode = 2; mode >= 0; --mode) {
             ConvParams p{};
-            p.in = d_in; p.res = d_res; p.out = d_out; p.out_f32 = d_logits; p.w = d_wpacked; p.bias = d_bias;
+            p.in = d_in; p.res = d_res; p.out = d_out; p.out_f32 = d_logits; p.w = impl == 1 ? d_wpacked : d_wpacked2;
+            p.bias = d_bias;
             p.S = S; p.tiles = tiles; p.n_boards = n_boards; p.pitch = pitch; p.mode = mode;
             p.out_ch_offset = 0; p.out_ch_valid = 128;
             CK(cudaMemset(d_out, 0xFF, act_elems * 2));
             CK(cudaMemset(d_logits, 0xFF, (size_t)128 * S * 4));
-            CK(conv3x3_tc_launch(p, sms, 0));
+            if (impl == 1) CK(conv3x3_tc_launch(p, sms, 0)); else CK(conv3x3_tc2_launch(p, sms, 0));
             cudaError_t e = cudaDeviceSynchronize();
             if (e != cudaSuccess) {
                 printf("mode %d sms %d: kernel failed: %s\n", mode, sms, cudaGetErrorString(e));
@@ -164,8 +173,7 @@ int main(int argc, char** argv) {
                     }
                 }
             }
-            printf("mode %d grid<=%3d: max|err| %.3e (max|ref| %.3f) bad %ld%s\n", mode, sms, maxerr, maxref, bad,
-                   bad ? "  <-- FAIL" : "  ok");
+            printf("impl %d mode %d grid<=%3d: max|err| %.3e (max|ref| %.3f) bad %ld%s\n", impl, mode, sms, maxerr, maxref, bad, bad ? "  <-- FAIL" : "  ok");
             if (bad) {
                 ++fails;
                 int rel = first_bad_slot - CONV_GUARD;
@@ -176,18 +184,22 @@ int main(int argc, char** argv) {
     }
 
     // ---- timing (mode 1, the res-block conv) ----
-    {
+    for (int impl = 1; impl <= 2; ++impl) {
+        if (impl_only && impl != impl_only) continue;
         ConvParams p{};
-        p.in = d_in; p.res = d_res; p.out = d_out; p.out_f32 = d_logits; p.w = d_wpacked; p.bias = d_bias;
+        p.in = d_in; p.res = d_res; p.out = d_out; p.out_f32 = d_logits; p.w = impl == 1 ? d_wpacked : d_wpacked2;
+        p.bias = d_bias;
         p.S = S; p.tiles = tiles; p.n_boards = n_boards; p.pitch = pitch; p.mode = 1;
         p.out_ch_valid = 128;
+        auto launch = [&]() { return impl == 1 ? conv3x3_tc_launch(p, prop.multiProcessorCount, 0)
+                                               : conv3x3_tc2_launch(p, prop.multiProcessorCount, 0); };
         cudaEvent_t e0, e1;
         CK(cudaEventCreate(&e0));
         CK(cudaEventCreate(&e1));
-        for (int i = 0; i < 5; ++i) CK(conv3x3_tc_launch(p, prop.multiProcessorCount, 0));
+        for (int i = 0; i < 5; ++i) CK(launch());
         CK(cudaEventRecord(e0));
         const int reps = 50;
-        for (int i = 0; i < reps; ++i) CK(conv3x3_tc_launch(p, prop.multiProcessorCount, 0));
+        for (int i = 0; i < reps; ++i) CK(launch());
         CK(cudaEventRecord(e1));
         CK(cudaEventSynchronize(e1));
         float ms;
@@ -195,8 +207,8 @@ int main(int argc, char** argv) {
         double per = ms / reps * 1e-3;
         double useful = 2.0 * n_boards * N * N * 128.0 * 1152.0;
         double issued = 2.0 * tiles * 256.0 * 128.0 * 1152.0;
-        printf("timing: %.1f us/layer  useful %.1f TFLOP/s  issued %.1f TFLOP/s\n", per * 1e6, useful / per * 1e-12,
-               issued / per * 1e-12);
+        printf("timing impl %d: %.1f us/layer  useful %.1f TFLOP/s  issued %.1f TFLOP/s\n", impl, per * 1e6,
+               useful / per * 1e-12, issued / per * 1e-12);
     }
     printf(fails ? "SELFTEST FAILED\n" : "SELFTEST PASSED\n");
     return fails ? 1 : 0;

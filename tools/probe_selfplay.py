@@ -1,7 +1,7 @@
 import sys, time; sys.path.insert(0,'.')
 import numpy as np, tak_b200 as tb
 from tak_b200 import weights as W
-for G in (4096,):
+for G in (4096, 8192):
     eng = tb.Engine(6, G, nodes_per_game=1<<18, max_batch=G)
     eng.net_create(6); eng.net_load_weights(W.random_weights(6, seed=0))
     eng.reset(0, G, 4)
