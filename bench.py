@@ -167,6 +167,7 @@ def run_b200(args):
     import torch
 
     import tak_b200 as tb
+    from tak_b200 import parallel as par
     from tak_b200 import weights as W
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -187,11 +188,7 @@ def run_b200(args):
     eng.net_create(6)
     # weights: rank 0 draws them, NCCL broadcasts the fp32 blob over NVLink, every rank folds/packs its own copy
     elems = W.blob_size(6)
-    blob_dev = torch.empty(elems, dtype=torch.float32, device=dev)
-    if rank == 0:
-        blob_dev.copy_(torch.from_numpy(W.random_weights(6, seed=0)))
-    if dist:
-        dist.broadcast(blob_dev, src=0)
+    blob_dev = par.broadcast_weights(W.random_weights(6, seed=0) if rank == 0 else None, elems, dev)
     torch.cuda.synchronize()
     eng.net_load_weights_device(blob_dev.data_ptr(), elems)
 
@@ -202,22 +199,14 @@ def run_b200(args):
             dist.barrier()
 
     def max_over_ranks(x: float) -> float:
-        if not dist:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return par.max_over_ranks(x, dev)
 
     def sum_over_ranks(x: float) -> float:
-        if not dist:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+        return par.sum_over_ranks(x, dev)
 
     # ---------------- device-resident self-play: `value` ----------------
     eng.selfplay_begin(rollouts=R, half_komi=4, instant_win=1, exploit_ply=40, noise_ply=80, noise_alpha=0.2,
-                       noise_ratio=0.3, seed=0x7A4B, game_id_base=rank * G)
+                       noise_ratio=0.3, seed=0x7A4B, game_id_base=par.game_id_base(rank, G))
     replay_bytes = 0
     for _ in range(args.warmup):
         eng.selfplay_step(1)
@@ -239,19 +228,8 @@ def run_b200(args):
     clocks = sampler.stop()
     recs = eng.selfplay_drain(16 * G)
     # replay gather: fixed-size records, all-gathered over NCCL (outside the timed rollouts, as the trainer would)
-    if dist:
-        cnt = torch.tensor([len(recs)], dtype=torch.int64, device=dev)
-        counts = [torch.zeros_like(cnt) for _ in range(world)]
-        dist.all_gather(counts, cnt)
-        mx = int(max(c.item() for c in counts))
-        rec_bytes = C.sizeof(tb.ReplayRecord)
-        payload = torch.zeros(max(mx, 1) * rec_bytes, dtype=torch.uint8, device=dev)
-        if recs:
-            raw = np.frombuffer(b"".join(bytes(r) for r in recs), dtype=np.uint8)
-            payload[: raw.size].copy_(torch.from_numpy(raw.copy()))
-        gathered = [torch.empty_like(payload) for _ in range(world)]
-        dist.all_gather(gathered, payload)
-        replay_bytes = int(sum(c.item() for c in counts)) * rec_bytes
+    all_recs = par.gather_replay(recs, tb.ReplayRecord, dev)
+    replay_bytes = len(all_recs) * C.sizeof(tb.ReplayRecord)
     t_max = max_over_ranks(max(dev_ms, 0.0))           # device time (CUDA events on the engine stream), max over ranks
     total_plies = sum_over_ranks(float(plies))
     value = total_plies / (t_max / 1e3)

@@ -1,0 +1,72 @@
+"""Multi-GPU plumbing of the self-play path (one process per GPU, torch.distributed).
+
+Games never interact, so each rank owns a contiguous block of global game ids, its own search trees and a network
+replica; the rollout loop has no collective.  Exactly two exchanges exist:
+  * `broadcast_weights`  rank 0's fp32 weight blob -> every rank (NCCL broadcast over NVLink; gloo in CPU tests)
+  * `gather_replay`      fixed-size replay records of all ranks -> every rank (all_gather of padded byte tensors)
+The reference has no distributed code (single process, single GPU: alpha-tak/src/lib.rs:21-23).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Sequence
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def game_id_base(rank: int, games_per_rank: int) -> int:
+    """Global id of local game 0: ranks own [rank*G, (rank+1)*G)."""
+    return rank * games_per_rank
+
+
+def broadcast_weights(blob: np.ndarray | None, elems: int, device: torch.device, src: int = 0) -> torch.Tensor:
+    """Returns the fp32 blob as a tensor on `device` on every rank (only `src` needs to pass `blob`)."""
+    t = torch.empty(elems, dtype=torch.float32, device=device)
+    if not dist.is_initialized() or dist.get_rank() == src:
+        assert blob is not None and blob.size == elems
+        t.copy_(torch.from_numpy(np.ascontiguousarray(blob, dtype=np.float32)))
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.broadcast(t, src=src)
+    return t
+
+
+def gather_replay(records: Sequence, record_type, device: torch.device) -> List:
+    """all_gather of ragged lists of fixed-size ctypes records; returns the concatenation in rank order."""
+    size = C.sizeof(record_type)
+    raw = b"".join(bytes(r) for r in records)
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return list(records)
+    world = dist.get_world_size()
+    cnt = torch.tensor([len(records)], dtype=torch.int64, device=device)
+    counts = [torch.zeros_like(cnt) for _ in range(world)]
+    dist.all_gather(counts, cnt)
+    counts = [int(c.item()) for c in counts]
+    mx = max(max(counts), 1)
+    payload = torch.zeros(mx * size, dtype=torch.uint8, device=device)
+    if raw:
+        payload[: len(raw)].copy_(torch.from_numpy(np.frombuffer(raw, dtype=np.uint8).copy()))
+    gathered = [torch.empty_like(payload) for _ in range(world)]
+    dist.all_gather(gathered, payload)
+    out = []
+    for r, c in enumerate(counts):
+        buf = gathered[r][: c * size].cpu().numpy().tobytes()
+        out += [record_type.from_buffer_copy(buf[i * size:(i + 1) * size]) for i in range(c)]
+    return out
+
+
+def max_over_ranks(x: float, device: torch.device) -> float:
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return x
+    t = torch.tensor([x], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(x: float, device: torch.device) -> float:
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return x
+    t = torch.tensor([x], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
