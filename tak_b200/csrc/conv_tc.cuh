@@ -161,7 +161,11 @@ static __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_tc_kernel(cons
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
+#if defined(CONV_EXP) && (CONV_EXP & 128)
+            constexpr uint32_t idesc = umma_idesc_bf16_f32(128, 256);  // experiment: issue-rate probe (garbage B)
+#else
             constexpr uint32_t idesc = umma_idesc_bf16_f32(128, 128);
+#endif
             uint32_t wcount = 0;
             int it = 0;
             for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
@@ -194,7 +198,12 @@ static __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_tc_kernel(cons
                                 a_base + chunk * (CONV_ROWS * 16) + (CONV_HALO_ROWS + t * 128 + shift) * 16;
                             const uint64_t adesc = umma_desc_kmajor_noswz(a_addr, CONV_ROWS * 16, 128);
                             const uint64_t bdesc = umma_desc_kmajor_noswz(w_base + j * 2 * (128 * 16), 128 * 16, 128);
+#if defined(CONV_EXP) && (CONV_EXP & 128)
+                            const uint64_t bprobe = umma_desc_kmajor_noswz(smem_u32(a_buf) + j * 8192, 256 * 16, 128);
+                            umma_bf16(d_base, adesc, bprobe, idesc, (st | j) != 0);
+#else
                             umma_bf16(d_base + t * 128, adesc, bdesc, idesc, (st | j) != 0);
+#endif
                         }
                     }
 #if !(defined(CONV_EXP) && (CONV_EXP & 1))

@@ -138,7 +138,13 @@ static __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(C2_THREADS, 1
     } else if (warp == 1) {
         // ===================== MMA issuer (leader CTA only) =====================
         if (rank == 0 && lane == 0) {
+#if defined(CONV_EXP) && (CONV_EXP & 128)
+            constexpr uint32_t idesc = umma_idesc_bf16_f32(256, 256);  // experiment: issue-rate probe (garbage B)
+#elif defined(CONV_EXP) && (CONV_EXP & 256)
+            constexpr uint32_t idesc = umma_idesc_bf16_f32(256, 64);
+#else
             constexpr uint32_t idesc = umma_idesc_bf16_f32(256, 128);
+#endif
             int it = 0;
             for (int tile = pair; tile < p.tiles; tile += n_pairs, ++it) {
                 const int ab = it & 1;
@@ -150,7 +156,11 @@ static __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(C2_THREADS, 1
                 mbar_wait_cluster(BAR(C2B_A_READY + ab), (it >> 1) & 1);          // both A tiles landed
                 tc_fence_after();
                 const uint32_t a_base = smem_u32(a_buf + ab * C2_A_BYTES);
+#if defined(CONV_EXP) && (CONV_EXP & 128)
+                const uint32_t d_addr = tmem_base + (as & 1) * 256;
+#else
                 const uint32_t d_addr = tmem_base + as * 128;
+#endif
 #pragma unroll 1
                 for (int st = 0; st < CONV_STAGES_PER_LAYER; ++st) {
                     const int tap = st >> 1, half = st & 1;
@@ -158,7 +168,13 @@ static __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(C2_THREADS, 1
                         mbar_wait_cluster(BAR(C2B_W_READY + tap), 0);
                         tc_fence_after();
                     }
+#if defined(CONV_EXP) && (CONV_EXP & 32)
+                    const int shift = 0;  // experiment: every tap reads the 128 B-aligned window
+#elif defined(CONV_EXP) && (CONV_EXP & 64)
+                    const int shift = (tap / 3 - 1) * 8;  // experiment: aligned but distinct windows
+#else
                     const int shift = (tap / 3 - 1) * p.pitch + (tap % 3 - 1);
+#endif
                     const uint32_t w_base = smem_u32(w_buf + st * C2_W_STAGE_BYTES);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {

@@ -1,0 +1,390 @@
+// 3x3 "same" convolution of the AlphaTak residual tower as a tcgen05 implicit GEMM (sm_100a), third generation.
+//
+// Replaces, per layer, the cuDNN conv + BatchNorm(eval) + ReLU (+ residual add) library calls the reference issues
+// through tch-rs (alpha-tak/src/model/net6.rs:70-78, res_block.rs:13-23, policy head net6.rs:99-103).  BatchNorm is
+// folded into the weights/bias on the host.
+//
+// Data layout in HBM ("strip planes"):
+//   activations  act[chunk c = 0..15][slot s = 0..S-1][8 channels]  bf16   (channel = 8*c + j)
+//   A tile is 256 slots = one STRIP of BPT boards laid side by side: slot(b,y,x) = (b/BPT)*256 + y*PITCH + (b%BPT)*BW
+//   + x with BW = N+1 (one zero pad column per board) and PITCH = BPT*BW.  6x6: BPT 6, PITCH 42, 252 of 256 slots used;
+//   5x5: BPT 8, PITCH 48.  There are NO pad rows in memory: a tap (ky,kx) is the constant slot shift (ky-1)*PITCH +
+//   (kx-1), horizontal neighbours outside a board land on a pad column (or wrap onto the previous strip row's last pad
+//   column), vertical neighbours outside the strip land on zero rows that exist only in shared memory.
+//   Useful MMA rows: 216/256 (6x6), 200/256 (5x5) -- versus 36/49 and 25/36 for a per-board padded frame.
+//   weights  w[slab k = 0..7][ky][kx][kchunk 2][c_out 128][8 c_in] bf16: the K-major no-swizzle UMMA operand image in
+//   consumption order, one 12 KiB bulk copy per (slab, ky) stage.
+//
+// GEMM view per tile: D[256 slots x 128 c_out] += A[256 x 1152] * W[128 x 1152]^T, two M=128,N=128 fp32 accumulators
+// in TMEM, issued as 8 K-SLABS (16 input channels) x 9 taps x 2 halves of tcgen05.mma.cta_group::1.kind::f16 (K=16).
+// The slab-outer order is what makes the kernel fit: an activation slab ([zero halo][256 rows][zero halo] x 32 B,
+// 11.5 KiB) is dead after its 18 MMAs, so activations stream through a 6-slab ring (69 KiB) instead of two resident
+// 72 KiB tiles, and the freed shared memory holds a 12-stage / 144 KiB weight ring -- deep enough to cover the L2
+// latency of the 288 KiB of weights every tile consumes (the 64 KiB ring of the first version was latency-bound:
+// 62.7 us/layer against 45.1 us with the weight stream disabled; the CTA-pair version with resident weights was bound
+// by the ~100-cycle issue floor of cta_group::2 N=128 instructions, profiles/r01_conv_experiments.md).
+//
+// Warp roles (352 threads, 1 persistent CTA per SM):
+//   warp 0     activation-slab producer (cp.async.bulk, 2 x 4 KiB per slab)          -> slab_full
+//   warp 10    weight-stage producer (cp.async.bulk, 12 KiB per stage)               -> w_full
+//   warp 1     TMEM allocator + single-thread tcgen05.mma issuer; tcgen05.commit     -> w_empty / slab_empty / acc_full
+//   warps 2-9  epilogue: residual prefetch, tcgen05.ld (software pipelined) -> +bias (+residual) -> ReLU -> pad mask
+//              -> bf16 strip planes, or fp32 logits + per-slot softmax partials for the policy head
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+
+#include "ptx_sm100.cuh"
+
+namespace tb {
+
+// strip layout shared by every kernel that touches activations / logits
+template <int N>
+struct SlotMap {
+    static constexpr int BW = N + 1;               // board width incl. its zero pad column
+    static constexpr int BPT = 256 / (N * BW);     // boards per 256-slot tile (strip)
+    static constexpr int PITCH = BPT * BW;         // slots per strip row
+    static constexpr int USED = N * PITCH;         // slots of a tile that map to a (board, y, x or pad column)
+    __host__ __device__ static constexpr int tiles(int boards) { return (boards + BPT - 1) / BPT; }
+    __host__ __device__ static constexpr size_t slot(int b, int y, int x) {
+        return size_t(b / BPT) * 256 + size_t(y * PITCH + (b % BPT) * BW + x);
+    }
+};
+
+constexpr int C3_TILE_M = 256;
+constexpr int C3_HALO = 56;                                // >= PITCH + 1 (43 for 6x6, 49 for 5x5)
+constexpr int C3_ROWS = C3_TILE_M + 2 * C3_HALO;           // 368 rows per K chunk of a slab
+constexpr int C3_SLAB_BYTES = 2 * C3_ROWS * 16;            // 11776: 16 input channels
+constexpr int C3_SLABS = 6;                                // activation ring depth
+constexpr int C3_W_STAGE_BYTES = 3 * 2 * 128 * 16;         // 12288: one (slab, ky): 3 taps x 16 c_in x 128 c_out
+constexpr int C3_W_STAGES = 12;                            // weight ring depth (144 KiB in flight)
+constexpr int C3_STAGES_PER_SLAB = 3;
+constexpr int C3_MAX_SLABS = 8;                            // 128 input channels
+constexpr int C3_THREADS = 352;
+constexpr int C3_SMEM_BYTES = C3_SLABS * C3_SLAB_BYTES + C3_W_STAGES * C3_W_STAGE_BYTES + 1024;
+constexpr size_t C3_W_LAYER_ELEMS = size_t(C3_MAX_SLABS) * 9 * 2 * 128 * 8;  // bf16 elements per packed layer
+
+enum ConvMode : int {
+    CONV_RELU = 0,        // out = relu(conv + bias)                     -> bf16 strip planes
+    CONV_RES_RELU = 1,    // out = relu(conv + bias + res)               -> bf16 strip planes
+    CONV_LOGITS_F32 = 2,  // out = conv + bias  (no activation)          -> fp32 [channel][slot] + softmax partials
+};
+
+struct ConvParams {
+    const __nv_bfloat16* in;    // strip planes [16][S][8]
+    const __nv_bfloat16* res;   // strip planes (mode 1) or nullptr
+    __nv_bfloat16* out;         // strip planes (modes 0/1)
+    float* out_f32;             // [out_ch_total][S] (mode 2)
+    float2* partials;           // mode 2: [group][S] per-slot {max, sum exp(l - max)} over this group's valid channels
+    const __nv_bfloat16* w;     // [slabs][3][3][2][128][8]
+    const float* bias;          // [128]
+    int S;                      // plane stride in slots (= allocated tiles * 256)
+    int tiles;                  // tiles to process
+    int n_boards;
+    int n;                      // board size N
+    int bw;                     // N + 1
+    int bpt;                    // boards per tile
+    int pitch;                  // bpt * bw
+    int slabs;                  // ceil(c_in / 16) <= 8
+    int mode;
+    int out_ch_offset;          // mode 2: first output channel of this 128-wide group
+    int out_ch_valid;           // mode 2: number of real channels in this group (<=128)
+    int group;                  // mode 2: group index for `partials`
+};
+
+// barrier slots
+enum : int {
+    C3B_SLAB_FULL = 0,                          // [C3_SLABS]
+    C3B_SLAB_EMPTY = C3B_SLAB_FULL + C3_SLABS,  // [C3_SLABS]
+    C3B_W_FULL = C3B_SLAB_EMPTY + C3_SLABS,     // [C3_W_STAGES]
+    C3B_W_EMPTY = C3B_W_FULL + C3_W_STAGES,     // [C3_W_STAGES]
+    C3B_ACC_FULL = C3B_W_EMPTY + C3_W_STAGES,   // [2]
+    C3B_ACC_EMPTY = C3B_ACC_FULL + 2,           // [2]
+    C3B_COUNT = C3B_ACC_EMPTY + 2
+};
+
+template <int MODE>
+static __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc3_kernel(const ConvParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* a_buf = smem;                                   // C3_SLABS x C3_SLAB_BYTES
+    uint8_t* w_buf = smem + C3_SLABS * C3_SLAB_BYTES;        // C3_W_STAGES x C3_W_STAGE_BYTES
+    uint8_t* tail = w_buf + C3_W_STAGES * C3_W_STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tail);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail + C3B_COUNT * 8);
+    float* s_bias = reinterpret_cast<float*>(tail + C3B_COUNT * 8 + 16);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t bar0 = smem_u32(bars);
+    auto BAR = [&](int i) { return bar0 + 8u * i; };
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < C3_SLABS; ++i) {
+            mbar_init(BAR(C3B_SLAB_FULL + i), 1);
+            mbar_init(BAR(C3B_SLAB_EMPTY + i), 1);
+        }
+        for (int i = 0; i < C3_W_STAGES; ++i) {
+            mbar_init(BAR(C3B_W_FULL + i), 1);
+            mbar_init(BAR(C3B_W_EMPTY + i), 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(BAR(C3B_ACC_FULL + i), 1);
+            mbar_init(BAR(C3B_ACC_EMPTY + i), 8);  // one arrive per epilogue warp
+        }
+        mbar_fence_init();
+    }
+    // Programmatic dependent launch: the next layer's CTAs may be scheduled as soon as SMs free up; everything before
+    // griddep_wait() (barrier init, halo fill, TMEM alloc, first weight stages) overlaps the previous layer's tail.
+    griddep_launch_dependents();
+    if (threadIdx.x < 128) s_bias[threadIdx.x] = p.bias[threadIdx.x];
+    // zero halos: the rows above / below the 256 loaded rows of every slab buffer are never written by the bulk copies
+    for (int i = threadIdx.x; i < C3_SLABS * 2 * 2 * C3_HALO; i += C3_THREADS) {
+        const int row = i % C3_HALO, side = (i / C3_HALO) & 1, plane = i / (2 * C3_HALO);  // plane = slab*2 + kchunk
+        uint8_t* dst = a_buf + plane * (C3_ROWS * 16) + (side ? (C3_HALO + C3_TILE_M + row) : row) * 16;
+        *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy zeros visible to the tensor core
+    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const size_t plane_bytes = static_cast<size_t>(p.S) * 16;
+    const int n_slabs = p.slabs;
+
+    if (warp == 0) {
+        // ===================== activation-slab producer =====================
+        if (lane == 0) {
+            griddep_wait();  // activations are written by the previous layer
+            uint32_t cnt = 0;
+            for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+                const uint8_t* src0 = reinterpret_cast<const uint8_t*>(p.in) + static_cast<size_t>(tile) * (C3_TILE_M * 16);
+                for (int k = 0; k < n_slabs; ++k, ++cnt) {
+                    const int sb = cnt % C3_SLABS;
+                    const uint32_t ph = (cnt / C3_SLABS) & 1;
+#if defined(CONV_EXP) && (CONV_EXP & 4)
+                    if (cnt >= C3_SLABS) continue;
+#endif
+                    mbar_wait(BAR(C3B_SLAB_EMPTY + sb), ph ^ 1);
+                    mbar_expect_tx(BAR(C3B_SLAB_FULL + sb), 2 * C3_TILE_M * 16);
+                    const uint32_t dst = smem_u32(a_buf + sb * C3_SLAB_BYTES) + C3_HALO * 16;
+                    bulk_g2s(dst, src0 + static_cast<size_t>(2 * k) * plane_bytes, C3_TILE_M * 16,
+                             BAR(C3B_SLAB_FULL + sb));
+                    bulk_g2s(dst + C3_ROWS * 16, src0 + static_cast<size_t>(2 * k + 1) * plane_bytes, C3_TILE_M * 16,
+                             BAR(C3B_SLAB_FULL + sb));
+                }
+            }
+        }
+    } else if (warp == 10) {
+        // ===================== weight-stage producer (weights never depend on the previous kernel) ==================
+        if (lane == 0) {
+            uint32_t cnt = 0;
+            const int stages = n_slabs * C3_STAGES_PER_SLAB;
+#if defined(CONV_EXP) && (CONV_EXP & 1)
+            if (false)
+#endif
+            for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+                for (int st = 0; st < stages; ++st, ++cnt) {
+                    const int ws = cnt % C3_W_STAGES;
+                    const uint32_t ph = (cnt / C3_W_STAGES) & 1;
+                    mbar_wait(BAR(C3B_W_EMPTY + ws), ph ^ 1);
+                    mbar_expect_tx(BAR(C3B_W_FULL + ws), C3_W_STAGE_BYTES);
+                    bulk_g2s(smem_u32(w_buf + ws * C3_W_STAGE_BYTES),
+                             reinterpret_cast<const uint8_t*>(p.w) + static_cast<size_t>(st) * C3_W_STAGE_BYTES,
+                             C3_W_STAGE_BYTES, BAR(C3B_W_FULL + ws));
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16_f32(128, 128);
+            uint32_t wcnt = 0, scnt = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
+                const int as = it & 1;
+                mbar_wait(BAR(C3B_ACC_EMPTY + as), ((it >> 1) & 1) ^ 1);  // accumulator stage drained by the epilogue
+                tc_fence_after();
+                const uint32_t d_base = tmem_base + as * 256;
+#pragma unroll 1
+                for (int k = 0; k < n_slabs; ++k, ++scnt) {
+                    const int sb = scnt % C3_SLABS;
+#if defined(CONV_EXP) && (CONV_EXP & 4)
+                    if (scnt < C3_SLABS)
+#endif
+                    mbar_wait(BAR(C3B_SLAB_FULL + sb), (scnt / C3_SLABS) & 1);
+                    tc_fence_after();
+                    const uint32_t a_base = smem_u32(a_buf + sb * C3_SLAB_BYTES) + C3_HALO * 16;
+#pragma unroll 1
+                    for (int ky = 0; ky < 3; ++ky, ++wcnt) {
+                        const int ws = wcnt % C3_W_STAGES;
+#if !(defined(CONV_EXP) && (CONV_EXP & 1))
+                        mbar_wait(BAR(C3B_W_FULL + ws), (wcnt / C3_W_STAGES) & 1);
+#endif
+                        tc_fence_after();
+                        const uint32_t w_base = smem_u32(w_buf + ws * C3_W_STAGE_BYTES);
+#pragma unroll
+                        for (int kx = 0; kx < 3; ++kx) {
+                            const int shift = (ky - 1) * p.pitch + (kx - 1);
+                            const uint64_t bdesc = umma_desc_kmajor_noswz(w_base + kx * 4096, 128 * 16, 128);
+#pragma unroll
+                            for (int t = 0; t < 2; ++t) {
+                                const uint64_t adesc =
+                                    umma_desc_kmajor_noswz(a_base + (t * 128 + shift) * 16, C3_ROWS * 16, 128);
+                                umma_bf16(d_base + t * 128, adesc, bdesc, idesc, (k | ky | kx) != 0);
+                            }
+                        }
+#if !(defined(CONV_EXP) && (CONV_EXP & 1))
+                        umma_commit(BAR(C3B_W_EMPTY + ws));     // weight stage free once these MMAs retire
+#endif
+                    }
+                    umma_commit(BAR(C3B_SLAB_EMPTY + sb));      // activation slab free
+                }
+                umma_commit(BAR(C3B_ACC_FULL + as));            // accumulators ready
+            }
+        }
+    } else if (warp >= 2 && warp < 10) {
+        // ===================== epilogue (8 warps, one thread per slot row) =====================
+        const int ew = warp - 2;          // 0..7
+        const int t = ew >> 2;            // accumulator half 0/1
+        const int quarter = warp & 3;     // TMEM lane quarter this warp may access
+        const int row = t * 128 + quarter * 32 + lane;
+        const int ry = row / p.pitch, rrem = row - ry * p.pitch;
+        const int rj = rrem / p.bw, rx = rrem - rj * p.bw;
+        const bool in_frame = ry < p.n && rx < p.n;   // a real square (not a pad column / tile remainder)
+        griddep_wait();  // residual input / output buffers belong to earlier layers until they complete
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
+            const int as = it & 1;
+            const uint32_t ph2 = (it >> 1) & 1;
+            const size_t slot = static_cast<size_t>(tile) * C3_TILE_M + row;
+            const bool valid = in_frame && (tile * p.bpt + rj) < p.n_boards;
+            // the residual does not depend on the MMAs: fetch the whole row before waiting for the accumulator
+            uint4 res[16];
+            if (MODE == CONV_RES_RELU) {
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    res[c] = make_uint4(0, 0, 0, 0);
+                    if (valid) res[c] = __ldg(reinterpret_cast<const uint4*>(p.res + (static_cast<size_t>(c) * p.S + slot) * 8));
+                }
+            }
+            mbar_wait(BAR(C3B_ACC_FULL + as), ph2);
+            tc_fence_after();
+#if defined(CONV_EXP) && (CONV_EXP & 2)
+            if (p.S != -12345) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(BAR(C3B_ACC_EMPTY + as)); continue; }
+#endif
+            const uint32_t taddr = tmem_base + as * 256 + t * 128 + (static_cast<uint32_t>(quarter * 32) << 16);
+            uint32_t r[2][32];
+            float pm = -INFINITY, psum = 0.f;  // mode 2: running softmax partial of this slot
+            tmem_ld32(taddr, r[0]);
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+                tmem_ld_wait();
+                if (cc < 3) tmem_ld32(taddr + (cc + 1) * 32, r[(cc + 1) & 1]);  // next chunk in flight while this one is processed
+                const uint32_t(&rc)[32] = r[cc & 1];
+                if (MODE == CONV_LOGITS_F32) {
+                    float v[32];
+                    float cm = -INFINITY;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int ch = cc * 32 + j;
+                        v[j] = __uint_as_float(rc[j]) + s_bias[ch];
+                        if (ch < p.out_ch_valid) {
+                            p.out_f32[static_cast<size_t>(p.out_ch_offset + ch) * p.S + slot] = valid ? v[j] : 0.0f;
+                            cm = fmaxf(cm, v[j]);
+                        }
+                    }
+                    if (cm > -INFINITY) {
+                        const float nm = fmaxf(pm, cm);
+                        float s = psum * __expf(pm - nm);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (cc * 32 + j < p.out_ch_valid) s += __expf(v[j] - nm);
+                        pm = nm;
+                        psum = s;
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {  // 4 chunks of 8 channels
+                        const int chunk = cc * 4 + q;
+                        float v[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(rc[q * 8 + j]) + s_bias[chunk * 8 + j];
+                        if (MODE == CONV_RES_RELU) {
+                            const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&res[chunk]);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                float2 f = __bfloat1622float2(rb[j]);
+                                v[2 * j] += f.x;
+                                v[2 * j + 1] += f.y;
+                            }
+                        }
+                        uint4 ov;
+                        __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&ov);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            float a = valid ? fmaxf(v[2 * j], 0.0f) : 0.0f;
+                            float b = valid ? fmaxf(v[2 * j + 1], 0.0f) : 0.0f;
+                            ob[j] = __floats2bfloat162_rn(a, b);
+                        }
+                        *reinterpret_cast<uint4*>(p.out + (static_cast<size_t>(chunk) * p.S + slot) * 8) = ov;
+                    }
+                }
+            }
+            if (MODE == CONV_LOGITS_F32)
+                p.partials[static_cast<size_t>(p.group) * p.S + slot] = make_float2(pm, psum);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(BAR(C3B_ACC_EMPTY + as));
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// Host-side launch. `stream` is the engine's stream; `num_sms` from the device properties.
+inline cudaError_t conv3x3_tc3_launch(const ConvParams& p, int num_sms, cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv3x3_tc3_kernel<CONV_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             C3_SMEM_BYTES);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(conv3x3_tc3_kernel<CONV_RES_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     C3_SMEM_BYTES);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(conv3x3_tc3_kernel<CONV_LOGITS_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     C3_SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    const int grid = p.tiles < num_sms ? p.tiles : num_sms;
+    if (grid <= 0) return cudaSuccess;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(C3_THREADS);
+    cfg.dynamicSmemBytes = C3_SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // PDL: see griddep_* in the kernel
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (p.mode == CONV_RELU) return cudaLaunchKernelEx(&cfg, conv3x3_tc3_kernel<CONV_RELU>, p);
+    if (p.mode == CONV_RES_RELU) return cudaLaunchKernelEx(&cfg, conv3x3_tc3_kernel<CONV_RES_RELU>, p);
+    return cudaLaunchKernelEx(&cfg, conv3x3_tc3_kernel<CONV_LOGITS_F32>, p);
+}
+
+// fill the layout fields of ConvParams for board size n
+inline void conv_params_set_layout(ConvParams& p, int n) {
+    p.n = n;
+    p.bw = n + 1;
+    p.bpt = 256 / (n * (n + 1));
+    p.pitch = p.bpt * p.bw;
+}
+
+}  // namespace tb

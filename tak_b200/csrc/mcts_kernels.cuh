@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(GAME_THREADS)
     const int cnt = v.pend_cnt[gid];
     if (cnt == 0) return;
     const int l = threadIdx.x & 31;
-    constexpr int P = N + 1, NSQ = N * N;
+    constexpr int NSQ = N * N;
     const int half = v.half[gid];
     uint4* stat = v.stat + arena_base(v, gid, half);
     uint2* link = v.link + arena_base(v, gid, half);
@@ -287,7 +287,7 @@ __global__ void __launch_bounds__(GAME_THREADS)
                 atomicOr(v.err, MERR_BAD_MOVE);
             } else if (ps.arch == 6) {
                 const int ch = idx / NSQ, sq = idx % NSQ, row = sq / N, col = sq % N;
-                const float lg = ps.logits[size_t(ch) * ps.S + CONV_GUARD + size_t(ei) * (P * P) + (row + 1) * P + col];
+                const float lg = ps.logits[size_t(ch) * ps.S + SlotMap<N>::slot(ei, row, col)];
                 prior = __fdiv_rn(expf(__fsub_rn(lg, mx)), sum);
             } else if (ps.arch == 5) {
                 prior = __fdiv_rn(expf(__fsub_rn(ps.logits[size_t(ei) * ps.psz + idx], mx)), sum);

@@ -5,7 +5,7 @@
 
 #include <cmath>
 
-#include "conv_tc2.cuh"
+#include "conv_tc3.cuh"
 #include "net_kernels.cuh"
 
 namespace tb {
@@ -22,11 +22,11 @@ int64_t net_blob_elems(const NetState& ns) {
     return total;
 }
 
-// fold BN(eval) into conv weight/bias and pack for conv_tc2 (CTA pair, resident weights):
-//   [rank = c_out/64][stage = tap*2+half][kchunk 8][c_out%64][8 c_in]   (2 x 144 KiB)
+// fold BN(eval) into conv weight/bias and pack for conv_tc3 (K-slab streaming, consumption order):
+//   [slab = c_in/16][ky][kx][kchunk = (c_in/8)%2][c_out 128][8 c_in]
 static void pack_conv(const float* w /*[co][ci][3][3]*/, const float* b, const float* bn /*gamma,beta,mean,var or null*/,
                       int c_out, int c_in, int co_base, std::vector<__nv_bfloat16>& packed, std::vector<float>& bias) {
-    packed.assign(size_t(18) * 8 * 128 * 8, __float2bfloat16(0.f));
+    packed.assign(C3_W_LAYER_ELEMS, __float2bfloat16(0.f));
     bias.assign(128, 0.f);
     for (int col = 0; col < 128; ++col) {
         const int co = co_base + col;
@@ -41,9 +41,8 @@ static void pack_conv(const float* w /*[co][ci][3][3]*/, const float* b, const f
         for (int ci = 0; ci < c_in; ++ci)
             for (int tap = 0; tap < 9; ++tap) {
                 const float v = float(double(w[(size_t(co) * c_in + ci) * 9 + tap]) * scale);
-                const int half = ci >> 6, kc = (ci & 63) >> 3, j = ci & 7;
-                packed[((((size_t(col >> 6) * 18 + (tap * 2 + half)) * 8 + kc) * 64) + (col & 63)) * 8 + j] =
-                    __float2bfloat16(v);
+                const int slab = ci >> 4, kc = (ci >> 3) & 1, j = ci & 7;
+                packed[((((size_t(slab) * 9 + tap) * 2 + kc) * 128) + col) * 8 + j] = __float2bfloat16(v);
             }
     }
 }
@@ -121,18 +120,23 @@ int net_load_blob(tak_engine* e, const float* blob, int64_t elems) {
     return TAK_OK;
 }
 
+static int tiles_for(int n, int boards) { return n == 5 ? SlotMap<5>::tiles(boards) : SlotMap<6>::tiles(boards); }
+
 int net_ensure_capacity(tak_engine* e, int boards) {
     NetState& ns = *e->net;
     if (boards <= ns.cap_boards) return TAK_OK;
-    const int P = ns.n + 1;
-    const int tiles = (boards * P * P + P + 1 + CONV_TILE_M - 1) / CONV_TILE_M;
-    const int S = CONV_GUARD + tiles * CONV_TILE_M + CONV_GUARD;
+    const int tiles = tiles_for(ns.n, boards);
+    const int S = tiles * C3_TILE_M;
     for (int i = 0; i < 3; ++i) {
         TB_CUDA(ns.act[i].ensure(size_t(S) * 256));
         TB_CUDA(cudaMemsetAsync(ns.act[i].p, 0, size_t(S) * 256, e->stream));
     }
-    if (ns.arch == 6) TB_CUDA(ns.logits.ensure(size_t(ns.policy_groups) * 128 * S * 4));
-    else if (ns.arch == 5) TB_CUDA(ns.logits.ensure(size_t(boards) * ns.policy_out * 4));
+    if (ns.arch == 6) {
+        TB_CUDA(ns.logits.ensure(size_t(ns.policy_groups) * 128 * S * 4));
+        TB_CUDA(ns.partials.ensure(size_t(ns.policy_groups) * S * 8));
+    } else if (ns.arch == 5) {
+        TB_CUDA(ns.logits.ensure(size_t(boards) * ns.policy_out * 4));
+    }
     TB_CUDA(ns.stats.ensure(size_t(boards) * 8));
     TB_CUDA(ns.values.ensure(size_t(boards) * 4));
     ns.cap_boards = boards;
@@ -144,26 +148,26 @@ template <int N>
 static int forward_t(tak_engine* e, const uint8_t* d_states, const int* d_index, int boards, float* d_policy_out) {
     NetState& ns = *e->net;
     if (int r = net_ensure_capacity(e, boards)) return r;
-    const int P = N + 1;
-    const int tiles = (boards * P * P + P + 1 + CONV_TILE_M - 1) / CONV_TILE_M;
+    const int tiles = SlotMap<N>::tiles(boards);
     const int S = ns.cap_S;  // plane stride is fixed by the allocation
     __nv_bfloat16* x = ns.act[0].as<__nv_bfloat16>();
     __nv_bfloat16* t = ns.act[1].as<__nv_bfloat16>();
     __nv_bfloat16* y = ns.act[2].as<__nv_bfloat16>();
     const int wblocks = (boards + 7) / 8;
-    k_encode<N><<<(boards + 1 + 7) / 8, 256, 0, e->stream>>>(d_states, d_index, boards, x, S);
+    k_encode<N><<<wblocks, 256, 0, e->stream>>>(d_states, d_index, boards, x, S);
     e->launches++;
     TB_CUDA(cudaGetLastError());
     auto conv = [&](const ConvLayer& L, const __nv_bfloat16* in, const __nv_bfloat16* res, __nv_bfloat16* out,
-                    int mode, float* out_f32, int ch_off, int ch_valid) -> int {
+                    int mode, int slabs, int grp, int ch_valid) -> int {
         NetProfile* prof = ns.profile;
         if (prof) TB_CUDA(cudaEventRecord(prof->ev[2 * prof->n], e->stream));
         ConvParams p{};
-        p.in = in; p.res = res; p.out = out; p.out_f32 = out_f32;
+        conv_params_set_layout(p, N);
+        p.in = in; p.res = res; p.out = out; p.out_f32 = ns.logits.as<float>(); p.partials = ns.partials.as<float2>();
         p.w = L.w.as<__nv_bfloat16>(); p.bias = L.bias.as<float>();
-        p.S = S; p.tiles = tiles; p.n_boards = boards; p.pitch = P; p.mode = mode;
-        p.out_ch_offset = ch_off; p.out_ch_valid = ch_valid;
-        TB_CUDA(conv3x3_tc2_launch(p, e->num_sms, e->stream));
+        p.S = S; p.tiles = tiles; p.n_boards = boards; p.slabs = slabs; p.mode = mode;
+        p.out_ch_offset = grp * 128; p.out_ch_valid = ch_valid; p.group = grp;
+        TB_CUDA(conv3x3_tc3_launch(p, e->num_sms, e->stream));
         e->launches++;
         if (prof) {
             TB_CUDA(cudaEventRecord(prof->ev[2 * prof->n + 1], e->stream));
@@ -171,13 +175,13 @@ static int forward_t(tak_engine* e, const uint8_t* d_states, const int* d_index,
         }
         return TAK_OK;
     };
-    // initial conv + BN + ReLU (net6.rs:72-76)
-    if (int r = conv(ns.layers[0], x, nullptr, y, CONV_RELU, nullptr, 0, 128)) return r;
+    // initial conv + BN + ReLU (net6.rs:72-76); only ceil(c_in/16) K-slabs carry input planes
+    if (int r = conv(ns.layers[0], x, nullptr, y, CONV_RELU, (ns.c_in + 15) / 16, 0, 128)) return r;
     std::swap(x, y);
     // residual tower (res_block.rs:14-22)
     for (int blk = 0; blk < ns.blocks; ++blk) {
-        if (int r = conv(ns.layers[1 + 2 * blk], x, nullptr, t, CONV_RELU, nullptr, 0, 128)) return r;
-        if (int r = conv(ns.layers[2 + 2 * blk], t, x, y, CONV_RES_RELU, nullptr, 0, 128)) return r;
+        if (int r = conv(ns.layers[1 + 2 * blk], x, nullptr, t, CONV_RELU, C3_MAX_SLABS, 0, 128)) return r;
+        if (int r = conv(ns.layers[2 + 2 * blk], t, x, y, CONV_RES_RELU, C3_MAX_SLABS, 0, 128)) return r;
         std::swap(x, y);
     }
     ns.trunk_out = x;
@@ -185,12 +189,16 @@ static int forward_t(tak_engine* e, const uint8_t* d_states, const int* d_index,
     if (ns.arch == 6) {
         for (int grp = 0; grp < ns.policy_groups; ++grp) {
             const int valid = std::min(128, ns.policy_ch - grp * 128);
-            if (int r = conv(ns.policy_layers[grp], x, nullptr, nullptr, CONV_LOGITS_F32, ns.logits.as<float>(),
-                             grp * 128, valid))
+            if (int r = conv(ns.policy_layers[grp], x, nullptr, nullptr, CONV_LOGITS_F32, C3_MAX_SLABS, grp, valid))
                 return r;
         }
-        k_policy_stats_conv<N><<<boards, 256, 0, e->stream>>>(ns.logits.as<float>(), S, ns.policy_ch, boards,
-                                                              ns.stats.as<float2>(), d_policy_out);
+        k_policy_stats_conv<N><<<wblocks, 256, 0, e->stream>>>(ns.partials.as<float2>(), S, ns.policy_groups, boards,
+                                                               ns.stats.as<float2>());
+        if (d_policy_out) {
+            e->launches++;
+            k_policy_full_conv<N><<<boards, 256, 0, e->stream>>>(ns.logits.as<float>(), S, ns.policy_ch,
+                                                                 ns.stats.as<float2>(), d_policy_out);
+        }
     } else {
         k_policy_fc<N><<<boards, 256, 0, e->stream>>>(x, S, ns.fc_policy_w.as<__nv_bfloat16>(),
                                                       ns.fc_policy_b.as<float>(), ns.policy_out,
@@ -226,7 +234,7 @@ void net_destroy(tak_engine* e) {
     for (auto& L : ns.layers) { L.w.release(); L.bias.release(); }
     for (auto& L : ns.policy_layers) { L.w.release(); L.bias.release(); }
     for (DevBuf* b : {&ns.fc_policy_w, &ns.fc_policy_b, &ns.value_w, &ns.act[0], &ns.act[1], &ns.act[2], &ns.logits,
-                      &ns.stats, &ns.values, &ns.stage_states, &ns.stage_policy, &ns.stage_repr})
+                      &ns.partials, &ns.stats, &ns.values, &ns.stage_states, &ns.stage_policy, &ns.stage_repr})
         b->release();
     delete e->net;
     e->net = nullptr;

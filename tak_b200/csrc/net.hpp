@@ -1,4 +1,4 @@
-// Network state of an engine (weights packed for conv_tc, activation slot planes, head outputs).
+// Network state of an engine (weights packed for conv_tc3, activation strip planes, head outputs).
 #pragma once
 #include <cuda_bf16.h>
 
@@ -7,7 +7,7 @@
 namespace tb {
 
 struct ConvLayer {
-    DevBuf w;     // bf16 [18][8][128][8]
+    DevBuf w;     // bf16 [slab 8][ky 3][kx 3][kchunk 2][c_out 128][8 c_in]
     DevBuf bias;  // fp32 [128]
 };
 
@@ -33,8 +33,9 @@ struct NetState {
     float value_bias = 0.f;
     // activations
     int cap_boards = 0, cap_S = 0;
-    DevBuf act[3];                         // bf16 slot planes
+    DevBuf act[3];                         // bf16 strip planes [16][S][8]
     DevBuf logits;                         // Net6: fp32 [256][S]; Net5: fp32 [B][1575]
+    DevBuf partials;                       // Net6: float2 [groups][S] per-slot softmax partials (conv epilogue)
     DevBuf stats;                          // float2 {max, sum exp} per board
     DevBuf values;                         // fp32 [B]
     const __nv_bfloat16* trunk_out = nullptr;

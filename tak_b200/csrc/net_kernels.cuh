@@ -6,7 +6,7 @@
 #pragma once
 #include <cuda_bf16.h>
 
-#include "conv_tc2.cuh"
+#include "conv_tc3.cuh"
 #include "tak_device.cuh"
 
 namespace tb {
@@ -55,21 +55,13 @@ __device__ __forceinline__ float repr_plane(const ReprCtx<N>& cx, int ch, Col co
     return 0.f;  // channel padding up to 128
 }
 
-// one warp per board; `states` = packed records of the boards to encode (index list optional)
+// one warp per board; `states` = packed records of the boards to encode (index list optional).  Pad columns and the
+// tile remainder are zero already: the planes are zero-filled at allocation and every conv epilogue rewrites them as 0.
 template <int N>
 __global__ void __launch_bounds__(256)
     k_encode(const uint8_t* states, const int* index, int n_boards, __nv_bfloat16* planes, int S) {
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    constexpr int P = N + 1;
-    if (w == n_boards) {
-        // terminator: the pad row below the last board may hold a larger earlier batch's data -> zero it
-        const size_t slot0 = size_t(CONV_GUARD) + size_t(n_boards) * (P * P);
-        for (int i = threadIdx.x & 31; i < 16 * (P + 1); i += 32)
-            *reinterpret_cast<uint4*>(planes + (size_t(i / (P + 1)) * S + slot0 + i % (P + 1)) * 8) =
-                make_uint4(0, 0, 0, 0);
-        return;
-    }
-    if (w > n_boards) return;
+    if (w >= n_boards) return;
     WarpGame<N> g;
     g.load(states + size_t(index ? index[w] : w) * StateLayout<N>::S);
     ReprCtx<N> cx;
@@ -85,7 +77,7 @@ __global__ void __launch_bounds__(256)
         const int h = half ? g.h1 : g.h0;
         const int kind = ((g.walls >> o) & 1) ? 1 : ((g.caps >> o) & 1) ? 2 : 0;
         const int x = o / N, y = o % N;
-        const size_t slot = size_t(CONV_GUARD) + size_t(w) * (P * P) + (y + 1) * P + x;
+        const size_t slot = SlotMap<N>::slot(w, y, x);
         for (int chunk = 0; chunk < 16; ++chunk) {
             uint4 v;
             __nv_bfloat162* vb = reinterpret_cast<__nv_bfloat162*>(&v);
@@ -150,36 +142,45 @@ __device__ __forceinline__ float block_reduce_sum(float v, float* s_tmp) {
 }
 
 // Net6-style head (policy conv): softmax statistics over ALL channels x squares of one board (net6.rs:100-103).
-// logits: [n_ch_padded][S] fp32 with pad slots; stats[b] = {max, sum of exp(l - max)}.
-// If policy_out != nullptr the full softmax vector [b][n_ch * N*N] (index = ch*N*N + row*N + col) is written too.
+// The conv epilogue already reduced every slot's channels to {max, sum exp(l - max)} per 128-channel group
+// (partials[group][S]); one warp per board merges the N*N x groups partials: stats[b] = {max, sum of exp(l - max)}.
 template <int N>
 __global__ void __launch_bounds__(256)
-    k_policy_stats_conv(const float* logits, int S, int n_ch, int n_boards, float2* stats, float* policy_out) {
-    __shared__ float s_tmp[8];
-    const int b = blockIdx.x;
-    constexpr int P = N + 1, NSQ = N * N;
-    const size_t base = size_t(CONV_GUARD) + size_t(b) * (P * P);
+    k_policy_stats_conv(const float2* partials, int S, int groups, int n_boards, float2* stats) {
+    const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (b >= n_boards) return;
+    constexpr int NSQ = N * N;
+    const int l = threadIdx.x & 31;
     float mx = -INFINITY;
-    for (int ch = threadIdx.x; ch < n_ch; ch += blockDim.x) {
-        const float* row = logits + size_t(ch) * S + base;
-        for (int y = 0; y < N; ++y)
-            for (int x = 0; x < N; ++x) mx = fmaxf(mx, row[(y + 1) * P + x]);
+    for (int i = l; i < NSQ * groups; i += 32) {
+        const int g = i / NSQ, sq = i % NSQ;
+        mx = fmaxf(mx, partials[size_t(g) * S + SlotMap<N>::slot(b, sq / N, sq % N)].x);
     }
-    mx = block_reduce_max(mx, s_tmp);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, o));
     float sum = 0.f;
-    for (int ch = threadIdx.x; ch < n_ch; ch += blockDim.x) {
-        const float* row = logits + size_t(ch) * S + base;
-        for (int y = 0; y < N; ++y)
-            for (int x = 0; x < N; ++x) sum += expf(row[(y + 1) * P + x] - mx);
+    for (int i = l; i < NSQ * groups; i += 32) {
+        const int g = i / NSQ, sq = i % NSQ;
+        const float2 pr = partials[size_t(g) * S + SlotMap<N>::slot(b, sq / N, sq % N)];
+        sum += pr.y * expf(pr.x - mx);
     }
-    sum = block_reduce_sum(sum, s_tmp);
-    if (threadIdx.x == 0) stats[b] = make_float2(mx, sum);
-    if (policy_out) {
-        float* dst = policy_out + size_t(b) * n_ch * NSQ;
-        for (int i = threadIdx.x; i < n_ch * NSQ; i += blockDim.x) {
-            const int ch = i / NSQ, sq = i % NSQ, y = sq / N, x = sq % N;
-            dst[i] = expf(logits[size_t(ch) * S + base + (y + 1) * P + x] - mx) / sum;
-        }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(FULL, sum, o);
+    if (l == 0) stats[b] = make_float2(mx, sum);
+}
+// full softmax vector [b][n_ch * N*N] (index = ch*N*N + row*N + col) from the logits and the board statistics: the
+// host-facing Network::policy_eval surface (network.rs:34); the search gathers only the legal moves' priors instead.
+template <int N>
+__global__ void __launch_bounds__(256)
+    k_policy_full_conv(const float* logits, int S, int n_ch, const float2* stats, float* policy_out) {
+    const int b = blockIdx.x;
+    constexpr int NSQ = N * N;
+    const float2 st = stats[b];
+    float* dst = policy_out + size_t(b) * n_ch * NSQ;
+    for (int i = threadIdx.x; i < n_ch * NSQ; i += blockDim.x) {
+        const int ch = i / NSQ, sq = i % NSQ;
+        const float lg = logits[size_t(ch) * S + SlotMap<N>::slot(b, sq / N, sq % N)];
+        dst[i] = __fdiv_rn(expf(__fsub_rn(lg, st.x)), st.y);
     }
 }
 
@@ -190,13 +191,12 @@ template <int N>
 __global__ void __launch_bounds__(256)
     k_policy_fc(const __nv_bfloat16* act, int S, const __nv_bfloat16* wt, const float* bias, int n_out,
                 float* logits_out /*[b][n_out]*/) {
-    constexpr int P = N + 1, NSQ = N * N, K = 128 * NSQ;
+    constexpr int NSQ = N * N, K = 128 * NSQ;
     __shared__ float s_act[K];
     const int b = blockIdx.x;
-    const size_t base = size_t(CONV_GUARD) + size_t(b) * (P * P);
     for (int i = threadIdx.x; i < K; i += blockDim.x) {
         const int c = i / NSQ, pos = i % NSQ, y = pos / N, x = pos % N;
-        s_act[i] = __bfloat162float(act[(size_t(c >> 3) * S + base + (y + 1) * P + x) * 8 + (c & 7)]);
+        s_act[i] = __bfloat162float(act[(size_t(c >> 3) * S + SlotMap<N>::slot(b, y, x)) * 8 + (c & 7)]);
     }
     __syncthreads();
     for (int j = threadIdx.x; j < n_out; j += blockDim.x) {
@@ -220,7 +220,7 @@ static __global__ void __launch_bounds__(256)
     if (threadIdx.x == 0) stats[b] = make_float2(mx, sum);
     if (policy_out)
         for (int j = threadIdx.x; j < n_out; j += blockDim.x)
-            policy_out[size_t(b) * n_out + j] = expf(row[j] - mx) / sum;
+            policy_out[size_t(b) * n_out + j] = __fdiv_rn(expf(__fsub_rn(row[j], mx)), sum);
 }
 
 // value head (net6.rs:104-107 / net5.rs:109): tanh(fc(flatten_NCHW(s)))  -- one warp per board
@@ -229,13 +229,12 @@ __global__ void __launch_bounds__(256)
     k_value(const __nv_bfloat16* act, int S, const float* wv /*[128*NSQ]*/, float bv, int n_boards, float* out) {
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (w >= n_boards) return;
-    constexpr int P = N + 1, NSQ = N * N;
-    const size_t base = size_t(CONV_GUARD) + size_t(w) * (P * P);
+    constexpr int NSQ = N * N;
     const int l = threadIdx.x & 31;
     float acc = 0.f;
     for (int pos = l; pos < NSQ; pos += 32) {
         const int y = pos / N, x = pos % N;
-        const size_t slot = base + (y + 1) * P + x;
+        const size_t slot = SlotMap<N>::slot(w, y, x);
         for (int chunk = 0; chunk < 16; ++chunk) {
             const uint4 v = *reinterpret_cast<const uint4*>(act + (size_t(chunk) * S + slot) * 8);
             const __nv_bfloat162* vb = reinterpret_cast<const __nv_bfloat162*>(&v);

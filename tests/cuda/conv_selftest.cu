@@ -1,13 +1,16 @@
-// Standalone GPU self-test for tak_b200/csrc/conv_tc.cuh (no Python, no torch): compares the tcgen05
-// implicit-GEMM conv against a naive one-thread-per-output CUDA kernel on random data, then times it.
+// Standalone GPU self-test for tak_b200/csrc/conv_tc3.cuh (no Python, no torch): compares the tcgen05 implicit-GEMM
+// conv against a naive dense NHWC convolution (one thread per output, layout-independent: it knows nothing about
+// strips, pad columns or halos) on random data, checks that every pad slot is written as zero, checks the per-slot
+// softmax partials of the policy mode, then times the kernel.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -I tak_b200/csrc tests/cuda/conv_selftest.cu -o build/conv_selftest
+// Usage: conv_selftest [boards=2000] [N=6] [slabs=8]
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
 
-#include "conv_tc2.cuh"
+#include "conv_tc3.cuh"
 
 using namespace tb;
 
@@ -29,186 +32,187 @@ static inline uint64_t splitmix() {
 }
 static inline float urand() { return (splitmix() >> 40) * (1.0f / 16777216.0f); }
 
-// naive reference: out[slot][co] = bias[co] + sum_{tap,ci} in[slot+shift][ci] * w[co][tap][ci]
-__global__ void conv_ref_kernel(const __nv_bfloat16* in, const __nv_bfloat16* wplain /*[co][tap][ci]*/,
-                                const float* bias, float* out /*[S][128]*/, int S, int pitch, int n_boards) {
-    int slot = blockIdx.x;
-    int co = threadIdx.x;
-    if (!conv_slot_valid(slot, pitch, n_boards)) {
-        out[(size_t)slot * 128 + co] = 0.f;
-        return;
-    }
+// naive reference on dense tensors: in [b][y][x][ci] bf16, w [co][tap][ci] bf16 -> out [b][y][x][co] fp32
+__global__ void conv_ref_kernel(const __nv_bfloat16* in, const __nv_bfloat16* w, const float* bias, float* out, int N,
+                                int c_in) {
+    const int pos = blockIdx.x;  // b*N*N + y*N + x
+    const int co = threadIdx.x;
+    const int b = pos / (N * N), y = (pos / N) % N, x = pos % N;
     float acc = 0.f;
     for (int tap = 0; tap < 9; ++tap) {
-        int s2 = slot + (tap / 3 - 1) * pitch + (tap % 3 - 1);
-        for (int ci = 0; ci < 128; ++ci) {
-            float a = __bfloat162float(in[((size_t)(ci >> 3) * S + s2) * 8 + (ci & 7)]);
-            float b = __bfloat162float(wplain[((size_t)co * 9 + tap) * 128 + ci]);
-            acc += a * b;
-        }
+        const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+        if (yy < 0 || yy >= N || xx < 0 || xx >= N) continue;
+        const __nv_bfloat16* a = in + ((size_t)(b * N + yy) * N + xx) * 128;
+        for (int ci = 0; ci < c_in; ++ci)
+            acc += __bfloat162float(a[ci]) * __bfloat162float(w[((size_t)co * 9 + tap) * 128 + ci]);
     }
-    out[(size_t)slot * 128 + co] = acc + bias[co];
+    out[(size_t)pos * 128 + co] = acc + bias[co];
 }
 
 int main(int argc, char** argv) {
-    int n_boards = argc > 1 ? atoi(argv[1]) : 2000;
-    int N = argc > 2 ? atoi(argv[2]) : 6;
-    int pitch = N + 1, spb = pitch * pitch;
-    int tiles = (n_boards * spb + pitch + 1 + CONV_TILE_M - 1) / CONV_TILE_M;
-    int S = CONV_GUARD + tiles * CONV_TILE_M + CONV_GUARD;
+    const int n_boards = argc > 1 ? atoi(argv[1]) : 2000;
+    const int N = argc > 2 ? atoi(argv[2]) : 6;
+    const int slabs = argc > 3 ? atoi(argv[3]) : 8;
+    if (N != 5 && N != 6) { printf("N must be 5 or 6\n"); return 2; }
+    ConvParams lay{};
+    conv_params_set_layout(lay, N);
+    const int tiles = (n_boards + lay.bpt - 1) / lay.bpt;
+    const int S = tiles * C3_TILE_M;
+    const int c_in = slabs * 16;
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, 0));
-    printf("device %s sms %d  boards %d N %d tiles %d S %d smem %d\n", prop.name, prop.multiProcessorCount, n_boards,
-           N, tiles, S, CONV_SMEM_BYTES);
+    printf("device %s sms %d  boards %d N %d bpt %d pitch %d tiles %d S %d slabs %d smem %d\n", prop.name,
+           prop.multiProcessorCount, n_boards, N, lay.bpt, lay.pitch, tiles, S, slabs, C3_SMEM_BYTES);
+    auto slot_of = [&](int b, int y, int x) { return (size_t)(b / lay.bpt) * 256 + y * lay.pitch + (b % lay.bpt) * lay.bw + x; };
 
-    size_t act_elems = (size_t)16 * S * 8;
+    const size_t act_elems = (size_t)16 * S * 8;
+    const size_t dense = (size_t)n_boards * N * N * 128;
     std::vector<__nv_bfloat16> h_in(act_elems, __float2bfloat16(0.f)), h_res(act_elems, __float2bfloat16(0.f));
+    std::vector<__nv_bfloat16> h_din(dense, __float2bfloat16(0.f)), h_dres(dense, __float2bfloat16(0.f));
     for (int b = 0; b < n_boards; ++b)
         for (int y = 0; y < N; ++y)
             for (int x = 0; x < N; ++x) {
-                int slot = CONV_GUARD + b * spb + (y + 1) * pitch + x;
+                const size_t slot = slot_of(b, y, x), pos = ((size_t)b * N + y) * N + x;
                 for (int ci = 0; ci < 128; ++ci) {
-                    h_in[((size_t)(ci >> 3) * S + slot) * 8 + (ci & 7)] = __float2bfloat16(urand() - 0.3f);
-                    h_res[((size_t)(ci >> 3) * S + slot) * 8 + (ci & 7)] = __float2bfloat16(urand() - 0.5f);
+                    // channels beyond c_in hold junk on purpose: with slabs < 8 the kernel must never read them
+                    const __nv_bfloat16 a = __float2bfloat16(urand() - 0.3f), r = __float2bfloat16(urand() - 0.5f);
+                    h_in[((size_t)(ci >> 3) * S + slot) * 8 + (ci & 7)] = a;
+                    h_res[((size_t)(ci >> 3) * S + slot) * 8 + (ci & 7)] = r;
+                    h_din[pos * 128 + ci] = a;
+                    h_dres[pos * 128 + ci] = r;
                 }
             }
-    std::vector<__nv_bfloat16> h_wplain((size_t)128 * 9 * 128), h_wpacked((size_t)18 * 8 * 128 * 8),
-        h_wpacked2((size_t)18 * 8 * 128 * 8);
+    std::vector<__nv_bfloat16> h_wplain((size_t)128 * 9 * 128), h_wpacked(C3_W_LAYER_ELEMS, __float2bfloat16(0.f));
     std::vector<float> h_bias(128);
     for (auto& v : h_bias) v = urand() - 0.5f;
     for (int co = 0; co < 128; ++co)
         for (int tap = 0; tap < 9; ++tap)
             for (int ci = 0; ci < 128; ++ci) {
-                __nv_bfloat16 w = __float2bfloat16((urand() - 0.5f) * 0.06f);
+                const __nv_bfloat16 w = __float2bfloat16((urand() - 0.5f) * 0.06f);
                 h_wplain[((size_t)co * 9 + tap) * 128 + ci] = w;
-                int half = ci >> 6, kc = (ci & 63) >> 3, j = ci & 7;
-                h_wpacked[((((size_t)(tap * 2 + half) * 8 + kc) * 128) + co) * 8 + j] = w;
-                // CTA-pair layout: [rank = co/64][stage][kc][co%64][8]
-                h_wpacked2[(((((size_t)(co >> 6) * 18 + (tap * 2 + half)) * 8 + kc) * 64) + (co & 63)) * 8 + j] = w;
+                const int slab = ci >> 4, kc = (ci >> 3) & 1, j = ci & 7;
+                h_wpacked[(((((size_t)slab * 9 + tap) * 2 + kc) * 128) + co) * 8 + j] = w;
             }
 
-    __nv_bfloat16 *d_in, *d_res, *d_out, *d_wplain, *d_wpacked, *d_wpacked2;
+    __nv_bfloat16 *d_in, *d_res, *d_out, *d_wplain, *d_wpacked, *d_din;
     float *d_bias, *d_ref, *d_logits;
+    float2* d_part;
     CK(cudaMalloc(&d_in, act_elems * 2));
     CK(cudaMalloc(&d_res, act_elems * 2));
     CK(cudaMalloc(&d_out, act_elems * 2));
+    CK(cudaMalloc(&d_din, dense * 2));
     CK(cudaMalloc(&d_wplain, h_wplain.size() * 2));
     CK(cudaMalloc(&d_wpacked, h_wpacked.size() * 2));
-    CK(cudaMalloc(&d_wpacked2, h_wpacked2.size() * 2));
-    CK(cudaMemcpy(d_wpacked2, h_wpacked2.data(), h_wpacked2.size() * 2, cudaMemcpyHostToDevice));
     CK(cudaMalloc(&d_bias, 512));
-    CK(cudaMalloc(&d_ref, (size_t)S * 128 * 4));
+    CK(cudaMalloc(&d_ref, dense * 4));
     CK(cudaMalloc(&d_logits, (size_t)128 * S * 4));
+    CK(cudaMalloc(&d_part, (size_t)S * 8));
     CK(cudaMemcpy(d_in, h_in.data(), act_elems * 2, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_res, h_res.data(), act_elems * 2, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_din, h_din.data(), dense * 2, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_wplain, h_wplain.data(), h_wplain.size() * 2, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_wpacked, h_wpacked.data(), h_wpacked.size() * 2, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_bias, h_bias.data(), 512, cudaMemcpyHostToDevice));
-    CK(cudaMemset(d_out, 0xFF, act_elems * 2));  // poison: every slot of every tile must be written
-    CK(cudaMemset(d_logits, 0, (size_t)128 * S * 4));
 
-    conv_ref_kernel<<<S, 128>>>(d_in, d_wplain, d_bias, d_ref, S, pitch, n_boards);
+    conv_ref_kernel<<<n_boards * N * N, 128>>>(d_din, d_wplain, d_bias, d_ref, N, c_in);
     CK(cudaDeviceSynchronize());
-    std::vector<float> h_ref((size_t)S * 128);
-    CK(cudaMemcpy(h_ref.data(), d_ref, h_ref.size() * 4, cudaMemcpyDeviceToHost));
+    std::vector<float> h_ref(dense);
+    CK(cudaMemcpy(h_ref.data(), d_ref, dense * 4, cudaMemcpyDeviceToHost));
+
+    auto params = [&](int mode, int ch_valid) {
+        ConvParams p = lay;
+        p.in = d_in; p.res = d_res; p.out = d_out; p.out_f32 = d_logits; p.partials = d_part; p.w = d_wpacked;
+        p.bias = d_bias; p.S = S; p.tiles = tiles; p.n_boards = n_boards; p.slabs = slabs; p.mode = mode;
+        p.out_ch_offset = 0; p.out_ch_valid = ch_valid; p.group = 0;
+        return p;
+    };
 
     int fails = 0;
-    const int impl_only = argc > 3 ? atoi(argv[3]) : 0;
-    for (int impl = 1; impl <= 2; ++impl)
     for (int sms : {prop.multiProcessorCount, 24}) {
-        if (impl_only && impl != impl_only) continue;
         for (int mode = 2; mode >= 0; --mode) {
-            ConvParams p{};
-            p.in = d_in; p.res = d_res; p.out = d_out; p.out_f32 = d_logits; p.w = impl == 1 ? d_wpacked : d_wpacked2;
-            p.bias = d_bias;
-            p.S = S; p.tiles = tiles; p.n_boards = n_boards; p.pitch = pitch; p.mode = mode;
-            p.out_ch_offset = 0; p.out_ch_valid = 128;
-            CK(cudaMemset(d_out, 0xFF, act_elems * 2));
+            const int ch_valid = mode == 2 ? 123 : 128;
+            ConvParams p = params(mode, ch_valid);
+            CK(cudaMemset(d_out, 0xFF, act_elems * 2));  // poison: every slot of every tile must be written
             CK(cudaMemset(d_logits, 0xFF, (size_t)128 * S * 4));
-            if (impl == 1) CK(conv3x3_tc_launch(p, sms, 0)); else CK(conv3x3_tc2_launch(p, sms, 0));
+            CK(cudaMemset(d_part, 0xFF, (size_t)S * 8));
+            CK(conv3x3_tc3_launch(p, sms, 0));
             cudaError_t e = cudaDeviceSynchronize();
             if (e != cudaSuccess) {
                 printf("mode %d sms %d: kernel failed: %s\n", mode, sms, cudaGetErrorString(e));
                 return 3;
             }
             double maxerr = 0, maxref = 0;
-            long bad = 0;
-            int first_bad_slot = -1, first_bad_ch = -1;
+            long bad = 0, bad_pad = 0, bad_part = 0;
+            // which slots are real squares
+            std::vector<int> pos_of(S, -1);
+            for (int b = 0; b < n_boards; ++b)
+                for (int y = 0; y < N; ++y)
+                    for (int x = 0; x < N; ++x) pos_of[slot_of(b, y, x)] = (b * N + y) * N + x;
             if (mode == 2) {
                 std::vector<float> h_log((size_t)128 * S);
+                std::vector<float2> h_part(S);
                 CK(cudaMemcpy(h_log.data(), d_logits, h_log.size() * 4, cudaMemcpyDeviceToHost));
-                for (int slot = CONV_GUARD; slot < CONV_GUARD + tiles * CONV_TILE_M; ++slot)
-                    for (int ch = 0; ch < 128; ++ch) {
-                        float r = h_ref[(size_t)slot * 128 + ch], g = h_log[(size_t)ch * S + slot];
-                        double err = fabs((double)r - g);
-                        if (!(err <= 2e-3 + 1e-3 * fabs(r))) {
-                            if (!bad) { first_bad_slot = slot; first_bad_ch = ch; }
-                            ++bad;
-                        }
+                CK(cudaMemcpy(h_part.data(), d_part, (size_t)S * 8, cudaMemcpyDeviceToHost));
+                for (int slot = 0; slot < S; ++slot) {
+                    double mx = -1e30, sum = 0;
+                    for (int ch = 0; ch < ch_valid; ++ch) {
+                        const float g = h_log[(size_t)ch * S + slot];
+                        if (pos_of[slot] < 0) { if (g != 0.f) ++bad_pad; continue; }
+                        const float r = h_ref[(size_t)pos_of[slot] * 128 + ch];
+                        const double err = fabs((double)r - g);
+                        if (!(err <= 2e-3 + 1e-3 * fabs(r))) ++bad;
                         if (err > maxerr || err != err) maxerr = err;
                         if (fabs(r) > maxref) maxref = fabs(r);
+                        if (g > mx) mx = g;
                     }
+                    if (pos_of[slot] < 0) continue;
+                    for (int ch = 0; ch < ch_valid; ++ch) sum += exp((double)h_log[(size_t)ch * S + slot] - mx);
+                    const float2 pr = h_part[slot];
+                    if (!(pr.x == (float)mx) || !(fabs(pr.y - sum) <= 1e-4 * sum)) ++bad_part;
+                }
             } else {
                 std::vector<__nv_bfloat16> h_out(act_elems);
                 CK(cudaMemcpy(h_out.data(), d_out, act_elems * 2, cudaMemcpyDeviceToHost));
-                for (int slot = CONV_GUARD; slot < CONV_GUARD + tiles * CONV_TILE_M; ++slot) {
-                    bool valid = false;
-                    {
-                        int rel = slot - CONV_GUARD, board = rel / spb, loc = rel % spb, y = loc / pitch, x = loc % pitch;
-                        valid = board < n_boards && y >= 1 && x < pitch - 1;
-                    }
+                for (int slot = 0; slot < S; ++slot)
                     for (int ch = 0; ch < 128; ++ch) {
-                        size_t off = ((size_t)(ch >> 3) * S + slot) * 8 + (ch & 7);
-                        float r = h_ref[(size_t)slot * 128 + ch];
-                        if (mode == 1 && valid) r += __bfloat162float(h_res[off]);
-                        r = valid ? fmaxf(r, 0.f) : 0.f;
-                        float g = __bfloat162float(h_out[off]);
-                        double err = fabs((double)r - g);
-                        if (!(err <= 2e-3 + 8e-3 * fabs(r))) {
-                            if (!bad) { first_bad_slot = slot; first_bad_ch = ch; }
-                            ++bad;
-                        }
+                        const size_t off = ((size_t)(ch >> 3) * S + slot) * 8 + (ch & 7);
+                        const float g = __bfloat162float(h_out[off]);
+                        if (pos_of[slot] < 0) { if (g != 0.f || g != g) ++bad_pad; continue; }
+                        float r = h_ref[(size_t)pos_of[slot] * 128 + ch];
+                        if (mode == 1) r += __bfloat162float(h_dres[(size_t)pos_of[slot] * 128 + ch]);
+                        r = fmaxf(r, 0.f);
+                        const double err = fabs((double)r - g);
+                        if (!(err <= 2e-3 + 8e-3 * fabs(r))) ++bad;
                         if (err > maxerr || err != err) maxerr = err;
                         if (fabs(r) > maxref) maxref = fabs(r);
                     }
-                }
             }
-            printf("impl %d mode %d grid<=%3d: max|err| %.3e (max|ref| %.3f) bad %ld%s\n", impl, mode, sms, maxerr, maxref, bad, bad ? "  <-- FAIL" : "  ok");
-            if (bad) {
-                ++fails;
-                int rel = first_bad_slot - CONV_GUARD;
-                printf("   first bad: slot %d (tile %d row %d board %d loc %d) ch %d\n", first_bad_slot,
-                       rel / CONV_TILE_M, rel % CONV_TILE_M, rel / spb, rel % spb, first_bad_ch);
-            }
+            const bool ok = !bad && !bad_pad && !bad_part;
+            printf("mode %d grid<=%3d: max|err| %.3e (max|ref| %.3f) bad %ld bad_pad %ld bad_partials %ld%s\n", mode,
+                   sms, maxerr, maxref, bad, bad_pad, bad_part, ok ? "  ok" : "  <-- FAIL");
+            if (!ok) ++fails;
         }
     }
 
     // ---- timing (mode 1, the res-block conv) ----
-    for (int impl = 1; impl <= 2; ++impl) {
-        if (impl_only && impl != impl_only) continue;
-        ConvParams p{};
-        p.in = d_in; p.res = d_res; p.out = d_out; p.out_f32 = d_logits; p.w = impl == 1 ? d_wpacked : d_wpacked2;
-        p.bias = d_bias;
-        p.S = S; p.tiles = tiles; p.n_boards = n_boards; p.pitch = pitch; p.mode = 1;
-        p.out_ch_valid = 128;
-        auto launch = [&]() { return impl == 1 ? conv3x3_tc_launch(p, prop.multiProcessorCount, 0)
-                                               : conv3x3_tc2_launch(p, prop.multiProcessorCount, 0); };
+    {
+        ConvParams p = params(1, 128);
         cudaEvent_t e0, e1;
         CK(cudaEventCreate(&e0));
         CK(cudaEventCreate(&e1));
-        for (int i = 0; i < 5; ++i) CK(launch());
+        for (int i = 0; i < 5; ++i) CK(conv3x3_tc3_launch(p, prop.multiProcessorCount, 0));
         CK(cudaEventRecord(e0));
         const int reps = 50;
-        for (int i = 0; i < reps; ++i) CK(launch());
+        for (int i = 0; i < reps; ++i) CK(conv3x3_tc3_launch(p, prop.multiProcessorCount, 0));
         CK(cudaEventRecord(e1));
         CK(cudaEventSynchronize(e1));
         float ms;
         CK(cudaEventElapsedTime(&ms, e0, e1));
-        double per = ms / reps * 1e-3;
-        double useful = 2.0 * n_boards * N * N * 128.0 * 1152.0;
-        double issued = 2.0 * tiles * 256.0 * 128.0 * 1152.0;
-        printf("timing impl %d: %.1f us/layer  useful %.1f TFLOP/s  issued %.1f TFLOP/s\n", impl, per * 1e6,
-               useful / per * 1e-12, issued / per * 1e-12);
+        const double per = ms / reps * 1e-3;
+        const double useful = 2.0 * n_boards * N * N * 128.0 * 9.0 * c_in;
+        const double issued = 2.0 * tiles * 256.0 * 128.0 * 9.0 * c_in;
+        printf("timing: %.1f us/layer  useful %.1f TFLOP/s  issued %.1f TFLOP/s\n", per * 1e6, useful / per * 1e-12,
+               issued / per * 1e-12);
     }
     printf(fails ? "SELFTEST FAILED\n" : "SELFTEST PASSED\n");
     return fails ? 1 : 0;
