@@ -267,7 +267,7 @@ def run_b200(args):
     conv_flop = prof["flop"] - G * (2.0 * 128 * 36)  # all but the value FC runs in the conv kernel
     achieved = conv_flop / (prof["ms_conv"] * 1e-3) / 1e12
     roofline = {
-        "bound": "tensor", "kernel": "conv3x3_tc2_kernel", "achieved": achieved, "peak": pk["bf16_burst"],
+        "bound": "tensor", "kernel": "conv3x3_tc3_kernel", "achieved": achieved, "peak": pk["bf16_burst"],
         "unit": "TFLOP/s", "frac": achieved / pk["bf16_burst"], "traffic": None,
         "peak_kind": "burst bf16 (kernel timed alone, CUDA events around each launch), " + pk["source"],
         "avg_launch_us": 1e3 * prof["ms_conv"] / prof["conv_launches"],
@@ -287,7 +287,8 @@ def run_b200(args):
                        "games_per_gpu": G, "rollouts": R, "noise": "dirichlet(0.2) x0.3 below ply 80",
                        "pick": "visit-weighted sample below ply 40, argmax after", "instant_win": True,
                        "l2": "inputs larger than L2: per rollout step the net streams >1 GB of activations "
-                             "(G x 49 slots x 256 B x 2 x 35 layers) and 10 MB of weights",
+                             "(G/6 tiles x 256 slots x 256 B x 2 x 35 layers; 175 MB live per buffer at G=4096) and "
+                             "10 MB of weights, and the MCTS kernels walk a node pool of tens of GB",
                        "parallelism": f"games sharded over {world} rank(s), no collective in the rollout loop"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "what": "host game states -> tak_games_upload -> mcts_rollouts(800) -> mcts_children_batch + "
@@ -315,7 +316,8 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--games", type=int, default=4096, help="concurrent games per GPU")
+    ap.add_argument("--games", type=int, default=7992,
+                    help="concurrent games per GPU (7992 = 148 SMs x 9 tiles x 6 boards: whole waves of conv tiles)")
     ap.add_argument("--rollouts", type=int, default=800)
     ap.add_argument("--nodes-per-game", type=int, default=1 << 18)
     args = ap.parse_args()

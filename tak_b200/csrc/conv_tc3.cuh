@@ -13,21 +13,21 @@
 //   column), vertical neighbours outside the strip land on zero rows that exist only in shared memory.
 //   Useful MMA rows: 216/256 (6x6), 200/256 (5x5) -- versus 36/49 and 25/36 for a per-board padded frame.
 //   weights  w[slab k = 0..7][ky][kx][kchunk 2][c_out 128][8 c_in] bf16: the K-major no-swizzle UMMA operand image in
-//   consumption order, one 12 KiB bulk copy per (slab, ky) stage.
+//   consumption order, one 36 KiB bulk copy per slab.
 //
 // GEMM view per tile: D[256 slots x 128 c_out] += A[256 x 1152] * W[128 x 1152]^T, two M=128,N=128 fp32 accumulators
 // in TMEM, issued as 8 K-SLABS (16 input channels) x 9 taps x 2 halves of tcgen05.mma.cta_group::1.kind::f16 (K=16).
-// The slab-outer order is what makes the kernel fit: an activation slab ([zero halo][256 rows][zero halo] x 32 B,
-// 11.5 KiB) is dead after its 18 MMAs, so activations stream through a 6-slab ring (69 KiB) instead of two resident
-// 72 KiB tiles, and the freed shared memory holds a 12-stage / 144 KiB weight ring -- deep enough to cover the L2
-// latency of the 288 KiB of weights every tile consumes (the 64 KiB ring of the first version was latency-bound:
-// 62.7 us/layer against 45.1 us with the weight stream disabled; the CTA-pair version with resident weights was bound
-// by the ~100-cycle issue floor of cta_group::2 N=128 instructions, profiles/r01_conv_experiments.md).
+// The slab-outer order is what makes the kernel fit and fast: an activation slab ([zero halo][256 rows][zero halo] x
+// 32 B, 11.5 KiB) is dead after its 18 MMAs, so one pipeline stage = {activation slab, the slab's 9 taps of weights
+// (36 KiB)} = 47.5 KiB, a 4-stage ring holds 144 KiB of weights in flight, and the issuer needs ONE tcgen05.commit per
+// 18 MMAs.  Measured on B200 (profiles/r01_conv_experiments.md): each tcgen05.commit costs the issue stream ~200
+// cycles, so a 12 KiB weight stage with its own commit (24 + 8 commits per tile) ran 61-67 us/layer at 4096 boards,
+// this arrangement (8 + 1 commits) 41.8 us; cta_group::2 with resident weights is bound by a ~100-cycle floor per N=128
+// instruction (58.8 us); the bytes of the weight stream itself are not the limit (a quarter of the bytes: same time).
 //
-// Warp roles (352 threads, 1 persistent CTA per SM):
-//   warp 0     activation-slab producer (cp.async.bulk, 2 x 4 KiB per slab)          -> slab_full
-//   warp 10    weight-stage producer (cp.async.bulk, 12 KiB per stage)               -> w_full
-//   warp 1     TMEM allocator + single-thread tcgen05.mma issuer; tcgen05.commit     -> w_empty / slab_empty / acc_full
+// Warp roles (320 threads, 1 persistent CTA per SM):
+//   warp 0     producer: cp.async.bulk of the stage's activation slab (2 x 4 KiB) and weight slab (36 KiB) -> full
+//   warp 1     TMEM allocator + single-thread tcgen05.mma issuer; tcgen05.commit -> empty / acc_full
 //   warps 2-9  epilogue: residual prefetch, tcgen05.ld (software pipelined) -> +bias (+residual) -> ReLU -> pad mask
 //              -> bf16 strip planes, or fp32 logits + per-slot softmax partials for the policy head
 #pragma once
@@ -35,6 +35,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 
 #include "ptx_sm100.cuh"
 
@@ -56,15 +57,15 @@ struct SlotMap {
 constexpr int C3_TILE_M = 256;
 constexpr int C3_HALO = 56;                                // >= PITCH + 1 (43 for 6x6, 49 for 5x5)
 constexpr int C3_ROWS = C3_TILE_M + 2 * C3_HALO;           // 368 rows per K chunk of a slab
-constexpr int C3_SLAB_BYTES = 2 * C3_ROWS * 16;            // 11776: 16 input channels
-constexpr int C3_SLABS = 6;                                // activation ring depth
-constexpr int C3_W_STAGE_BYTES = 3 * 2 * 128 * 16;         // 12288: one (slab, ky): 3 taps x 16 c_in x 128 c_out
-constexpr int C3_W_STAGES = 12;                            // weight ring depth (144 KiB in flight)
-constexpr int C3_STAGES_PER_SLAB = 3;
+constexpr int C3_SLAB_BYTES = 2 * C3_ROWS * 16;            // 11776: 16 input channels of one tile (+ zero halos)
+constexpr int C3_W_SLAB_BYTES = 9 * 2 * 128 * 16;          // 36864: 9 taps x 16 c_in x 128 c_out
+constexpr int C3_STAGE_BYTES = C3_SLAB_BYTES + C3_W_SLAB_BYTES;  // 48640
+constexpr int C3_STAGES = 4;                               // ring depth (one stage = one K-slab: activations + weights)
 constexpr int C3_MAX_SLABS = 8;                            // 128 input channels
-constexpr int C3_THREADS = 352;
-constexpr int C3_SMEM_BYTES = C3_SLABS * C3_SLAB_BYTES + C3_W_STAGES * C3_W_STAGE_BYTES + 1024;
+constexpr int C3_THREADS = 320;
+constexpr int C3_SMEM_BYTES = C3_STAGES * C3_STAGE_BYTES + 1024;
 constexpr size_t C3_W_LAYER_ELEMS = size_t(C3_MAX_SLABS) * 9 * 2 * 128 * 8;  // bf16 elements per packed layer
+constexpr int C3_TILE_ALIGN = 1;
 
 enum ConvMode : int {
     CONV_RELU = 0,        // out = relu(conv + bias)                     -> bf16 strip planes
@@ -96,21 +97,18 @@ struct ConvParams {
 
 // barrier slots
 enum : int {
-    C3B_SLAB_FULL = 0,                          // [C3_SLABS]
-    C3B_SLAB_EMPTY = C3B_SLAB_FULL + C3_SLABS,  // [C3_SLABS]
-    C3B_W_FULL = C3B_SLAB_EMPTY + C3_SLABS,     // [C3_W_STAGES]
-    C3B_W_EMPTY = C3B_W_FULL + C3_W_STAGES,     // [C3_W_STAGES]
-    C3B_ACC_FULL = C3B_W_EMPTY + C3_W_STAGES,   // [2]
-    C3B_ACC_EMPTY = C3B_ACC_FULL + 2,           // [2]
+    C3B_FULL = 0,                        // [C3_STAGES] bulk-copy completion (activation slab + weight slab)
+    C3B_EMPTY = C3B_FULL + C3_STAGES,    // [C3_STAGES] tcgen05.commit after the stage's 18 MMAs
+    C3B_ACC_FULL = C3B_EMPTY + C3_STAGES,  // [2]
+    C3B_ACC_EMPTY = C3B_ACC_FULL + 2,    // [2]
     C3B_COUNT = C3B_ACC_EMPTY + 2
 };
 
 template <int MODE>
 static __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc3_kernel(const ConvParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    uint8_t* a_buf = smem;                                   // C3_SLABS x C3_SLAB_BYTES
-    uint8_t* w_buf = smem + C3_SLABS * C3_SLAB_BYTES;        // C3_W_STAGES x C3_W_STAGE_BYTES
-    uint8_t* tail = w_buf + C3_W_STAGES * C3_W_STAGE_BYTES;
+    uint8_t* stage_buf = smem;                               // C3_STAGES x {activation slab, weight slab}
+    uint8_t* tail = smem + C3_STAGES * C3_STAGE_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(tail);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail + C3B_COUNT * 8);
     float* s_bias = reinterpret_cast<float*>(tail + C3B_COUNT * 8 + 16);
@@ -121,13 +119,9 @@ static __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc3_kernel(const
     auto BAR = [&](int i) { return bar0 + 8u * i; };
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < C3_SLABS; ++i) {
-            mbar_init(BAR(C3B_SLAB_FULL + i), 1);
-            mbar_init(BAR(C3B_SLAB_EMPTY + i), 1);
-        }
-        for (int i = 0; i < C3_W_STAGES; ++i) {
-            mbar_init(BAR(C3B_W_FULL + i), 1);
-            mbar_init(BAR(C3B_W_EMPTY + i), 1);
+        for (int i = 0; i < C3_STAGES; ++i) {
+            mbar_init(BAR(C3B_FULL + i), 1);
+            mbar_init(BAR(C3B_EMPTY + i), 1);
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(BAR(C3B_ACC_FULL + i), 1);
@@ -136,13 +130,14 @@ static __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc3_kernel(const
         mbar_fence_init();
     }
     // Programmatic dependent launch: the next layer's CTAs may be scheduled as soon as SMs free up; everything before
-    // griddep_wait() (barrier init, halo fill, TMEM alloc, first weight stages) overlaps the previous layer's tail.
+    // griddep_wait() (barrier init, halo fill, TMEM alloc, first weight slabs) overlaps the previous layer's tail.
     griddep_launch_dependents();
     if (threadIdx.x < 128) s_bias[threadIdx.x] = p.bias[threadIdx.x];
     // zero halos: the rows above / below the 256 loaded rows of every slab buffer are never written by the bulk copies
-    for (int i = threadIdx.x; i < C3_SLABS * 2 * 2 * C3_HALO; i += C3_THREADS) {
-        const int row = i % C3_HALO, side = (i / C3_HALO) & 1, plane = i / (2 * C3_HALO);  // plane = slab*2 + kchunk
-        uint8_t* dst = a_buf + plane * (C3_ROWS * 16) + (side ? (C3_HALO + C3_TILE_M + row) : row) * 16;
+    for (int i = threadIdx.x; i < C3_STAGES * 2 * 2 * C3_HALO; i += C3_THREADS) {
+        const int row = i % C3_HALO, side = (i / C3_HALO) & 1, plane = i / (2 * C3_HALO);  // plane = stage*2 + kchunk
+        uint8_t* dst = stage_buf + (plane >> 1) * C3_STAGE_BYTES + (plane & 1) * (C3_ROWS * 16) +
+                       (side ? (C3_HALO + C3_TILE_M + row) : row) * 16;
         *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy zeros visible to the tensor core
@@ -156,45 +151,35 @@ static __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc3_kernel(const
     const int n_slabs = p.slabs;
 
     if (warp == 0) {
-        // ===================== activation-slab producer =====================
+        // ===================== producer: one stage = activation slab (2 x 4 KiB) + weight slab (36 KiB) ============
         if (lane == 0) {
+            auto load_w = [&](int sb, int k) {
+                mbar_expect_tx(BAR(C3B_FULL + sb), 2 * C3_TILE_M * 16 + C3_W_SLAB_BYTES);
+                bulk_g2s(smem_u32(stage_buf + sb * C3_STAGE_BYTES + C3_SLAB_BYTES),
+                         reinterpret_cast<const uint8_t*>(p.w) + static_cast<size_t>(k) * C3_W_SLAB_BYTES,
+                         C3_W_SLAB_BYTES, BAR(C3B_FULL + sb));
+            };
+            auto load_a = [&](int sb, int tile, int k) {
+                const uint8_t* src0 = reinterpret_cast<const uint8_t*>(p.in) + static_cast<size_t>(tile) * (C3_TILE_M * 16);
+                const uint32_t dst = smem_u32(stage_buf + sb * C3_STAGE_BYTES) + C3_HALO * 16;
+                bulk_g2s(dst, src0 + static_cast<size_t>(2 * k) * plane_bytes, C3_TILE_M * 16, BAR(C3B_FULL + sb));
+                bulk_g2s(dst + C3_ROWS * 16, src0 + static_cast<size_t>(2 * k + 1) * plane_bytes, C3_TILE_M * 16,
+                         BAR(C3B_FULL + sb));
+            };
+            // weights never depend on the previous kernel: the first ring's worth goes out before griddep_wait()
+            const int total = blockIdx.x < p.tiles ? ((p.tiles - 1 - blockIdx.x) / gridDim.x + 1) * n_slabs : 0;
+            const int pre = total < C3_STAGES ? total : C3_STAGES;
+            for (int c = 0; c < pre; ++c) load_w(c, c % n_slabs);
             griddep_wait();  // activations are written by the previous layer
             uint32_t cnt = 0;
             for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
-                const uint8_t* src0 = reinterpret_cast<const uint8_t*>(p.in) + static_cast<size_t>(tile) * (C3_TILE_M * 16);
                 for (int k = 0; k < n_slabs; ++k, ++cnt) {
-                    const int sb = cnt % C3_SLABS;
-                    const uint32_t ph = (cnt / C3_SLABS) & 1;
-#if defined(CONV_EXP) && (CONV_EXP & 4)
-                    if (cnt >= C3_SLABS) continue;
-#endif
-                    mbar_wait(BAR(C3B_SLAB_EMPTY + sb), ph ^ 1);
-                    mbar_expect_tx(BAR(C3B_SLAB_FULL + sb), 2 * C3_TILE_M * 16);
-                    const uint32_t dst = smem_u32(a_buf + sb * C3_SLAB_BYTES) + C3_HALO * 16;
-                    bulk_g2s(dst, src0 + static_cast<size_t>(2 * k) * plane_bytes, C3_TILE_M * 16,
-                             BAR(C3B_SLAB_FULL + sb));
-                    bulk_g2s(dst + C3_ROWS * 16, src0 + static_cast<size_t>(2 * k + 1) * plane_bytes, C3_TILE_M * 16,
-                             BAR(C3B_SLAB_FULL + sb));
-                }
-            }
-        }
-    } else if (warp == 10) {
-        // ===================== weight-stage producer (weights never depend on the previous kernel) ==================
-        if (lane == 0) {
-            uint32_t cnt = 0;
-            const int stages = n_slabs * C3_STAGES_PER_SLAB;
-#if defined(CONV_EXP) && (CONV_EXP & 1)
-            if (false)
-#endif
-            for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
-                for (int st = 0; st < stages; ++st, ++cnt) {
-                    const int ws = cnt % C3_W_STAGES;
-                    const uint32_t ph = (cnt / C3_W_STAGES) & 1;
-                    mbar_wait(BAR(C3B_W_EMPTY + ws), ph ^ 1);
-                    mbar_expect_tx(BAR(C3B_W_FULL + ws), C3_W_STAGE_BYTES);
-                    bulk_g2s(smem_u32(w_buf + ws * C3_W_STAGE_BYTES),
-                             reinterpret_cast<const uint8_t*>(p.w) + static_cast<size_t>(st) * C3_W_STAGE_BYTES,
-                             C3_W_STAGE_BYTES, BAR(C3B_W_FULL + ws));
+                    const int sb = cnt % C3_STAGES;
+                    if (cnt >= C3_STAGES) {
+                        mbar_wait(BAR(C3B_EMPTY + sb), ((cnt / C3_STAGES) & 1) ^ 1);
+                        load_w(sb, k);
+                    }
+                    load_a(sb, tile, k);
                 }
             }
         }
@@ -202,7 +187,7 @@ static __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc3_kernel(const
         // ===================== MMA issuer =====================
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc_bf16_f32(128, 128);
-            uint32_t wcnt = 0, scnt = 0;
+            uint32_t scnt = 0;
             int it = 0;
             for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
                 const int as = it & 1;
@@ -211,37 +196,25 @@ static __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc3_kernel(const
                 const uint32_t d_base = tmem_base + as * 256;
 #pragma unroll 1
                 for (int k = 0; k < n_slabs; ++k, ++scnt) {
-                    const int sb = scnt % C3_SLABS;
-#if defined(CONV_EXP) && (CONV_EXP & 4)
-                    if (scnt < C3_SLABS)
-#endif
-                    mbar_wait(BAR(C3B_SLAB_FULL + sb), (scnt / C3_SLABS) & 1);
+                    const int sb = scnt % C3_STAGES;
+                    mbar_wait(BAR(C3B_FULL + sb), (scnt / C3_STAGES) & 1);
                     tc_fence_after();
-                    const uint32_t a_base = smem_u32(a_buf + sb * C3_SLAB_BYTES) + C3_HALO * 16;
-#pragma unroll 1
-                    for (int ky = 0; ky < 3; ++ky, ++wcnt) {
-                        const int ws = wcnt % C3_W_STAGES;
-#if !(defined(CONV_EXP) && (CONV_EXP & 1))
-                        mbar_wait(BAR(C3B_W_FULL + ws), (wcnt / C3_W_STAGES) & 1);
-#endif
-                        tc_fence_after();
-                        const uint32_t w_base = smem_u32(w_buf + ws * C3_W_STAGE_BYTES);
+                    const uint32_t a_base = smem_u32(stage_buf + sb * C3_STAGE_BYTES) + C3_HALO * 16;
+                    const uint32_t w_base = smem_u32(stage_buf + sb * C3_STAGE_BYTES + C3_SLAB_BYTES);
 #pragma unroll
-                        for (int kx = 0; kx < 3; ++kx) {
-                            const int shift = (ky - 1) * p.pitch + (kx - 1);
-                            const uint64_t bdesc = umma_desc_kmajor_noswz(w_base + kx * 4096, 128 * 16, 128);
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const int shift = (tap / 3 - 1) * p.pitch + (tap % 3 - 1);
+                        const uint64_t bdesc = umma_desc_kmajor_noswz(w_base + tap * 4096, 128 * 16, 128);
 #pragma unroll
-                            for (int t = 0; t < 2; ++t) {
-                                const uint64_t adesc =
-                                    umma_desc_kmajor_noswz(a_base + (t * 128 + shift) * 16, C3_ROWS * 16, 128);
-                                umma_bf16(d_base + t * 128, adesc, bdesc, idesc, (k | ky | kx) != 0);
-                            }
+                        for (int t = 0; t < 2; ++t) {
+                            const uint64_t adesc =
+                                umma_desc_kmajor_noswz(a_base + (t * 128 + shift) * 16, C3_ROWS * 16, 128);
+                            umma_bf16(d_base + t * 128, adesc, bdesc, idesc, (k | tap) != 0);
                         }
-#if !(defined(CONV_EXP) && (CONV_EXP & 1))
-                        umma_commit(BAR(C3B_W_EMPTY + ws));     // weight stage free once these MMAs retire
-#endif
                     }
-                    umma_commit(BAR(C3B_SLAB_EMPTY + sb));      // activation slab free
+                    // ONE commit per slab: tcgen05.commit costs the issue stream ~200 cycles (measured), so the
+                    // activation slab and its weights are released together
+                    umma_commit(BAR(C3B_EMPTY + sb));
                 }
                 umma_commit(BAR(C3B_ACC_FULL + as));            // accumulators ready
             }

@@ -120,7 +120,12 @@ int net_load_blob(tak_engine* e, const float* blob, int64_t elems) {
     return TAK_OK;
 }
 
-static int tiles_for(int n, int boards) { return n == 5 ? SlotMap<5>::tiles(boards) : SlotMap<6>::tiles(boards); }
+// tiles of `boards` boards, rounded up to the cluster granularity of the conv kernel (the extra tiles hold no boards:
+// their activations stay zero)
+static int tiles_for(int n, int boards) {
+    const int t = n == 5 ? SlotMap<5>::tiles(boards) : SlotMap<6>::tiles(boards);
+    return (t + C3_TILE_ALIGN - 1) / C3_TILE_ALIGN * C3_TILE_ALIGN;
+}
 
 int net_ensure_capacity(tak_engine* e, int boards) {
     NetState& ns = *e->net;
@@ -148,7 +153,7 @@ template <int N>
 static int forward_t(tak_engine* e, const uint8_t* d_states, const int* d_index, int boards, float* d_policy_out) {
     NetState& ns = *e->net;
     if (int r = net_ensure_capacity(e, boards)) return r;
-    const int tiles = SlotMap<N>::tiles(boards);
+    const int tiles = tiles_for(N, boards);
     const int S = ns.cap_S;  // plane stride is fixed by the allocation
     __nv_bfloat16* x = ns.act[0].as<__nv_bfloat16>();
     __nv_bfloat16* t = ns.act[1].as<__nv_bfloat16>();

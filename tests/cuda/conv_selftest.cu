@@ -56,7 +56,7 @@ int main(int argc, char** argv) {
     if (N != 5 && N != 6) { printf("N must be 5 or 6\n"); return 2; }
     ConvParams lay{};
     conv_params_set_layout(lay, N);
-    const int tiles = (n_boards + lay.bpt - 1) / lay.bpt;
+    const int tiles = ((n_boards + lay.bpt - 1) / lay.bpt + C3_TILE_ALIGN - 1) / C3_TILE_ALIGN * C3_TILE_ALIGN;
     const int S = tiles * C3_TILE_M;
     const int c_in = slabs * 16;
     cudaDeviceProp prop;
