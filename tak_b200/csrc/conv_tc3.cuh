@@ -63,7 +63,7 @@ constexpr int C3_STAGE_BYTES = C3_SLAB_BYTES + C3_W_SLAB_BYTES;  // 48640
 constexpr int C3_STAGES = 4;                               // ring depth (one stage = one K-slab: activations + weights)
 constexpr int C3_MAX_SLABS = 8;                            // 128 input channels
 constexpr int C3_THREADS = 320;
-constexpr int C3_SMEM_BYTES = C3_STAGES * C3_STAGE_BYTES + 1024;
+constexpr int C3_SMEM_BYTES = C3_STAGES * C3_STAGE_BYTES + 2048;
 constexpr size_t C3_W_LAYER_ELEMS = size_t(C3_MAX_SLABS) * 9 * 2 * 128 * 8;  // bf16 elements per packed layer
 constexpr int C3_TILE_ALIGN = 1;
 
@@ -73,7 +73,8 @@ enum ConvMode : int {
     CONV_LOGITS_F32 = 2,  // out = conv + bias  (no activation)          -> fp32 [channel][slot] + softmax partials
 };
 
-struct ConvParams {
+// one convolution of the tower
+struct ConvLayerDesc {
     const __nv_bfloat16* in;    // strip planes [16][S][8]
     const __nv_bfloat16* res;   // strip planes (mode 1) or nullptr
     __nv_bfloat16* out;         // strip planes (modes 0/1)
@@ -81,37 +82,66 @@ struct ConvParams {
     float2* partials;           // mode 2: [group][S] per-slot {max, sum exp(l - max)} over this group's valid channels
     const __nv_bfloat16* w;     // [slabs][3][3][2][128][8]
     const float* bias;          // [128]
-    int S;                      // plane stride in slots (= allocated tiles * 256)
-    int tiles;                  // tiles to process
-    int n_boards;
-    int n;                      // board size N
-    int bw;                     // N + 1
-    int bpt;                    // boards per tile
-    int pitch;                  // bpt * bw
     int slabs;                  // ceil(c_in / 16) <= 8
     int mode;
     int out_ch_offset;          // mode 2: first output channel of this 128-wide group
     int out_ch_valid;           // mode 2: number of real channels in this group (<=128)
     int group;                  // mode 2: group index for `partials`
+    int pad_;
+};
+
+constexpr int C3_MAX_LAYERS = 36;   // Net6: 1 + 2*16 trunk convs + 2 policy groups
+constexpr int C3_GROUP = 3;         // tiles a CTA carries through the whole tower together
+
+// The whole conv tower in ONE launch.  A strip tile never reads another tile (zero halos, pad columns), so a CTA can
+// take a tile through every layer without any grid-wide synchronisation: CTA c owns tiles c, c+grid, ...; it walks
+// them in groups of <= 3, running all layers over a group before moving on:  for group { for layer { for tile in group
+// } }.  While the tensor core works on (layer, tile B) the epilogue of (layer, tile A) stores A's outputs and the
+// producer already streams them back in for (layer+1, tile A); the only hand-off is the per-tile `ready` mbarrier.
+// A group's activations (3 tiles x 3 buffers x 64 KiB per CTA, 85 MB per GPU) never leave L2, and the per-layer launch
+// prologue / exposed last epilogue of a layer-per-launch schedule disappear.
+struct ConvParams {
+    ConvLayerDesc layers[C3_MAX_LAYERS];
+    int n_layers;
+    int S;                      // plane stride in slots (= allocated tiles * 256)
+    int tile_begin, tile_end;   // tiles to process
+    int n_boards;
+    int n;                      // board size N
+    int bw;                     // N + 1
+    int bpt;                    // boards per tile
+    int pitch;                  // bpt * bw
 };
 
 // barrier slots
 enum : int {
-    C3B_FULL = 0,                        // [C3_STAGES] bulk-copy completion (activation slab + weight slab)
-    C3B_EMPTY = C3B_FULL + C3_STAGES,    // [C3_STAGES] tcgen05.commit after the stage's 18 MMAs
+    C3B_FULL = 0,                          // [C3_STAGES] bulk-copy completion (activation slab + weight slab)
+    C3B_EMPTY = C3B_FULL + C3_STAGES,      // [C3_STAGES] tcgen05.commit after the stage's 18 MMAs
     C3B_ACC_FULL = C3B_EMPTY + C3_STAGES,  // [2]
-    C3B_ACC_EMPTY = C3B_ACC_FULL + 2,    // [2]
-    C3B_COUNT = C3B_ACC_EMPTY + 2
+    C3B_ACC_EMPTY = C3B_ACC_FULL + 2,      // [2]
+    C3B_READY = C3B_ACC_EMPTY + 2,         // [C3_GROUP] outputs of (layer, tile-in-group) stored by all 8 epilogue warps
+    C3B_COUNT = C3B_READY + C3_GROUP
 };
 
-template <int MODE>
-static __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc3_kernel(const ConvParams p) {
+// work-item walk shared by the three roles: groups of tiles, all layers per group
+struct TowerWalk {
+    int n_my, n_groups, base, rem;
+    __device__ TowerWalk(const ConvParams& p) {
+        const int first = p.tile_begin + blockIdx.x;
+        n_my = first < p.tile_end ? (p.tile_end - 1 - first) / int(gridDim.x) + 1 : 0;
+        n_groups = (n_my + C3_GROUP - 1) / C3_GROUP;
+        base = n_groups ? n_my / n_groups : 0;
+        rem = n_groups ? n_my % n_groups : 0;
+    }
+    __device__ int group_size(int g) const { return base + (g < rem ? 1 : 0); }
+};
+
+static __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc3_kernel(const __grid_constant__ ConvParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* stage_buf = smem;                               // C3_STAGES x {activation slab, weight slab}
     uint8_t* tail = smem + C3_STAGES * C3_STAGE_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(tail);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail + C3B_COUNT * 8);
-    float* s_bias = reinterpret_cast<float*>(tail + C3B_COUNT * 8 + 16);
+    float* s_bias = reinterpret_cast<float*>(tail + C3B_COUNT * 8 + 16);   // [2][128]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -127,12 +157,12 @@ static __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc3_kernel(const
             mbar_init(BAR(C3B_ACC_FULL + i), 1);
             mbar_init(BAR(C3B_ACC_EMPTY + i), 8);  // one arrive per epilogue warp
         }
+        for (int i = 0; i < C3_GROUP; ++i) mbar_init(BAR(C3B_READY + i), 8);
         mbar_fence_init();
     }
-    // Programmatic dependent launch: the next layer's CTAs may be scheduled as soon as SMs free up; everything before
-    // griddep_wait() (barrier init, halo fill, TMEM alloc, first weight slabs) overlaps the previous layer's tail.
+    // Programmatic dependent launch: the kernel after the tower may be scheduled as SMs free up; everything before
+    // griddep_wait() (barrier init, halo fill, TMEM alloc, first weight slab) overlaps the previous kernel's tail.
     griddep_launch_dependents();
-    if (threadIdx.x < 128) s_bias[threadIdx.x] = p.bias[threadIdx.x];
     // zero halos: the rows above / below the 256 loaded rows of every slab buffer are never written by the bulk copies
     for (int i = threadIdx.x; i < C3_STAGES * 2 * 2 * C3_HALO; i += C3_THREADS) {
         const int row = i % C3_HALO, side = (i / C3_HALO) & 1, plane = i / (2 * C3_HALO);  // plane = stage*2 + kchunk
@@ -148,38 +178,49 @@ static __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc3_kernel(const
     const uint32_t tmem_base = *tmem_slot;
 
     const size_t plane_bytes = static_cast<size_t>(p.S) * 16;
-    const int n_slabs = p.slabs;
+    const TowerWalk walk(p);
+    const int tile0 = p.tile_begin + blockIdx.x;
 
     if (warp == 0) {
-        // ===================== producer: one stage = activation slab (2 x 4 KiB) + weight slab (36 KiB) ============
+        // ===================== producer: one stage = weight slab (36 KiB) + activation slab (2 x 4 KiB) ============
         if (lane == 0) {
-            auto load_w = [&](int sb, int k) {
-                mbar_expect_tx(BAR(C3B_FULL + sb), 2 * C3_TILE_M * 16 + C3_W_SLAB_BYTES);
-                bulk_g2s(smem_u32(stage_buf + sb * C3_STAGE_BYTES + C3_SLAB_BYTES),
-                         reinterpret_cast<const uint8_t*>(p.w) + static_cast<size_t>(k) * C3_W_SLAB_BYTES,
-                         C3_W_SLAB_BYTES, BAR(C3B_FULL + sb));
-            };
-            auto load_a = [&](int sb, int tile, int k) {
-                const uint8_t* src0 = reinterpret_cast<const uint8_t*>(p.in) + static_cast<size_t>(tile) * (C3_TILE_M * 16);
-                const uint32_t dst = smem_u32(stage_buf + sb * C3_STAGE_BYTES) + C3_HALO * 16;
-                bulk_g2s(dst, src0 + static_cast<size_t>(2 * k) * plane_bytes, C3_TILE_M * 16, BAR(C3B_FULL + sb));
-                bulk_g2s(dst + C3_ROWS * 16, src0 + static_cast<size_t>(2 * k + 1) * plane_bytes, C3_TILE_M * 16,
-                         BAR(C3B_FULL + sb));
-            };
-            // weights never depend on the previous kernel: the first ring's worth goes out before griddep_wait()
-            const int total = blockIdx.x < p.tiles ? ((p.tiles - 1 - blockIdx.x) / gridDim.x + 1) * n_slabs : 0;
-            const int pre = total < C3_STAGES ? total : C3_STAGES;
-            for (int c = 0; c < pre; ++c) load_w(c, c % n_slabs);
-            griddep_wait();  // activations are written by the previous layer
             uint32_t cnt = 0;
-            for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
-                for (int k = 0; k < n_slabs; ++k, ++cnt) {
-                    const int sb = cnt % C3_STAGES;
-                    if (cnt >= C3_STAGES) {
-                        mbar_wait(BAR(C3B_EMPTY + sb), ((cnt / C3_STAGES) & 1) ^ 1);
-                        load_w(sb, k);
+            uint32_t items_of[C3_GROUP] = {0, 0, 0};  // work items issued so far per tile-in-group = `ready` completions due
+            bool first_a = true;
+            for (int g = 0, j0 = 0; g < walk.n_groups; j0 += walk.group_size(g), ++g) {
+                const int gs = walk.group_size(g);
+                for (int L = 0; L < p.n_layers; ++L) {
+                    const ConvLayerDesc& ld = p.layers[L];
+                    for (int jj = 0; jj < gs; ++jj) {
+                        const int tile = tile0 + (j0 + jj) * int(gridDim.x);
+                        const uint8_t* src0 = reinterpret_cast<const uint8_t*>(ld.in) + static_cast<size_t>(tile) * (C3_TILE_M * 16);
+                        for (int k = 0; k < ld.slabs; ++k, ++cnt) {
+                            const int sb = cnt % C3_STAGES;
+#if defined(CONV_EXP) && (CONV_EXP & 4)
+                            if (cnt >= C3_STAGES) continue;
+#endif
+                            if (cnt >= C3_STAGES) mbar_wait(BAR(C3B_EMPTY + sb), ((cnt / C3_STAGES) & 1) ^ 1);
+                            mbar_expect_tx(BAR(C3B_FULL + sb), 2 * C3_TILE_M * 16 + C3_W_SLAB_BYTES);
+                            // weights never depend on anything computed here: they go out first
+                            bulk_g2s(smem_u32(stage_buf + sb * C3_STAGE_BYTES + C3_SLAB_BYTES),
+                                     reinterpret_cast<const uint8_t*>(ld.w) + static_cast<size_t>(k) * C3_W_SLAB_BYTES,
+                                     C3_W_SLAB_BYTES, BAR(C3B_FULL + sb));
+                            if (k == 0) {
+                                if (first_a) {
+                                    griddep_wait();  // the tower's input planes are written by the previous kernel
+                                    first_a = false;
+                                }
+                                // this tile's previous layer must have been stored by the epilogue: ready[jj] completes
+                                // once per work item of slot jj, the latest one being (L-1, this tile)
+                                if (L > 0) mbar_wait(BAR(C3B_READY + jj), (items_of[jj] - 1) & 1);
+                            }
+                            const uint32_t dst = smem_u32(stage_buf + sb * C3_STAGE_BYTES) + C3_HALO * 16;
+                            bulk_g2s(dst, src0 + static_cast<size_t>(2 * k) * plane_bytes, C3_TILE_M * 16, BAR(C3B_FULL + sb));
+                            bulk_g2s(dst + C3_ROWS * 16, src0 + static_cast<size_t>(2 * k + 1) * plane_bytes,
+                                     C3_TILE_M * 16, BAR(C3B_FULL + sb));
+                        }
+                        items_of[jj]++;
                     }
-                    load_a(sb, tile, k);
                 }
             }
         }
@@ -189,34 +230,43 @@ static __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc3_kernel(const
             constexpr uint32_t idesc = umma_idesc_bf16_f32(128, 128);
             uint32_t scnt = 0;
             int it = 0;
-            for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
-                const int as = it & 1;
-                mbar_wait(BAR(C3B_ACC_EMPTY + as), ((it >> 1) & 1) ^ 1);  // accumulator stage drained by the epilogue
-                tc_fence_after();
-                const uint32_t d_base = tmem_base + as * 256;
+            for (int g = 0; g < walk.n_groups; ++g) {
+                const int gs = walk.group_size(g);
+                for (int L = 0; L < p.n_layers; ++L) {
+                    const int n_slabs = p.layers[L].slabs;
+                    for (int jj = 0; jj < gs; ++jj, ++it) {
+                        const int as = it & 1;
+                        mbar_wait(BAR(C3B_ACC_EMPTY + as), ((it >> 1) & 1) ^ 1);  // accumulator drained by the epilogue
+                        tc_fence_after();
+                        const uint32_t d_base = tmem_base + as * 256;
 #pragma unroll 1
-                for (int k = 0; k < n_slabs; ++k, ++scnt) {
-                    const int sb = scnt % C3_STAGES;
-                    mbar_wait(BAR(C3B_FULL + sb), (scnt / C3_STAGES) & 1);
-                    tc_fence_after();
-                    const uint32_t a_base = smem_u32(stage_buf + sb * C3_STAGE_BYTES) + C3_HALO * 16;
-                    const uint32_t w_base = smem_u32(stage_buf + sb * C3_STAGE_BYTES + C3_SLAB_BYTES);
+                        for (int k = 0; k < n_slabs; ++k, ++scnt) {
+                            const int sb = scnt % C3_STAGES;
+#if defined(CONV_EXP) && (CONV_EXP & 4)
+                            if (scnt < C3_STAGES)
+#endif
+                            mbar_wait(BAR(C3B_FULL + sb), (scnt / C3_STAGES) & 1);
+                            tc_fence_after();
+                            const uint32_t a_base = smem_u32(stage_buf + sb * C3_STAGE_BYTES) + C3_HALO * 16;
+                            const uint32_t w_base = smem_u32(stage_buf + sb * C3_STAGE_BYTES + C3_SLAB_BYTES);
 #pragma unroll
-                    for (int tap = 0; tap < 9; ++tap) {
-                        const int shift = (tap / 3 - 1) * p.pitch + (tap % 3 - 1);
-                        const uint64_t bdesc = umma_desc_kmajor_noswz(w_base + tap * 4096, 128 * 16, 128);
+                            for (int tap = 0; tap < 9; ++tap) {
+                                const int shift = (tap / 3 - 1) * p.pitch + (tap % 3 - 1);
+                                const uint64_t bdesc = umma_desc_kmajor_noswz(w_base + tap * 4096, 128 * 16, 128);
 #pragma unroll
-                        for (int t = 0; t < 2; ++t) {
-                            const uint64_t adesc =
-                                umma_desc_kmajor_noswz(a_base + (t * 128 + shift) * 16, C3_ROWS * 16, 128);
-                            umma_bf16(d_base + t * 128, adesc, bdesc, idesc, (k | tap) != 0);
+                                for (int t = 0; t < 2; ++t) {
+                                    const uint64_t adesc =
+                                        umma_desc_kmajor_noswz(a_base + (t * 128 + shift) * 16, C3_ROWS * 16, 128);
+                                    umma_bf16(d_base + t * 128, adesc, bdesc, idesc, (k | tap) != 0);
+                                }
+                            }
+                            // ONE commit per slab: tcgen05.commit costs the issue stream ~200 cycles (measured), so
+                            // the activation slab and its weights are released together
+                            umma_commit(BAR(C3B_EMPTY + sb));
                         }
+                        umma_commit(BAR(C3B_ACC_FULL + as));            // accumulators ready
                     }
-                    // ONE commit per slab: tcgen05.commit costs the issue stream ~200 cycles (measured), so the
-                    // activation slab and its weights are released together
-                    umma_commit(BAR(C3B_EMPTY + sb));
                 }
-                umma_commit(BAR(C3B_ACC_FULL + as));            // accumulators ready
             }
         }
     } else if (warp >= 2 && warp < 10) {
@@ -225,93 +275,117 @@ static __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc3_kernel(const
         const int t = ew >> 2;            // accumulator half 0/1
         const int quarter = warp & 3;     // TMEM lane quarter this warp may access
         const int row = t * 128 + quarter * 32 + lane;
+        const int etid = threadIdx.x - 64;  // 0..255 among the epilogue threads
         const int ry = row / p.pitch, rrem = row - ry * p.pitch;
         const int rj = rrem / p.bw, rx = rrem - rj * p.bw;
         const bool in_frame = ry < p.n && rx < p.n;   // a real square (not a pad column / tile remainder)
-        griddep_wait();  // residual input / output buffers belong to earlier layers until they complete
+        griddep_wait();  // output / residual buffers belong to earlier kernels until they complete
         int it = 0;
-        for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
-            const int as = it & 1;
-            const uint32_t ph2 = (it >> 1) & 1;
-            const size_t slot = static_cast<size_t>(tile) * C3_TILE_M + row;
-            const bool valid = in_frame && (tile * p.bpt + rj) < p.n_boards;
-            // the residual does not depend on the MMAs: fetch the whole row before waiting for the accumulator
-            uint4 res[16];
-            if (MODE == CONV_RES_RELU) {
+        for (int g = 0, j0 = 0; g < walk.n_groups; j0 += walk.group_size(g), ++g) {
+            const int gs = walk.group_size(g);
+            for (int L = 0; L < p.n_layers; ++L) {
+                const ConvLayerDesc& ld = p.layers[L];
+                const int mode = ld.mode;
+                for (int jj = 0; jj < gs; ++jj, ++it) {
+                    const int tile = tile0 + (j0 + jj) * int(gridDim.x);
+                    const int as = it & 1;
+                    const uint32_t ph2 = (it >> 1) & 1;
+                    const size_t slot = static_cast<size_t>(tile) * C3_TILE_M + row;
+                    const bool valid = in_frame && (tile * p.bpt + rj) < p.n_boards;
+                    // bias of this layer -> shared (double buffered by accumulator stage; the named barrier keeps the
+                    // 256 epilogue threads within one work item of each other)
+                    float* bias_s = s_bias + as * 128;
+                    if (etid < 128) bias_s[etid] = ld.bias[etid];
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    // the residual does not depend on the MMAs: fetch the whole row before waiting for the accumulator.
+                    // Plain (coherent) loads: these slots were stored by this very thread two layers ago.
+                    uint4 res[16];
+                    if (mode == CONV_RES_RELU) {
 #pragma unroll
-                for (int c = 0; c < 16; ++c) {
-                    res[c] = make_uint4(0, 0, 0, 0);
-                    if (valid) res[c] = __ldg(reinterpret_cast<const uint4*>(p.res + (static_cast<size_t>(c) * p.S + slot) * 8));
-                }
-            }
-            mbar_wait(BAR(C3B_ACC_FULL + as), ph2);
-            tc_fence_after();
-#if defined(CONV_EXP) && (CONV_EXP & 2)
-            if (p.S != -12345) { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(BAR(C3B_ACC_EMPTY + as)); continue; }
-#endif
-            const uint32_t taddr = tmem_base + as * 256 + t * 128 + (static_cast<uint32_t>(quarter * 32) << 16);
-            uint32_t r[2][32];
-            float pm = -INFINITY, psum = 0.f;  // mode 2: running softmax partial of this slot
-            tmem_ld32(taddr, r[0]);
-#pragma unroll
-            for (int cc = 0; cc < 4; ++cc) {
-                tmem_ld_wait();
-                if (cc < 3) tmem_ld32(taddr + (cc + 1) * 32, r[(cc + 1) & 1]);  // next chunk in flight while this one is processed
-                const uint32_t(&rc)[32] = r[cc & 1];
-                if (MODE == CONV_LOGITS_F32) {
-                    float v[32];
-                    float cm = -INFINITY;
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int ch = cc * 32 + j;
-                        v[j] = __uint_as_float(rc[j]) + s_bias[ch];
-                        if (ch < p.out_ch_valid) {
-                            p.out_f32[static_cast<size_t>(p.out_ch_offset + ch) * p.S + slot] = valid ? v[j] : 0.0f;
-                            cm = fmaxf(cm, v[j]);
+                        for (int c = 0; c < 16; ++c) {
+                            res[c] = make_uint4(0, 0, 0, 0);
+                            if (valid) res[c] = *reinterpret_cast<const uint4*>(ld.res + (static_cast<size_t>(c) * p.S + slot) * 8);
                         }
                     }
-                    if (cm > -INFINITY) {
-                        const float nm = fmaxf(pm, cm);
-                        float s = psum * __expf(pm - nm);
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (cc * 32 + j < p.out_ch_valid) s += __expf(v[j] - nm);
-                        pm = nm;
-                        psum = s;
+                    mbar_wait(BAR(C3B_ACC_FULL + as), ph2);
+                    tc_fence_after();
+#if defined(CONV_EXP) && (CONV_EXP & 2)
+                    if (p.S != -12345) {
+                        tc_fence_before(); __syncwarp();
+                        if (lane == 0) { mbar_arrive(BAR(C3B_ACC_EMPTY + as)); mbar_arrive(BAR(C3B_READY + jj)); }
+                        continue;
                     }
-                } else {
+#endif
+                    const uint32_t taddr = tmem_base + as * 256 + t * 128 + (static_cast<uint32_t>(quarter * 32) << 16);
+                    uint32_t r[2][32];
+                    float pm = -INFINITY, psum = 0.f;  // mode 2: running softmax partial of this slot
+                    tmem_ld32(taddr, r[0]);
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {  // 4 chunks of 8 channels
-                        const int chunk = cc * 4 + q;
-                        float v[8];
+                    for (int cc = 0; cc < 4; ++cc) {
+                        tmem_ld_wait();
+                        if (cc < 3) tmem_ld32(taddr + (cc + 1) * 32, r[(cc + 1) & 1]);  // next chunk in flight
+                        const uint32_t(&rc)[32] = r[cc & 1];
+                        if (mode == CONV_LOGITS_F32) {
+                            float v[32];
+                            float cm = -INFINITY;
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(rc[q * 8 + j]) + s_bias[chunk * 8 + j];
-                        if (MODE == CONV_RES_RELU) {
-                            const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&res[chunk]);
+                            for (int j = 0; j < 32; ++j) {
+                                const int ch = cc * 32 + j;
+                                v[j] = __uint_as_float(rc[j]) + bias_s[ch];
+                                if (ch < ld.out_ch_valid) {
+                                    ld.out_f32[static_cast<size_t>(ld.out_ch_offset + ch) * p.S + slot] = valid ? v[j] : 0.0f;
+                                    cm = fmaxf(cm, v[j]);
+                                }
+                            }
+                            if (cm > -INFINITY) {
+                                const float nm = fmaxf(pm, cm);
+                                float s = psum * __expf(pm - nm);
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                float2 f = __bfloat1622float2(rb[j]);
-                                v[2 * j] += f.x;
-                                v[2 * j + 1] += f.y;
+                                for (int j = 0; j < 32; ++j)
+                                    if (cc * 32 + j < ld.out_ch_valid) s += __expf(v[j] - nm);
+                                pm = nm;
+                                psum = s;
+                            }
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {  // 4 chunks of 8 channels
+                                const int chunk = cc * 4 + q;
+                                float v[8];
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(rc[q * 8 + j]) + bias_s[chunk * 8 + j];
+                                if (mode == CONV_RES_RELU) {
+                                    const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&res[chunk]);
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j) {
+                                        float2 f = __bfloat1622float2(rb[j]);
+                                        v[2 * j] += f.x;
+                                        v[2 * j + 1] += f.y;
+                                    }
+                                }
+                                uint4 ov;
+                                __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&ov);
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    float a = valid ? fmaxf(v[2 * j], 0.0f) : 0.0f;
+                                    float b = valid ? fmaxf(v[2 * j + 1], 0.0f) : 0.0f;
+                                    ob[j] = __floats2bfloat162_rn(a, b);
+                                }
+                                *reinterpret_cast<uint4*>(ld.out + (static_cast<size_t>(chunk) * p.S + slot) * 8) = ov;
                             }
                         }
-                        uint4 ov;
-                        __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&ov);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            float a = valid ? fmaxf(v[2 * j], 0.0f) : 0.0f;
-                            float b = valid ? fmaxf(v[2 * j + 1], 0.0f) : 0.0f;
-                            ob[j] = __floats2bfloat162_rn(a, b);
-                        }
-                        *reinterpret_cast<uint4*>(p.out + (static_cast<size_t>(chunk) * p.S + slot) * 8) = ov;
+                    }
+                    if (mode == CONV_LOGITS_F32)
+                        ld.partials[static_cast<size_t>(ld.group) * p.S + slot] = make_float2(pm, psum);
+                    tc_fence_before();
+                    // the stores above are read back by the bulk-copy engine (async proxy) for the next layer
+                    asm volatile("fence.proxy.async;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) {
+                        mbar_arrive(BAR(C3B_ACC_EMPTY + as));
+                        mbar_arrive(BAR(C3B_READY + jj));
                     }
                 }
             }
-            if (MODE == CONV_LOGITS_F32)
-                p.partials[static_cast<size_t>(p.group) * p.S + slot] = make_float2(pm, psum);
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(BAR(C3B_ACC_EMPTY + as));
         }
     }
 
@@ -320,23 +394,19 @@ static __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc3_kernel(const
     if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
-// Host-side launch. `stream` is the engine's stream; `num_sms` from the device properties.
+// Host-side launch (layers 0..n_layers-1 over tiles [tile_begin, tile_end)). `stream` is the engine's stream.
 inline cudaError_t conv3x3_tc3_launch(const ConvParams& p, int num_sms, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv3x3_tc3_kernel<CONV_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(conv3x3_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              C3_SMEM_BYTES);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(conv3x3_tc3_kernel<CONV_RES_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     C3_SMEM_BYTES);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(conv3x3_tc3_kernel<CONV_LOGITS_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     C3_SMEM_BYTES);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    const int grid = p.tiles < num_sms ? p.tiles : num_sms;
-    if (grid <= 0) return cudaSuccess;
+    const int tiles = p.tile_end - p.tile_begin;
+    const int grid = tiles < num_sms ? tiles : num_sms;
+    if (grid <= 0 || p.n_layers <= 0) return cudaSuccess;
+    if (p.n_layers > C3_MAX_LAYERS) return cudaErrorInvalidValue;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(C3_THREADS);
@@ -347,9 +417,7 @@ inline cudaError_t conv3x3_tc3_launch(const ConvParams& p, int num_sms, cudaStre
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (p.mode == CONV_RELU) return cudaLaunchKernelEx(&cfg, conv3x3_tc3_kernel<CONV_RELU>, p);
-    if (p.mode == CONV_RES_RELU) return cudaLaunchKernelEx(&cfg, conv3x3_tc3_kernel<CONV_RES_RELU>, p);
-    return cudaLaunchKernelEx(&cfg, conv3x3_tc3_kernel<CONV_LOGITS_F32>, p);
+    return cudaLaunchKernelEx(&cfg, conv3x3_tc3_kernel, p);
 }
 
 // fill the layout fields of ConvParams for board size n

@@ -162,41 +162,43 @@ static int forward_t(tak_engine* e, const uint8_t* d_states, const int* d_index,
     k_encode<N><<<wblocks, 256, 0, e->stream>>>(d_states, d_index, boards, x, S);
     e->launches++;
     TB_CUDA(cudaGetLastError());
+    // the whole conv tower (initial conv, residual blocks, Net6 policy conv groups) is ONE launch: conv_tc3.cuh
+    ConvParams p{};
+    conv_params_set_layout(p, N);
+    p.S = S; p.tile_begin = 0; p.tile_end = tiles; p.n_boards = boards;
     auto conv = [&](const ConvLayer& L, const __nv_bfloat16* in, const __nv_bfloat16* res, __nv_bfloat16* out,
-                    int mode, int slabs, int grp, int ch_valid) -> int {
+                    int mode, int slabs, int grp, int ch_valid) {
+        ConvLayerDesc& d = p.layers[p.n_layers++];
+        d.in = in; d.res = res; d.out = out; d.out_f32 = ns.logits.as<float>(); d.partials = ns.partials.as<float2>();
+        d.w = L.w.as<__nv_bfloat16>(); d.bias = L.bias.as<float>();
+        d.slabs = slabs; d.mode = mode; d.out_ch_offset = grp * 128; d.out_ch_valid = ch_valid; d.group = grp;
+    };
+    // initial conv + BN + ReLU (net6.rs:72-76); only ceil(c_in/16) K-slabs carry input planes
+    conv(ns.layers[0], x, nullptr, y, CONV_RELU, (ns.c_in + 15) / 16, 0, 128);
+    std::swap(x, y);
+    // residual tower (res_block.rs:14-22)
+    for (int blk = 0; blk < ns.blocks; ++blk) {
+        conv(ns.layers[1 + 2 * blk], x, nullptr, t, CONV_RELU, C3_MAX_SLABS, 0, 128);
+        conv(ns.layers[2 + 2 * blk], t, x, y, CONV_RES_RELU, C3_MAX_SLABS, 0, 128);
+        std::swap(x, y);
+    }
+    ns.trunk_out = x;
+    if (ns.arch == 6)  // policy conv (net6.rs:99-100), 128 output channels per group
+        for (int grp = 0; grp < ns.policy_groups; ++grp)
+            conv(ns.policy_layers[grp], x, nullptr, nullptr, CONV_LOGITS_F32, C3_MAX_SLABS, grp,
+                 std::min(128, ns.policy_ch - grp * 128));
+    {
         NetProfile* prof = ns.profile;
         if (prof) TB_CUDA(cudaEventRecord(prof->ev[2 * prof->n], e->stream));
-        ConvParams p{};
-        conv_params_set_layout(p, N);
-        p.in = in; p.res = res; p.out = out; p.out_f32 = ns.logits.as<float>(); p.partials = ns.partials.as<float2>();
-        p.w = L.w.as<__nv_bfloat16>(); p.bias = L.bias.as<float>();
-        p.S = S; p.tiles = tiles; p.n_boards = boards; p.slabs = slabs; p.mode = mode;
-        p.out_ch_offset = grp * 128; p.out_ch_valid = ch_valid; p.group = grp;
         TB_CUDA(conv3x3_tc3_launch(p, e->num_sms, e->stream));
         e->launches++;
         if (prof) {
             TB_CUDA(cudaEventRecord(prof->ev[2 * prof->n + 1], e->stream));
             prof->n++;
         }
-        return TAK_OK;
-    };
-    // initial conv + BN + ReLU (net6.rs:72-76); only ceil(c_in/16) K-slabs carry input planes
-    if (int r = conv(ns.layers[0], x, nullptr, y, CONV_RELU, (ns.c_in + 15) / 16, 0, 128)) return r;
-    std::swap(x, y);
-    // residual tower (res_block.rs:14-22)
-    for (int blk = 0; blk < ns.blocks; ++blk) {
-        if (int r = conv(ns.layers[1 + 2 * blk], x, nullptr, t, CONV_RELU, C3_MAX_SLABS, 0, 128)) return r;
-        if (int r = conv(ns.layers[2 + 2 * blk], t, x, y, CONV_RES_RELU, C3_MAX_SLABS, 0, 128)) return r;
-        std::swap(x, y);
     }
-    ns.trunk_out = x;
     // heads
     if (ns.arch == 6) {
-        for (int grp = 0; grp < ns.policy_groups; ++grp) {
-            const int valid = std::min(128, ns.policy_ch - grp * 128);
-            if (int r = conv(ns.policy_layers[grp], x, nullptr, nullptr, CONV_LOGITS_F32, C3_MAX_SLABS, grp, valid))
-                return r;
-        }
         k_policy_stats_conv<N><<<wblocks, 256, 0, e->stream>>>(ns.partials.as<float2>(), S, ns.policy_groups, boards,
                                                                ns.stats.as<float2>());
         if (d_policy_out) {

@@ -119,11 +119,17 @@ int main(int argc, char** argv) {
     std::vector<float> h_ref(dense);
     CK(cudaMemcpy(h_ref.data(), d_ref, dense * 4, cudaMemcpyDeviceToHost));
 
+    auto layer = [&](const __nv_bfloat16* in, const __nv_bfloat16* res, __nv_bfloat16* out, int mode, int ch_valid) {
+        ConvLayerDesc d{};
+        d.in = in; d.res = res; d.out = out; d.out_f32 = d_logits; d.partials = d_part; d.w = d_wpacked;
+        d.bias = d_bias; d.slabs = slabs; d.mode = mode; d.out_ch_offset = 0; d.out_ch_valid = ch_valid; d.group = 0;
+        return d;
+    };
     auto params = [&](int mode, int ch_valid) {
         ConvParams p = lay;
-        p.in = d_in; p.res = d_res; p.out = d_out; p.out_f32 = d_logits; p.partials = d_part; p.w = d_wpacked;
-        p.bias = d_bias; p.S = S; p.tiles = tiles; p.n_boards = n_boards; p.slabs = slabs; p.mode = mode;
-        p.out_ch_offset = 0; p.out_ch_valid = ch_valid; p.group = 0;
+        p.S = S; p.tile_begin = 0; p.tile_end = tiles; p.n_boards = n_boards;
+        p.n_layers = 1;
+        p.layers[0] = layer(d_in, d_res, d_out, mode, ch_valid);
         return p;
     };
 
@@ -194,6 +200,46 @@ int main(int argc, char** argv) {
         }
     }
 
+    // ---- fused tower: three chained layers in ONE launch must equal three single-layer launches bit for bit ----
+    if (slabs == 8) {
+        __nv_bfloat16 *d_a, *d_b, *d_c1, *d_c2;
+        CK(cudaMalloc(&d_a, act_elems * 2));
+        CK(cudaMalloc(&d_b, act_elems * 2));
+        CK(cudaMalloc(&d_c1, act_elems * 2));
+        CK(cudaMalloc(&d_c2, act_elems * 2));
+        for (int sms : {prop.multiProcessorCount, 24, 5}) {
+            ConvParams q = lay;
+            q.S = S; q.tile_begin = 0; q.tile_end = tiles; q.n_boards = n_boards;
+            const ConvLayerDesc l0 = layer(d_in, nullptr, d_a, 0, 128), l1 = layer(d_a, nullptr, d_b, 0, 128);
+            for (int pass = 0; pass < 2; ++pass) {
+                __nv_bfloat16* d_c = pass ? d_c2 : d_c1;
+                CK(cudaMemset(d_a, 0xFF, act_elems * 2));
+                CK(cudaMemset(d_b, 0xFF, act_elems * 2));
+                CK(cudaMemset(d_c, 0xFF, act_elems * 2));
+                const ConvLayerDesc l2 = layer(d_b, d_a, d_c, 1, 128);
+                if (pass == 0) {
+                    for (const ConvLayerDesc& l : {l0, l1, l2}) {
+                        q.n_layers = 1; q.layers[0] = l;
+                        CK(conv3x3_tc3_launch(q, sms, 0));
+                    }
+                } else {
+                    q.n_layers = 3; q.layers[0] = l0; q.layers[1] = l1; q.layers[2] = l2;
+                    CK(conv3x3_tc3_launch(q, sms, 0));
+                }
+                cudaError_t e = cudaDeviceSynchronize();
+                if (e != cudaSuccess) { printf("tower pass %d sms %d: kernel failed: %s\n", pass, sms, cudaGetErrorString(e)); return 3; }
+            }
+            std::vector<__nv_bfloat16> h1(act_elems), h2(act_elems);
+            CK(cudaMemcpy(h1.data(), d_c1, act_elems * 2, cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(h2.data(), d_c2, act_elems * 2, cudaMemcpyDeviceToHost));
+            const bool same = memcmp(h1.data(), h2.data(), act_elems * 2) == 0;
+            double sum = 0;
+            for (size_t i = 0; i < act_elems; i += 97) sum += __bfloat162float(h2[i]);
+            printf("tower 3 layers fused vs separate, grid<=%3d: %s (checksum %.3f)\n", sms, same ? "identical  ok" : "DIFFERENT  <-- FAIL", sum);
+            if (!same) ++fails;
+        }
+    }
+
     // ---- timing (mode 1, the res-block conv) ----
     {
         ConvParams p = params(1, 128);
@@ -213,6 +259,20 @@ int main(int argc, char** argv) {
         const double issued = 2.0 * tiles * 256.0 * 128.0 * 9.0 * c_in;
         printf("timing: %.1f us/layer  useful %.1f TFLOP/s  issued %.1f TFLOP/s\n", per * 1e6, useful / per * 1e-12,
                issued / per * 1e-12);
+        // a 32-layer tower in one launch (ping-pong between two buffers; values are irrelevant here)
+        ConvParams q = p;
+        q.n_layers = 32;
+        for (int l = 0; l < 32; ++l) q.layers[l] = layer(l & 1 ? d_out : d_in, nullptr, l & 1 ? d_in : d_out, 0, 128);
+        for (int i = 0; i < 2; ++i) CK(conv3x3_tc3_launch(q, prop.multiProcessorCount, 0));
+        CK(cudaEventRecord(e0));
+        const int reps2 = 5;
+        for (int i = 0; i < reps2; ++i) CK(conv3x3_tc3_launch(q, prop.multiProcessorCount, 0));
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        const double per2 = ms / reps2 / 32 * 1e-3;
+        printf("timing, 32-layer tower in one launch: %.1f us/layer  useful %.1f TFLOP/s  issued %.1f TFLOP/s\n",
+               per2 * 1e6, useful / per2 * 1e-12, issued / per2 * 1e-12);
     }
     printf(fails ? "SELFTEST FAILED\n" : "SELFTEST PASSED\n");
     return fails ? 1 : 0;
