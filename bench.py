@@ -163,6 +163,27 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------------------------
+def in_threads(fns):
+    """Run the callables concurrently (ctypes releases the GIL inside the C ABI) and return their results in order."""
+    out = [None] * len(fns)
+    err = []
+
+    def wrap(i, f):
+        try:
+            out[i] = f()
+        except BaseException as ex:  # noqa: BLE001 - re-raised below
+            err.append(ex)
+
+    ts = [threading.Thread(target=wrap, args=(i, f)) for i, f in enumerate(fns)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    if err:
+        raise err[0]
+    return out
+
+
 def run_b200(args):
     import torch
 
@@ -183,18 +204,29 @@ def run_b200(args):
         torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
 
-    G, R, n = args.games, args.rollouts, 6
-    eng = tb.Engine(n, G, device=local, nodes_per_game=args.nodes_per_game, max_batch=G)
-    eng.net_create(6)
-    # weights: rank 0 draws them, NCCL broadcasts the fp32 blob over NVLink, every rank folds/packs its own copy
+    # Games never interact, so a GPU's games are split over `replicas` independent engines (own stream, search trees and
+    # network replica) driven by one host thread each: while one replica's conv tower owns the tensor cores, the other's
+    # MCTS / encode / head kernels run beside it on the same SMs.
+    E = max(1, args.replicas)
+    G = args.games if args.games else 5328 * E          # games per GPU; 5328 = 148 SMs x 6 tiles x 6 boards
+    Gr = G // E
+    G = Gr * E
+    R, n = args.rollouts, 6
     elems = W.blob_size(6)
+    # weights: rank 0 draws them, NCCL broadcasts the fp32 blob over NVLink, every replica folds/packs its own copy
     blob_dev = par.broadcast_weights(W.random_weights(6, seed=0) if rank == 0 else None, elems, dev)
     torch.cuda.synchronize()
-    eng.net_load_weights_device(blob_dev.data_ptr(), elems)
+    engines = []
+    for r in range(E):
+        eng = tb.Engine(n, Gr, device=local, nodes_per_game=args.nodes_per_game, max_batch=Gr)
+        eng.net_create(6)
+        eng.net_load_weights_device(blob_dev.data_ptr(), elems)
+        engines.append(eng)
 
     def barrier():
         torch.cuda.synchronize()
-        eng.sync()
+        for eng in engines:
+            eng.sync()
         if dist:
             dist.barrier()
 
@@ -205,66 +237,89 @@ def run_b200(args):
         return par.sum_over_ranks(x, dev)
 
     # ---------------- device-resident self-play: `value` ----------------
-    eng.selfplay_begin(rollouts=R, half_komi=4, instant_win=1, exploit_ply=40, noise_ply=80, noise_alpha=0.2,
-                       noise_ratio=0.3, seed=0x7A4B, game_id_base=par.game_id_base(rank, G))
-    replay_bytes = 0
-    for _ in range(args.warmup):
-        eng.selfplay_step(1)
-        eng.selfplay_drain(4 * G)
+    for r, eng in enumerate(engines):
+        eng.selfplay_begin(rollouts=R, half_komi=4, instant_win=1, exploit_ply=40, noise_ply=80, noise_alpha=0.2,
+                           noise_ratio=0.3, seed=0x7A4B, game_id_base=par.game_id_base(rank * E + r, Gr))
+
+    def warm(eng):
+        for _ in range(args.warmup):
+            eng.selfplay_step(1)
+            eng.selfplay_drain(4 * Gr)
+
+    in_threads([lambda eng=eng: warm(eng) for eng in engines])
+
+    def timed(eng):
+        """K searched plies of every game of this replica; device time = CUDA events on the replica's stream."""
+        tot = {"ms": 0.0, "launches": 0, "evals": 0, "plies": 0, "done": 0, "recs": []}
+        left = args.steps
+        while left > 0:
+            k = min(left, 4)                       # the replay ring holds 16 records per game between drains
+            st = eng.selfplay_step(k)
+            tot["ms"] += st.device_ms
+            tot["launches"] += st.kernel_launches
+            tot["evals"] += st.evals
+            tot["plies"] += st.plies_played
+            tot["done"] += st.games_completed
+            left -= k
+            if left > 0:
+                tot["recs"] += eng.selfplay_drain(16 * Gr)
+        return tot
+
     sampler = ClockSampler(local)
     barrier()
     sampler.start()
     t_wall = time.perf_counter()
-    dev_ms, launches, evals, plies, games_done = 0.0, 0, 0, 0, 0
-    for _ in range(args.steps):
-        st = eng.selfplay_step(1)
-        dev_ms += st.device_ms
-        launches += st.kernel_launches
-        evals += st.evals
-        plies += st.plies_played
-        games_done += st.games_completed
+    res = in_threads([lambda eng=eng: timed(eng) for eng in engines])
     barrier()
     wall_ms = 1e3 * (time.perf_counter() - t_wall)
     clocks = sampler.stop()
-    recs = eng.selfplay_drain(16 * G)
+    dev_ms = max(r["ms"] for r in res)                  # replicas run concurrently: the GPU's time is the longest span
+    launches = sum(r["launches"] for r in res)
+    evals = sum(r["evals"] for r in res)
+    plies = sum(r["plies"] for r in res)
+    games_done = sum(r["done"] for r in res)
+    recs = sum((r["recs"] for r in res), [])
+    for eng in engines:
+        recs += eng.selfplay_drain(16 * Gr)
     # replay gather: fixed-size records, all-gathered over NCCL (outside the timed rollouts, as the trainer would)
     all_recs = par.gather_replay(recs, tb.ReplayRecord, dev)
     replay_bytes = len(all_recs) * C.sizeof(tb.ReplayRecord)
-    t_max = max_over_ranks(max(dev_ms, 0.0))           # device time (CUDA events on the engine stream), max over ranks
+    t_max = max_over_ranks(max(dev_ms, 0.0))           # device time (CUDA events on the engine streams), max over ranks
     total_plies = sum_over_ranks(float(plies))
     value = total_plies / (t_max / 1e3)
     total_launches = int(sum_over_ranks(float(launches)))
 
     # ---------------- end to end through the host-buffer ABI: `e2e` ----------------
-    ids = np.arange(G, dtype=np.int32)
-    host_states = eng.download(ids)  # the positions the self-play run reached, now living in host memory
+    ids = np.arange(Gr, dtype=np.int32)
+    host_states = [eng.download(ids) for eng in engines]  # the positions self-play reached, now in host memory
     state_bytes = {5: 288, 6: 384}.get(n, 384)
     h2d = G * state_bytes + G * 4
     stride = 256
     d2h = G * stride * 6 + G * 4 + G * 2
+    e2e_steps = max(1, min(args.steps, 2))
 
-    def e2e_step():
-        eng.upload(ids, host_states)           # H2D: packed game states from pinned staging
-        eng.tree_reset(ids)
-        eng.rollouts(ids, R)                   # select -> encode -> Net6 -> backup, R times
-        mv, vis, cnt = eng.children_batch(ids, stride)   # D2H: improved policy (visit counts) of every root
-        picks = eng.pick_move(ids)             # D2H: the moves to play
+    def e2e_run(i, steps):
+        eng = engines[i]
+        for _ in range(steps):
+            eng.upload(ids, host_states[i])        # H2D: packed game states from pinned staging
+            eng.tree_reset(ids)
+            eng.rollouts(ids, R)                   # select -> encode -> Net6 -> backup, R times
+            mv, vis, cnt = eng.children_batch(ids, stride)   # D2H: improved policy (visit counts) of every root
+            picks = eng.pick_move(ids)             # D2H: the moves to play
         return int(vis.sum()), picks
 
-    e2e_step()
+    in_threads([lambda i=i: e2e_run(i, 1) for i in range(E)])
     barrier()
     t0 = time.perf_counter()
-    e2e_steps = max(1, min(args.steps, 2))
-    for _ in range(e2e_steps):
-        e2e_step()
+    in_threads([lambda i=i: e2e_run(i, e2e_steps) for i in range(E)])
     barrier()
     e2e_t = max_over_ranks(time.perf_counter() - t0)
     e2e_value = world * G * e2e_steps / e2e_t
 
-    # ---------------- roofline of the dominant kernel (conv3x3_tc_kernel), measured live ----------------
-    prof = eng.net_forward_profile(0, G, 10)
+    # ---------------- roofline of the dominant kernel (conv3x3_tc3_kernel = the whole conv tower), measured live -------
+    prof = engines[0].net_forward_profile(0, Gr, 10)
     pk = peaks()
-    conv_flop = prof["flop"] - G * (2.0 * 128 * 36)  # all but the value FC runs in the conv kernel
+    conv_flop = prof["flop"] - Gr * (2.0 * 128 * 36)  # all but the value FC runs in the conv kernel
     achieved = conv_flop / (prof["ms_conv"] * 1e-3) / 1e12
     roofline = {
         "bound": "tensor", "kernel": "conv3x3_tc3_kernel", "achieved": achieved, "peak": pk["bf16_burst"],
@@ -272,6 +327,7 @@ def run_b200(args):
         "peak_kind": "burst bf16 (kernel timed alone, CUDA events around each launch), " + pk["source"],
         "avg_launch_us": 1e3 * prof["ms_conv"] / prof["conv_launches"],
         "algorithmic_flop_per_launch": conv_flop / prof["conv_launches"],
+        "boards_per_launch": Gr,
         "step_frac_sustained": (value / world) * R * FLOP_PER_EVAL_NET6 / (pk["bf16_sustained"] * 1e12),
         "forward_ms": prof["ms_forward"], "conv_share_of_forward": prof["ms_conv"] / prof["ms_forward"],
     }
@@ -284,12 +340,14 @@ def run_b200(args):
             "warmup": args.warmup, "ms_per_step": t_max / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": "6x6 batched self-play, 800 rollouts/move, random-init Net6 (configs[2])",
-                       "games_per_gpu": G, "rollouts": R, "noise": "dirichlet(0.2) x0.3 below ply 80",
+                       "games_per_gpu": G, "replicas_per_gpu": E, "rollouts": R,
+                       "noise": "dirichlet(0.2) x0.3 below ply 80",
                        "pick": "visit-weighted sample below ply 40, argmax after", "instant_win": True,
-                       "l2": "inputs larger than L2: per rollout step the net streams >1 GB of activations "
-                             "(G/6 tiles x 256 slots x 256 B x 2 x 35 layers; 175 MB live per buffer at G=4096) and "
-                             "10 MB of weights, and the MCTS kernels walk a node pool of tens of GB",
-                       "parallelism": f"games sharded over {world} rank(s), no collective in the rollout loop"},
+                       "l2": "inputs larger than L2: every rollout step walks a node pool of tens of GB (12.6 MB per "
+                             "game) and evaluates other leaves; the conv tower keeps a tile group's activations in L2 "
+                             "by design and writes 36 KB of logits per leaf to HBM",
+                       "parallelism": f"games sharded over {world} rank(s) x {E} engine replica(s), no collective in "
+                                      "the rollout loop"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "what": "host game states -> tak_games_upload -> mcts_rollouts(800) -> mcts_children_batch + "
                             "mcts_pick_move -> host"},
@@ -302,7 +360,8 @@ def run_b200(args):
                       "games_completed": games_done, "replay_records_gathered_bytes": replay_bytes,
                       "net_evals_per_s": evals / (dev_ms / 1e3) if dev_ms else None},
         }
-    eng.close()
+    for eng in engines:
+        eng.close()
     if dist:
         dist.barrier()
         dist.destroy_process_group()
@@ -316,8 +375,9 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--games", type=int, default=7992,
-                    help="concurrent games per GPU (7992 = 148 SMs x 9 tiles x 6 boards: whole waves of conv tiles)")
+    ap.add_argument("--games", type=int, default=0,
+                    help="concurrent games per GPU (default 5328 per replica = 148 SMs x 6 conv tiles x 6 boards)")
+    ap.add_argument("--replicas", type=int, default=2, help="independent engine replicas per GPU (host thread each)")
     ap.add_argument("--rollouts", type=int, default=800)
     ap.add_argument("--nodes-per-game", type=int, default=1 << 18)
     args = ap.parse_args()

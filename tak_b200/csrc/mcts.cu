@@ -96,7 +96,9 @@ int mcts_launch_tree_reset(tak_engine* e, const int* d_ids, int n) {
 
 int mcts_launch_rollout(tak_engine* e, const int* d_ids, int n, int k, const uint8_t* d_enable) {
     MctsState& m = *e->mcts;
-    TB_DISPATCH_N(e->n, (k_mcts_rollout<N_><<<warp_blocks(n), GAME_THREADS, 0, e->stream>>>(
+    // 4 warps per block (80 registers/thread): small enough to share an SM with a resident conv-tower CTA of another
+    // engine replica working on the same GPU (bench.py runs two replicas per GPU so MCTS hides under the tower)
+    TB_DISPATCH_N(e->n, (k_mcts_rollout<N_><<<(n + 3) / 4, 128, 0, e->stream>>>(
                             m.view(), e->states.as<uint8_t>(), d_ids, n, k, d_enable)));
     e->launches++;
     m.queued = true;
@@ -106,7 +108,7 @@ int mcts_launch_rollout(tak_engine* e, const int* d_ids, int n, int k, const uin
 
 int mcts_launch_compact(tak_engine* e) {
     MctsState& m = *e->mcts;
-    k_mcts_compact<<<1, 1024, 0, e->stream>>>(m.pend_cnt.as<int>(), e->max_games, m.kcap, m.eval_index.as<int>(),
+    k_mcts_compact<<<1, 256, 0, e->stream>>>(m.pend_cnt.as<int>(), e->max_games, m.kcap, m.eval_index.as<int>(),
                                               m.eval_slot.as<int>(), m.eval_count.as<int>());
     e->launches++;
     TB_CUDA(cudaGetLastError());

@@ -299,7 +299,7 @@ class Engine:
         arr = (ReplayRecord * cap)()
         cnt = C.c_int32()
         check(self.lib.selfplay_drain(self._h, arr, cap, C.byref(cnt)))
-        return list(arr)[:cnt.value]
+        return [arr[i] for i in range(cnt.value)]
 
 
 # ---- single-object mirrors of the Rust types --------------------------------------------------------------------
