@@ -184,6 +184,53 @@ def in_threads(fns):
     return out
 
 
+PERFT6_D5 = 1_253_506_520  # tak/tests/perft.rs:98 (the value the reference keeps commented out)
+
+
+def movegen_mnodes(eng, world, rank, dev, pk):
+    """The metric's second half: movegen + play + result throughput as perft(5) of the 6x6 opening position through the
+    C ABI (tak_perft), breadth-first on the device.  With N ranks the 36 root moves are dealt round-robin and the counts
+    are summed with one all-reduce."""
+    from tak_b200 import parallel as par
+
+    depth = 5
+    eng.reset(0, 1, 0)                       # slot 0 of this rank's engine (self-play is over) holds the opening
+    root = eng.download([0])[0]
+    ms, nodes, mat = 0.0, 0, 0
+    eng.perft(root, 3)                       # warm-up (allocations)
+    if world == 1:
+        nodes = eng.perft(root, depth)
+        st = eng.perft_stats()
+        ms, mat = st["ms"], st["materialised"]
+    else:
+        moves = eng.possible_moves([0])[0]
+        for i, mv in enumerate(moves):
+            if i % world != rank:
+                continue
+            eng.upload([0], [root])
+            assert not eng.play([0], [int(mv)]).any()
+            nodes += eng.perft(eng.download([0])[0], depth - 1)
+            st = eng.perft_stats()
+            ms += st["ms"]
+            mat += st["materialised"]
+    total = int(par.sum_over_ranks(float(nodes), dev))
+    t_max = par.max_over_ranks(ms, dev)
+    mat_total = par.sum_over_ranks(float(mat), dev)
+    S, b = 384, 1_253_506_520 / 34_953_528     # packed state bytes; mean branching of the counted level
+    # HBM bytes the breadth-first expansion must move: every materialised node is written once (S + 2 B move) and read
+    # once by the next level's count and once by its expand; the 1.25e9 leaves are only counted on chip
+    algo_bytes = mat_total * (3 * S + 2)
+    gbs = algo_bytes / (t_max * 1e-3) / 1e9 if t_max else 0.0
+    return {"value": total / (t_max * 1e-3) / 1e6 if t_max else None, "unit": "Mnodes/s",
+            "workload": "6x6 perft depth 5 from the opening via tak_perft (movegen + play + result, bit-exact count)",
+            "nodes": total, "exact": total == PERFT6_D5, "ms": t_max, "materialised_states": int(mat_total),
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s",
+                         "frac": gbs / pk["hbm"] if pk["hbm"] else None,
+                         "note": "interior levels only (35.0 M states materialised); the leaf level is counted from "
+                                 "registers, so the kernel is issue-bound there, not HBM-bound",
+                         "mean_branching_last_level": b}}
+
+
 def run_b200(args):
     import torch
 
@@ -212,6 +259,7 @@ def run_b200(args):
     Gr = G // E
     G = Gr * E
     R, n = args.rollouts, 6
+    pk = peaks()
     elems = W.blob_size(6)
     # weights: rank 0 draws them, NCCL broadcasts the fp32 blob over NVLink, every replica folds/packs its own copy
     blob_dev = par.broadcast_weights(W.random_weights(6, seed=0) if rank == 0 else None, elems, dev)
@@ -318,12 +366,14 @@ def run_b200(args):
 
     # ---------------- roofline of the dominant kernel (conv3x3_tc3_kernel = the whole conv tower), measured live -------
     prof = engines[0].net_forward_profile(0, Gr, 10)
-    pk = peaks()
     conv_flop = prof["flop"] - Gr * (2.0 * 128 * 36)  # all but the value FC runs in the conv kernel
     achieved = conv_flop / (prof["ms_conv"] * 1e-3) / 1e12
     roofline = {
         "bound": "tensor", "kernel": "conv3x3_tc3_kernel", "achieved": achieved, "peak": pk["bf16_burst"],
-        "unit": "TFLOP/s", "frac": achieved / pk["bf16_burst"], "traffic": None,
+        "unit": "TFLOP/s", "frac": achieved / pk["bf16_burst"],
+        # dram__bytes_read.sum + dram__bytes_write.sum of one tower launch over 5328 boards (ncu --set full,
+        # profiles/r01_conv_tc3_ncu_full.txt), scaled to this launch's boards: logits + write-backs of the activations
+        "traffic": 1_748_107_824 * Gr / 5328,
         "peak_kind": "burst bf16 (kernel timed alone, CUDA events around each launch), " + pk["source"],
         "avg_launch_us": 1e3 * prof["ms_conv"] / prof["conv_launches"],
         "algorithmic_flop_per_launch": conv_flop / prof["conv_launches"],
@@ -331,6 +381,9 @@ def run_b200(args):
         "step_frac_sustained": (value / world) * R * FLOP_PER_EVAL_NET6 / (pk["bf16_sustained"] * 1e12),
         "forward_ms": prof["ms_forward"], "conv_share_of_forward": prof["ms_conv"] / prof["ms_forward"],
     }
+
+    # ---------------- movegen Mnodes/s: 6x6 perft(5) from the opening, root moves sharded over ranks ----------------
+    movegen = movegen_mnodes(engines[0], world, rank, dev, pk)
 
     line = None
     if rank == 0:
@@ -353,6 +406,7 @@ def run_b200(args):
                             "mcts_pick_move -> host"},
             "gpu_launches": total_launches,
             "roofline": roofline,
+            "movegen": movegen,
             "cpu_baseline": {"value": cpu["value"], "unit": UNIT, "cores": cpu["cores"], "kind": "port",
                              "sample": cpu["sample"]},
             "clocks": clocks,

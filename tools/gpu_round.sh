@@ -6,8 +6,8 @@ nvidia-smi --query-gpu=name,clocks.max.sm,power.limit --format=csv > gpurun_out/
 nproc >> gpurun_out/gpu.txt
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
 tail -5 gpurun_out/pytest_gpu.log
-timeout 300 ./build/conv_selftest 4096 6 > gpurun_out/conv_selftest.log 2>&1; tail -4 gpurun_out/conv_selftest.log
-timeout 600 python bench.py --steps 3 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; cat gpurun_out/bench.json; tail -3 gpurun_out/bench.err
-timeout 600 python bench.py --steps 3 --warmup 3 --games 8192 > gpurun_out/bench_g8192.json 2> gpurun_out/bench_g8192.err; cat gpurun_out/bench_g8192.json
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 3 --rollouts 20 > gpurun_out/b_ncu.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv3x3_tc2 -s 40 -c 3 -o gpurun_out/conv_tc2_full -f python tools/probe_forward.py 4096 2 > gpurun_out/ncu_full.log 2>&1; tail -3 gpurun_out/ncu_full.log
+timeout 300 ./build/conv_selftest 5328 6 > gpurun_out/conv_selftest.log 2>&1; tail -4 gpurun_out/conv_selftest.log
+timeout 900 python bench.py --steps 3 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; cat gpurun_out/bench.json; tail -n 3 gpurun_out/bench.err
+timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err; cat gpurun_out/bench_reference.json
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 3 --rollouts 20 --replicas 1 --games 5328 > gpurun_out/b_ncu.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv3x3_tc3 -s 2 -c 2 -o gpurun_out/conv_tc3_full -f python tools/probe_forward.py 5328 2 > gpurun_out/ncu_full.log 2>&1; tail -n 3 gpurun_out/ncu_full.log
