@@ -107,6 +107,8 @@ def cpu_selfplay_sample(rollouts_sample: int, full_rollouts: int, workers: int =
     from tak_b200 import weights as W
 
     n = 6
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core it can
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
     net = RefNet(6, W.random_weights(6, seed=seed), device="cpu")
     games, searches = [], []
     for i in range(workers):
@@ -216,7 +218,8 @@ def movegen_mnodes(eng, world, rank, dev, pk):
     total = int(par.sum_over_ranks(float(nodes), dev))
     t_max = par.max_over_ranks(ms, dev)
     mat_total = par.sum_over_ranks(float(mat), dev)
-    S, b = 384, 1_253_506_520 / 34_953_528     # packed state bytes; mean branching of the counted level
+    S = 384                                   # packed 6x6 state bytes
+    b = total / mat_total if mat_total else 0.0   # ~ mean branching of the counted level (92 from the opening)
     # HBM bytes the breadth-first expansion must move: every materialised node is written once (S + 2 B move) and read
     # once by the next level's count and once by its expand; the 1.25e9 leaves are only counted on chip
     algo_bytes = mat_total * (3 * S + 2)
@@ -226,8 +229,9 @@ def movegen_mnodes(eng, world, rank, dev, pk):
             "nodes": total, "exact": total == PERFT6_D5, "ms": t_max, "materialised_states": int(mat_total),
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s",
                          "frac": gbs / pk["hbm"] if pk["hbm"] else None,
-                         "note": "interior levels only (35.0 M states materialised); the leaf level is counted from "
-                                 "registers, so the kernel is issue-bound there, not HBM-bound",
+                         "note": "interior levels only (13.7 M states materialised at depth <= 4); the 1.25e9 leaves are "
+                                 "counted from registers (closed-form move counts), so that level is issue-bound, not "
+                                 "HBM-bound",
                          "mean_branching_last_level": b}}
 
 
@@ -387,7 +391,8 @@ def run_b200(args):
 
     line = None
     if rank == 0:
-        cpu = cpu_selfplay_sample(max(8, min(R, 24)), R)
+        # the CPU baseline is timed beside the GPU arm at N=1 only (at N>1 the other ranks' host threads share the cores)
+        cpu = cpu_selfplay_sample(max(8, min(R, 24)), R) if world == 1 else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": t_max / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -408,7 +413,7 @@ def run_b200(args):
             "roofline": roofline,
             "movegen": movegen,
             "cpu_baseline": {"value": cpu["value"], "unit": UNIT, "cores": cpu["cores"], "kind": "port",
-                             "sample": cpu["sample"]},
+                             "sample": cpu["sample"]} if cpu else None,
             "clocks": clocks,
             "extra": {"wall_ms_per_step": wall_ms / args.steps, "evals_per_step": evals / max(1, args.steps),
                       "games_completed": games_done, "replay_records_gathered_bytes": replay_bytes,
