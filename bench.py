@@ -199,7 +199,7 @@ def movegen_mnodes(eng, world, rank, dev, pk):
     eng.reset(0, 1, 0)                       # slot 0 of this rank's engine (self-play is over) holds the opening
     root = eng.download([0])[0]
     ms, nodes, mat = 0.0, 0, 0
-    eng.perft(root, 3)                       # warm-up (allocations)
+    eng.perft(root, depth)                   # warm-up at full depth: the frontier arenas are allocated here
     if world == 1:
         nodes = eng.perft(root, depth)
         st = eng.perft_stats()
