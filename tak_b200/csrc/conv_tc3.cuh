@@ -15,8 +15,12 @@
 //   weights  w[slab k = 0..7][ky][kx][kchunk 2][c_out 128][8 c_in] bf16: the K-major no-swizzle UMMA operand image in
 //   consumption order, one 36 KiB bulk copy per slab.
 //
-// GEMM view per tile: D[256 slots x 128 c_out] += A[256 x 1152] * W[128 x 1152]^T, two M=128,N=128 fp32 accumulators
-// in TMEM, issued as 8 K-SLABS (16 input channels) x 9 taps x 2 halves of tcgen05.mma.cta_group::1.kind::f16 (K=16).
+// GEMM view per tile, TRANSPOSED: D^T[128 c_out x 256 slots] += W[128 x 1152] * X[256 x 1152]^T -- the weights are the
+// A operand (M = 128), the activation slab is the B operand (N = 256), one M=128,N=256 fp32 accumulator (256 TMEM
+// columns, 2 stages), issued as 8 K-SLABS (16 input channels) x 9 taps of tcgen05.mma.cta_group::1.kind::f16 (K=16).
+// N = 256 matters: an SS-mode instruction reads its operands from shared memory, 4+4 KiB per 64 math cycles at
+// N = 128 (= all 128 B/clk: measured 79 cycles/instruction) but 4+8 KiB per 128 math cycles at N = 256; the same
+// tower ran 42.6 us/layer (1.33 PFLOP/s useful) with two N=128 halves per tap and 35.9 us with one N=256 instruction.
 // The slab-outer order is what makes the kernel fit and fast: an activation slab ([zero halo][256 rows][zero halo] x
 // 32 B, 11.5 KiB) is dead after its 18 MMAs, so one pipeline stage = {activation slab, the slab's 9 taps of weights
 // (36 KiB)} = 47.5 KiB, a 4-stage ring holds 144 KiB of weights in flight, and the issuer needs ONE tcgen05.commit per
@@ -28,8 +32,8 @@
 // Warp roles (320 threads, 1 persistent CTA per SM):
 //   warp 0     producer: cp.async.bulk of the stage's activation slab (2 x 4 KiB) and weight slab (36 KiB) -> full
 //   warp 1     TMEM allocator + single-thread tcgen05.mma issuer; tcgen05.commit -> empty / acc_full
-//   warps 2-9  epilogue: residual prefetch, tcgen05.ld (software pipelined) -> +bias (+residual) -> ReLU -> pad mask
-//              -> bf16 strip planes, or fp32 logits + per-slot softmax partials for the policy head
+//   warps 2-9  epilogue: residual prefetch, tcgen05.ld (software pipelined) -> 8x8 shfl transpose -> +bias (+residual)
+//              -> ReLU -> pad mask -> bf16 strip planes, or fp32 logits + per-slot softmax partials (policy head)
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -79,7 +83,7 @@ struct ConvLayerDesc {
     const __nv_bfloat16* res;   // strip planes (mode 1) or nullptr
     __nv_bfloat16* out;         // strip planes (modes 0/1)
     float* out_f32;             // [out_ch_total][S] (mode 2)
-    float2* partials;           // mode 2: [group][S] per-slot {max, sum exp(l - max)} over this group's valid channels
+    float2* partials;           // mode 2: [group*4 + lane quarter][S] per-slot {max, sum exp(l - max)} over 32 channels
     const __nv_bfloat16* w;     // [slabs][3][3][2][128][8]
     const float* bias;          // [128]
     int slabs;                  // ceil(c_in / 16) <= 8
@@ -121,6 +125,22 @@ enum : int {
     C3B_READY = C3B_ACC_EMPTY + 2,         // [C3_GROUP] outputs of (layer, tile-in-group) stored by all 8 epilogue warps
     C3B_COUNT = C3B_READY + C3_GROUP
 };
+
+// one round of the 8x8 block transpose across the 8 lanes of a channel chunk (blocks = x[8i + b], i = 0..3)
+template <int M>
+__device__ __forceinline__ void transpose8_stage(uint32_t (&x)[32], int j) {
+    const bool up = (j & M) != 0;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+        if (b & M) continue;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t send = up ? x[8 * i + b] : x[8 * i + (b | M)];
+            const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, M);
+            if (up) x[8 * i + b] = recv; else x[8 * i + (b | M)] = recv;
+        }
+    }
+}
 
 // work-item walk shared by the three roles: groups of tiles, all layers per group
 struct TowerWalk {
@@ -227,7 +247,7 @@ static __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc3_kernel(const
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16_f32(128, 128);
+            constexpr uint32_t idesc = umma_idesc_bf16_f32(128, 256);  // D^T[c_out 128 x 256 slots]
             uint32_t scnt = 0;
             int it = 0;
             for (int g = 0; g < walk.n_groups; ++g) {
@@ -252,13 +272,9 @@ static __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc3_kernel(const
 #pragma unroll
                             for (int tap = 0; tap < 9; ++tap) {
                                 const int shift = (tap / 3 - 1) * p.pitch + (tap % 3 - 1);
-                                const uint64_t bdesc = umma_desc_kmajor_noswz(w_base + tap * 4096, 128 * 16, 128);
-#pragma unroll
-                                for (int t = 0; t < 2; ++t) {
-                                    const uint64_t adesc =
-                                        umma_desc_kmajor_noswz(a_base + (t * 128 + shift) * 16, C3_ROWS * 16, 128);
-                                    umma_bf16(d_base + t * 128, adesc, bdesc, idesc, (k | tap) != 0);
-                                }
+                                const uint64_t wdesc = umma_desc_kmajor_noswz(w_base + tap * 4096, 128 * 16, 128);
+                                const uint64_t xdesc = umma_desc_kmajor_noswz(a_base + shift * 16, C3_ROWS * 16, 128);
+                                umma_bf16(d_base, wdesc, xdesc, idesc, (k | tap) != 0);
                             }
                             // ONE commit per slab: tcgen05.commit costs the issue stream ~200 cycles (measured), so
                             // the activation slab and its weights are released together
@@ -270,15 +286,29 @@ static __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc3_kernel(const
             }
         }
     } else if (warp >= 2 && warp < 10) {
-        // ===================== epilogue (8 warps, one thread per slot row) =====================
-        const int ew = warp - 2;          // 0..7
-        const int t = ew >> 2;            // accumulator half 0/1
-        const int quarter = warp & 3;     // TMEM lane quarter this warp may access
-        const int row = t * 128 + quarter * 32 + lane;
-        const int etid = threadIdx.x - 64;  // 0..255 among the epilogue threads
-        const int ry = row / p.pitch, rrem = row - ry * p.pitch;
-        const int rj = rrem / p.bw, rx = rrem - rj * p.bw;
-        const bool in_frame = ry < p.n && rx < p.n;   // a real square (not a pad column / tile remainder)
+        // ===================== epilogue (8 warps) =====================
+        // The accumulator is D^T: TMEM lane = output channel, column = slot.  Warp w reads lane quarter q = w%4
+        // (channels 32q..32q+31) and column half h (slots 128h..128h+127) in 4 chunks of 32 columns; a thread starts
+        // with ONE channel x 32 slots.  The strip planes want 8 channels x 16 B per slot, so the 8 lanes of a channel
+        // chunk transpose their 8x8 blocks through 3 rounds of shfl.xor (fp32, before any rounding): lane j of group g
+        // ends with channels 8*(4q+g)..+7 of slots 8i+j (i = 0..3) -> 16 B vector loads of the residual and 16 B
+        // stores, 128 B contiguous across the 8 lanes.
+        const int q = warp & 3;
+        const int h = (warp - 2) >> 2;
+        const int grp8 = lane >> 3, j = lane & 7;
+        const int chunk = 4 * q + grp8;               // 8-channel chunk this thread stores
+        const int etid = threadIdx.x - 64;            // 0..255 among the epilogue threads
+        // frame validity / board index of this thread's 16 slots per tile (slot = 128h + 32cc + 8i + j)
+        uint32_t frame_mask = 0;
+        uint64_t board_of = 0;                        // 4 bits per slot
+#pragma unroll
+        for (int idx = 0; idx < 16; ++idx) {
+            const int sl = 128 * h + 32 * (idx >> 2) + 8 * (idx & 3) + j;
+            const int ry = sl / p.pitch, rrem = sl - ry * p.pitch;
+            const int rj = rrem / p.bw, rx = rrem - rj * p.bw;
+            if (ry < p.n && rx < p.n) frame_mask |= 1u << idx;   // a real square (not a pad column / tile remainder)
+            board_of |= static_cast<uint64_t>(rj & 15) << (4 * idx);
+        }
         griddep_wait();  // output / residual buffers belong to earlier kernels until they complete
         int it = 0;
         for (int g = 0, j0 = 0; g < walk.n_groups; j0 += walk.group_size(g), ++g) {
@@ -290,23 +320,36 @@ static __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc3_kernel(const
                     const int tile = tile0 + (j0 + jj) * int(gridDim.x);
                     const int as = it & 1;
                     const uint32_t ph2 = (it >> 1) & 1;
-                    const size_t slot = static_cast<size_t>(tile) * C3_TILE_M + row;
-                    const bool valid = in_frame && (tile * p.bpt + rj) < p.n_boards;
+                    const size_t slot0 = static_cast<size_t>(tile) * C3_TILE_M + 128 * h + j;
+                    uint32_t valid_mask = 0;
+#pragma unroll
+                    for (int idx = 0; idx < 16; ++idx)
+                        if (((frame_mask >> idx) & 1) && tile * p.bpt + int((board_of >> (4 * idx)) & 15) < p.n_boards)
+                            valid_mask |= 1u << idx;
                     // bias of this layer -> shared (double buffered by accumulator stage; the named barrier keeps the
                     // 256 epilogue threads within one work item of each other)
                     float* bias_s = s_bias + as * 128;
                     if (etid < 128) bias_s[etid] = ld.bias[etid];
                     asm volatile("bar.sync 1, 256;" ::: "memory");
-                    // the residual does not depend on the MMAs: fetch the whole row before waiting for the accumulator.
+                    // the residual does not depend on the MMAs: the first chunk's 4 x 16 B are fetched before waiting for
+                    // the accumulator, the next chunk's while the current one is processed (registers: a 320-thread CTA
+                    // is allocated as 12 warps, i.e. 168 registers per thread at most).
                     // Plain (coherent) loads: these slots were stored by this very thread two layers ago.
-                    uint4 res[16];
-                    if (mode == CONV_RES_RELU) {
+                    auto load_res = [&](int cc, uint4 (&dst)[4]) {
 #pragma unroll
-                        for (int c = 0; c < 16; ++c) {
-                            res[c] = make_uint4(0, 0, 0, 0);
-                            if (valid) res[c] = *reinterpret_cast<const uint4*>(ld.res + (static_cast<size_t>(c) * p.S + slot) * 8);
+                        for (int i = 0; i < 4; ++i) {
+                            dst[i] = make_uint4(0, 0, 0, 0);
+                            if ((valid_mask >> (cc * 4 + i)) & 1)
+                                dst[i] = *reinterpret_cast<const uint4*>(
+                                    ld.res + (static_cast<size_t>(chunk) * p.S + slot0 + 32 * cc + 8 * i) * 8);
                         }
-                    }
+                    };
+                    uint4 res[2][4];
+                    if (mode == CONV_RES_RELU) load_res(0, res[0]);
+                    float bias8[8];
+#pragma unroll
+                    for (int b = 0; b < 8; ++b) bias8[b] = bias_s[chunk * 8 + b];
+                    const float bias_c = bias_s[32 * q + lane];
                     mbar_wait(BAR(C3B_ACC_FULL + as), ph2);
                     tc_fence_after();
 #if defined(CONV_EXP) && (CONV_EXP & 2)
@@ -316,66 +359,87 @@ static __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc3_kernel(const
                         continue;
                     }
 #endif
-                    const uint32_t taddr = tmem_base + as * 256 + t * 128 + (static_cast<uint32_t>(quarter * 32) << 16);
-                    uint32_t r[2][32];
-                    float pm = -INFINITY, psum = 0.f;  // mode 2: running softmax partial of this slot
-                    tmem_ld32(taddr, r[0]);
+                    const uint32_t taddr = tmem_base + as * 256 + 128 * h + (static_cast<uint32_t>(q * 32) << 16);
+                    uint32_t x[32];
 #pragma unroll
                     for (int cc = 0; cc < 4; ++cc) {
+                        tmem_ld32(taddr + cc * 32, x);   // 8 epilogue warps hide each other's TMEM latency
+                        if (mode == CONV_RES_RELU && cc < 3) load_res(cc + 1, res[(cc + 1) & 1]);
                         tmem_ld_wait();
-                        if (cc < 3) tmem_ld32(taddr + (cc + 1) * 32, r[(cc + 1) & 1]);  // next chunk in flight
-                        const uint32_t(&rc)[32] = r[cc & 1];
                         if (mode == CONV_LOGITS_F32) {
-                            float v[32];
-                            float cm = -INFINITY;
+                            // logits straight from the un-transposed registers: one channel, 32 consecutive slots
+                            const int ch = 32 * q + lane;
+                            const bool ch_ok = ch < ld.out_ch_valid;
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) {
-                                const int ch = cc * 32 + j;
-                                v[j] = __uint_as_float(rc[j]) + bias_s[ch];
-                                if (ch < ld.out_ch_valid) {
-                                    ld.out_f32[static_cast<size_t>(ld.out_ch_offset + ch) * p.S + slot] = valid ? v[j] : 0.0f;
-                                    cm = fmaxf(cm, v[j]);
-                                }
+                            for (int s4 = 0; s4 < 32; s4 += 4) {
+                                float4 o;
+                                o.x = __uint_as_float(x[s4 + 0]) + bias_c;
+                                o.y = __uint_as_float(x[s4 + 1]) + bias_c;
+                                o.z = __uint_as_float(x[s4 + 2]) + bias_c;
+                                o.w = __uint_as_float(x[s4 + 3]) + bias_c;
+                                x[s4 + 0] = __float_as_uint(ch_ok ? o.x : -INFINITY);
+                                x[s4 + 1] = __float_as_uint(ch_ok ? o.y : -INFINITY);
+                                x[s4 + 2] = __float_as_uint(ch_ok ? o.z : -INFINITY);
+                                x[s4 + 3] = __float_as_uint(ch_ok ? o.w : -INFINITY);
+                                if (ch_ok)
+                                    *reinterpret_cast<float4*>(ld.out_f32 + static_cast<size_t>(ld.out_ch_offset + ch) * p.S +
+                                                               (slot0 - j) + 32 * cc + s4) = o;
                             }
-                            if (cm > -INFINITY) {
-                                const float nm = fmaxf(pm, cm);
-                                float s = psum * __expf(pm - nm);
+                        }
+                        // 8x8 block transpose across the 8 lanes of a channel chunk: x[8i+b] (channel j, slot 8i+b) ->
+                        // x[8i+b] (channel b, slot 8i+j)
+                        transpose8_stage<4>(x, j);
+                        transpose8_stage<2>(x, j);
+                        transpose8_stage<1>(x, j);
+                        if (mode == CONV_LOGITS_F32) {
+                            // per-slot softmax partial over this warp's 32 channels: 8 in-thread, then the 4 lane groups
 #pragma unroll
-                                for (int j = 0; j < 32; ++j)
-                                    if (cc * 32 + j < ld.out_ch_valid) s += __expf(v[j] - nm);
-                                pm = nm;
-                                psum = s;
+                            for (int i = 0; i < 4; ++i) {
+                                float mx = -INFINITY;
+#pragma unroll
+                                for (int b = 0; b < 8; ++b) mx = fmaxf(mx, __uint_as_float(x[8 * i + b]));
+                                mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
+                                mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
+                                float sum = 0.f;
+                                if (mx > -INFINITY) {
+#pragma unroll
+                                    for (int b = 0; b < 8; ++b) sum += __expf(__uint_as_float(x[8 * i + b]) - mx);
+                                }
+                                sum += __shfl_xor_sync(0xffffffffu, sum, 8);
+                                sum += __shfl_xor_sync(0xffffffffu, sum, 16);
+                                if (grp8 == 0)
+                                    ld.partials[static_cast<size_t>(ld.group * 4 + q) * p.S + slot0 + 32 * cc + 8 * i] =
+                                        make_float2(mx, sum);
                             }
                         } else {
 #pragma unroll
-                            for (int q = 0; q < 4; ++q) {  // 4 chunks of 8 channels
-                                const int chunk = cc * 4 + q;
+                            for (int i = 0; i < 4; ++i) {
+                                const int idx = cc * 4 + i;
+                                const bool valid = (valid_mask >> idx) & 1;
                                 float v[8];
 #pragma unroll
-                                for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(rc[q * 8 + j]) + bias_s[chunk * 8 + j];
+                                for (int b = 0; b < 8; ++b) v[b] = __uint_as_float(x[8 * i + b]) + bias8[b];
                                 if (mode == CONV_RES_RELU) {
-                                    const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&res[chunk]);
+                                    const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&res[cc & 1][i]);
 #pragma unroll
-                                    for (int j = 0; j < 4; ++j) {
-                                        float2 f = __bfloat1622float2(rb[j]);
-                                        v[2 * j] += f.x;
-                                        v[2 * j + 1] += f.y;
+                                    for (int b = 0; b < 4; ++b) {
+                                        float2 f = __bfloat1622float2(rb[b]);
+                                        v[2 * b] += f.x;
+                                        v[2 * b + 1] += f.y;
                                     }
                                 }
                                 uint4 ov;
                                 __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&ov);
 #pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    float a = valid ? fmaxf(v[2 * j], 0.0f) : 0.0f;
-                                    float b = valid ? fmaxf(v[2 * j + 1], 0.0f) : 0.0f;
-                                    ob[j] = __floats2bfloat162_rn(a, b);
+                                for (int b = 0; b < 4; ++b) {
+                                    float lo = valid ? fmaxf(v[2 * b], 0.0f) : 0.0f;
+                                    float hi = valid ? fmaxf(v[2 * b + 1], 0.0f) : 0.0f;
+                                    ob[b] = __floats2bfloat162_rn(lo, hi);
                                 }
-                                *reinterpret_cast<uint4*>(ld.out + (static_cast<size_t>(chunk) * p.S + slot) * 8) = ov;
+                                *reinterpret_cast<uint4*>(ld.out + (static_cast<size_t>(chunk) * p.S + slot0 + 32 * cc + 8 * i) * 8) = ov;
                             }
                         }
                     }
-                    if (mode == CONV_LOGITS_F32)
-                        ld.partials[static_cast<size_t>(ld.group) * p.S + slot] = make_float2(pm, psum);
                     tc_fence_before();
                     // the stores above are read back by the bulk-copy engine (async proxy) for the next layer
                     asm volatile("fence.proxy.async;" ::: "memory");

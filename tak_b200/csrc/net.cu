@@ -138,7 +138,7 @@ int net_ensure_capacity(tak_engine* e, int boards) {
     }
     if (ns.arch == 6) {
         TB_CUDA(ns.logits.ensure(size_t(ns.policy_groups) * 128 * S * 4));
-        TB_CUDA(ns.partials.ensure(size_t(ns.policy_groups) * S * 8));
+        TB_CUDA(ns.partials.ensure(size_t(ns.policy_groups) * 4 * S * 8));
     } else if (ns.arch == 5) {
         TB_CUDA(ns.logits.ensure(size_t(boards) * ns.policy_out * 4));
     }
@@ -199,7 +199,7 @@ static int forward_t(tak_engine* e, const uint8_t* d_states, const int* d_index,
     }
     // heads
     if (ns.arch == 6) {
-        k_policy_stats_conv<N><<<wblocks, 256, 0, e->stream>>>(ns.partials.as<float2>(), S, ns.policy_groups, boards,
+        k_policy_stats_conv<N><<<wblocks, 256, 0, e->stream>>>(ns.partials.as<float2>(), S, ns.policy_groups * 4, boards,
                                                                ns.stats.as<float2>());
         if (d_policy_out) {
             e->launches++;

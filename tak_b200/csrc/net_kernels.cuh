@@ -142,8 +142,8 @@ __device__ __forceinline__ float block_reduce_sum(float v, float* s_tmp) {
 }
 
 // Net6-style head (policy conv): softmax statistics over ALL channels x squares of one board (net6.rs:100-103).
-// The conv epilogue already reduced every slot's channels to {max, sum exp(l - max)} per 128-channel group
-// (partials[group][S]); one warp per board merges the N*N x groups partials: stats[b] = {max, sum of exp(l - max)}.
+// The conv epilogue already reduced every slot's channels to {max, sum exp(l - max)} per 32-channel lane quarter
+// (partials[group*4 + quarter][S]); one warp per board merges the N*N x parts partials: stats[b] = {max, sum of exp(l - max)}.
 template <int N>
 __global__ void __launch_bounds__(256)
     k_policy_stats_conv(const float2* partials, int S, int groups, int n_boards, float2* stats) {
