@@ -377,7 +377,7 @@ def run_b200(args):
         "unit": "TFLOP/s", "frac": achieved / pk["bf16_burst"],
         # dram__bytes_read.sum + dram__bytes_write.sum of one tower launch over 5328 boards (ncu --set full,
         # profiles/r01_conv_tc3_ncu_full.txt), scaled to this launch's boards: logits + write-backs of the activations
-        "traffic": 1_748_107_824 * Gr / 5328,
+        "traffic": 1_799_644_848 * Gr / 5328,
         "peak_kind": "burst bf16 (kernel timed alone, CUDA events around each launch), " + pk["source"],
         "avg_launch_us": 1e3 * prof["ms_conv"] / prof["conv_launches"],
         "algorithmic_flop_per_launch": conv_flop / prof["conv_launches"],

@@ -234,6 +234,24 @@ int32_t selfplay_begin(tak_engine_t* e, const tak_selfplay_config_t* cfg);
 int32_t selfplay_step(tak_engine_t* e, int32_t moves, tak_selfplay_stats_t* out_stats);
 int32_t selfplay_drain(tak_engine_t* e, tak_replay_record_t* out, int32_t cap, int32_t* out_count);
 
+/* ---- alpha_tak::Example: replay text format and 8-fold symmetry augmentation -----
+ * tak_example_format     Display for Example<N> (alpha-tak/src/example.rs:81-100):
+ *                        "tps;white_stones;white_caps;black_stones;black_caps;half_komi;result;mov:visits,mov:visits"
+ * tak_example_parse      FromStr for Example<N> (example.rs:102-133): the game comes from the TPS, then the reserves
+ *                        and half_komi fields overwrite what the TPS implied; game_id / game_serial are zeroed
+ * tak_symmetry_move      Symmetry::<N>::symmetries(move)[k] (tak/src/symm.rs:41-55), k = 0..7
+ * tak_symmetry_state     Symmetry::<N>::symmetries(game)[k] (symm.rs:57-97)
+ * examples_to_tensors    Example::to_tensors (example.rs:63-78) for `count` examples at once, on the device: row 8e+k of
+ *                        inputs [8*count][C][N][N] = game_repr(symmetries(game)[k]); of pi [8*count][policy_size] =
+ *                        zeros with pi[move_index(symmetries(mov)[k])] = visits/total; of z [8*count] = result.
+ *                        Host buffers, or device buffers (left on the engine's stream) when on_device != 0.            */
+int32_t tak_example_format(const tak_replay_record_t* rec, char* out, int32_t cap);
+int32_t tak_example_parse(int32_t n, const char* text, tak_replay_record_t* out);
+int32_t tak_symmetry_move(int32_t n, uint16_t move, int32_t k, uint16_t* out);
+int32_t tak_symmetry_state(const tak_state_t* s, int32_t k, tak_state_t* out);
+int32_t examples_to_tensors(tak_engine_t* e, const tak_replay_record_t* recs, int32_t count, float* inputs, float* pi,
+                            float* z, int32_t on_device);
+
 #ifdef __cplusplus
 }
 #endif

@@ -69,6 +69,7 @@ struct DevBuf {
 struct NetState;      // net.cu
 struct MctsState;     // mcts.cu
 struct SelfplayState; // selfplay.cu
+struct ExamplesState; // examples.cu
 
 }  // namespace tb
 
@@ -110,6 +111,7 @@ struct tak_engine {
     tb::NetState* net = nullptr;
     tb::MctsState* mcts = nullptr;
     tb::SelfplayState* selfplay = nullptr;
+    tb::ExamplesState* examples = nullptr;
     uint64_t launches = 0;  // kernels launched by this engine (gpu_launches in bench.py)
 };
 
@@ -122,6 +124,7 @@ int state_bytes_for(int n);
 void net_destroy(tak_engine* e);
 void mcts_destroy(tak_engine* e);
 void selfplay_destroy(tak_engine* e);
+void examples_destroy(tak_engine* e);
 // host helper shared by modules: policy index of a move (alpha_tak::search::move_index)
 int host_move_index(int n, uint16_t mv);
 int host_policy_size(int n);

@@ -211,6 +211,7 @@ int32_t tak_engine_destroy(tak_engine_t* e) {
     if (!e) return TAK_OK;
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
+    examples_destroy(e);
     selfplay_destroy(e);
     mcts_destroy(e);
     net_destroy(e);

@@ -2,6 +2,7 @@
 // These replace the takparse 0.5.5 surface the reference re-exports (tak/src/lib.rs:15) and
 // alpha_tak::search::move_index (alpha-tak/src/search/move_map.rs:19-48) / From<Game> for Tps
 // (tak/src/tps.rs:7-96).  All of it works on the u16 move encoding and the POD tak_state_t.
+#include <cmath>
 #include <cstdarg>
 #include <cstdlib>
 #include <mutex>
@@ -298,6 +299,108 @@ int32_t tak_tps_parse(int32_t n, const char* text, tak_state_t* out) {
     }
     out->white_stones = uint8_t(ws); out->white_caps = uint8_t(wc);
     out->black_stones = uint8_t(bs); out->black_caps = uint8_t(bc);
+    return TAK_OK;
+}
+
+// ---- alpha_tak::Example text format (alpha-tak/src/example.rs:81-133) ---------------------------------------
+// Rust's `{}` for f32: shortest decimal that round-trips, no exponent for these magnitudes, "NaN" / "inf"
+static std::string rust_f32(float v) {
+    if (v != v) return "NaN";
+    if (v == INFINITY) return "inf";
+    if (v == -INFINITY) return "-inf";
+    char buf[64];
+    for (int prec = 1; prec <= 9; ++prec) {
+        snprintf(buf, sizeof buf, "%.*g", prec, double(v));
+        if (strtof(buf, nullptr) == v) break;
+    }
+    std::string t = buf;
+    if (t.find('e') != std::string::npos) {  // out of the range self-play produces; fall back to fixed notation
+        snprintf(buf, sizeof buf, "%.9f", double(v));
+        t = buf;
+        while (!t.empty() && t.back() == '0') t.pop_back();
+        if (!t.empty() && t.back() == '.') t.pop_back();
+    }
+    return t;
+}
+
+int32_t tak_example_format(const tak_replay_record_t* rec, char* out, int32_t cap) {
+    TB_CHECK(rec && out && cap > 0, TAK_ERR_BAD_ARG, "tak_example_format: bad argument");
+    TB_CHECK(rec->n_children >= 0 && rec->n_children <= TAK_REPLAY_MAX_CHILDREN, TAK_ERR_BAD_ARG,
+             "tak_example_format: bad child count");
+    char tps[1024];
+    if (int r = tak_tps_format(&rec->state, tps, sizeof tps)) return r;
+    const tak_state_t& g = rec->state;
+    std::string t = tps;
+    t += ';' + std::to_string(int(g.white_stones)) + ';' + std::to_string(int(g.white_caps)) + ';' +
+         std::to_string(int(g.black_stones)) + ';' + std::to_string(int(g.black_caps)) + ';' +
+         std::to_string(int(g.half_komi)) + ';' + rust_f32(rec->result) + ';';
+    for (int i = 0; i < rec->n_children; ++i) {
+        char mv[32];
+        if (int r = tak_ptn_format(g.n, rec->moves[i], mv, sizeof mv)) return r;
+        if (i) t += ',';
+        t += mv;
+        t += ':' + std::to_string(rec->visits[i]);
+    }
+    TB_CHECK(int(t.size()) < cap, TAK_ERR_CAPACITY, "tak_example_format: buffer too small");
+    std::memcpy(out, t.c_str(), t.size() + 1);
+    return TAK_OK;
+}
+
+int32_t tak_example_parse(int32_t n, const char* text, tak_replay_record_t* out) {
+    TB_CHECK(n >= 3 && n <= 8 && text && out, TAK_ERR_BAD_ARG, "tak_example_parse: bad argument");
+    std::memset(out, 0, sizeof *out);
+    std::string s = text;
+    while (!s.empty() && isspace(static_cast<unsigned char>(s.back()))) s.pop_back();
+    size_t b = 0;
+    while (b < s.size() && isspace(static_cast<unsigned char>(s[b]))) ++b;
+    s = s.substr(b);
+    std::vector<std::string> f;
+    for (size_t p = 0;;) {
+        const size_t q = s.find(';', p);
+        f.push_back(s.substr(p, q == std::string::npos ? q : q - p));
+        if (q == std::string::npos) break;
+        p = q + 1;
+    }
+    static const char* names[] = {"tps", "white stones", "white caps", "black stones", "black caps", "half komi",
+                                  "result", "policy"};
+    TB_CHECK(f.size() >= 8, TAK_ERR_PARSE, "missing %s", names[f.size()]);
+    if (int r = tak_tps_parse(n, f[0].c_str(), &out->state)) return r;
+    auto num = [&](const std::string& t, long lo, long hi, long* v) {
+        char* end = nullptr;
+        *v = strtol(t.c_str(), &end, 10);
+        return !t.empty() && *end == 0 && *v >= lo && *v <= hi;
+    };
+    long v;
+    TB_CHECK(num(f[1], 0, 255, &v), TAK_ERR_PARSE, "bad white stones"); out->state.white_stones = uint8_t(v);
+    TB_CHECK(num(f[2], 0, 255, &v), TAK_ERR_PARSE, "bad white caps");   out->state.white_caps = uint8_t(v);
+    TB_CHECK(num(f[3], 0, 255, &v), TAK_ERR_PARSE, "bad black stones"); out->state.black_stones = uint8_t(v);
+    TB_CHECK(num(f[4], 0, 255, &v), TAK_ERR_PARSE, "bad black caps");   out->state.black_caps = uint8_t(v);
+    TB_CHECK(num(f[5], -128, 127, &v), TAK_ERR_PARSE, "bad half komi"); out->state.half_komi = int8_t(v);
+    {
+        char* end = nullptr;
+        out->result = strtof(f[6].c_str(), &end);
+        TB_CHECK(!f[6].empty() && *end == 0, TAK_ERR_PARSE, "bad result");
+    }
+    int k = 0;
+    for (size_t p = 0; p <= f[7].size();) {
+        size_t q = f[7].find(',', p);
+        if (q == std::string::npos) q = f[7].size();
+        const std::string pair = f[7].substr(p, q - p);
+        const size_t c = pair.find(':');
+        TB_CHECK(c != std::string::npos, TAK_ERR_PARSE, "pair has missing delimiter");
+        TB_CHECK(k < TAK_REPLAY_MAX_CHILDREN, TAK_ERR_CAPACITY, "more than %d policy entries", TAK_REPLAY_MAX_CHILDREN);
+        if (int r = tak_ptn_parse(n, pair.substr(0, c).c_str(), &out->moves[k])) return r;
+        long long vis = 0;
+        {
+            const std::string t = pair.substr(c + 1);
+            char* end = nullptr;
+            vis = strtoll(t.c_str(), &end, 10);
+            TB_CHECK(!t.empty() && *end == 0 && vis >= 0 && vis <= 0xFFFFFFFFll, TAK_ERR_PARSE, "bad visit count");
+        }
+        out->visits[k++] = uint32_t(vis);
+        p = q + 1;
+    }
+    out->n_children = k;
     return TAK_OK;
 }
 
