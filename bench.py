@@ -235,6 +235,37 @@ def movegen_mnodes(eng, world, rank, dev, pk):
                          "mean_branching_last_level": b}}
 
 
+def augment_rate(eng, recs, dev, pk):
+    """examples_to_tensors (alpha-tak/src/example.rs:63-78) on replay records of this run, outputs left in HBM."""
+    import torch
+
+    import tak_b200 as tb
+    from tak_b200._lib import check
+
+    if not recs:
+        return None
+    k = len(recs)
+    arr = (tb.ReplayRecord * k)(*recs)
+    c, p, n = tb.input_channels(6), tb.policy_size(6), 6
+    inputs = torch.empty((8 * k, c, n, n), dtype=torch.float32, device=dev)
+    pi = torch.empty((8 * k, p), dtype=torch.float32, device=dev)
+    z = torch.empty(8 * k, dtype=torch.float32, device=dev)
+    fp = C.POINTER(C.c_float)
+    ptr = lambda t: C.cast(t.data_ptr(), fp)
+    call = lambda: check(eng.lib.examples_to_tensors(eng._h, arr, k, ptr(inputs), ptr(pi), ptr(z), 1))
+    call()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    reps = 3
+    for _ in range(reps):
+        call()
+    dt = (time.perf_counter() - t0) / reps
+    out_bytes = 8 * k * (c * n * n + p + 1) * 4 + 8 * k * p * 4   # tensors written + the zero fill of pi
+    return {"value": k / dt, "unit": "examples/s", "examples": k, "rows_out": 8 * k, "ms": 1e3 * dt,
+            "what": "host replay records -> H2D -> 8 symmetries x (game_repr, pi, z) in HBM, host-timed incl. the copy",
+            "hbm_write_gbs": out_bytes / dt / 1e9, "hbm_peak_gbs": pk["hbm"]}
+
+
 def run_b200(args):
     import torch
 
@@ -389,6 +420,9 @@ def run_b200(args):
     # ---------------- movegen Mnodes/s: 6x6 perft(5) from the opening, root moves sharded over ranks ----------------
     movegen = movegen_mnodes(engines[0], world, rank, dev, pk)
 
+    # ---------------- replay augmentation (next row N2): Example::to_tensors x 8 symmetries on the device ------------
+    augment = augment_rate(engines[0], recs[:2048] if recs else [], dev, pk)
+
     line = None
     if rank == 0:
         # the CPU baseline is timed beside the GPU arm at N=1 only (at N>1 the other ranks' host threads share the cores)
@@ -412,6 +446,7 @@ def run_b200(args):
             "gpu_launches": total_launches,
             "roofline": roofline,
             "movegen": movegen,
+            "augment": augment,
             "cpu_baseline": {"value": cpu["value"], "unit": UNIT, "cores": cpu["cores"], "kind": "port",
                              "sample": cpu["sample"]} if cpu else None,
             "clocks": clocks,

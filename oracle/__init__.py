@@ -103,6 +103,13 @@ def lib():
             "orc_search_reset": (None, [vp]),
             "orc_search_apply_noise": (None, [vp, C.POINTER(f32), f32]),
             "orc_search_node_count": (u64, [vp]),
+            "orc_symmetry_move": (i32, [u16, i32, i32]),
+            "orc_symmetry_game": (None, [vp, i32, C.POINTER(TakState)]),
+            "orc_example_to_tensors": (None, [vp, C.POINTER(u16), C.POINTER(C.c_uint32), i32, f32, C.POINTER(f32),
+                                              C.POINTER(f32)]),
+            "orc_example_format": (i32, [vp, C.POINTER(u16), C.POINTER(C.c_uint32), i32, f32, C.c_char_p, i32]),
+            "orc_example_parse": (vp, [C.c_char_p, i32, C.POINTER(u16), C.POINTER(C.c_uint32), i32, C.POINTER(i32),
+                                       C.POINTER(f32)]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(L, name)
@@ -297,3 +304,56 @@ def legacy_moves_5():
         lib().orc_legacy_move_5(i, buf, 32)
         out.append(buf.value.decode())
     return out
+
+
+# ---- tak::Symmetry / alpha_tak::Example (tak/src/symm.rs, alpha-tak/src/example.rs) ---------------------------------
+def symmetry_move(move: int, n: int, k: int) -> int:
+    """Symmetry::<N>::symmetries(move)[k]."""
+    return lib().orc_symmetry_move(move, n, k)
+
+
+def symmetry_game(game: "Game", k: int) -> TakState:
+    """Symmetry::<N>::symmetries(game)[k] as a POD state."""
+    s = TakState()
+    lib().orc_symmetry_game(game._h, k, C.byref(s))
+    return s
+
+
+class Example:
+    """Mirror of alpha_tak::Example<N>: (game, [(move, visits)], result)."""
+
+    def __init__(self, game: "Game", policy, result: float):
+        self.game, self.policy, self.result = game, [(int(m), int(v)) for m, v in policy], float(result)
+
+    def _arrays(self):
+        k = len(self.policy)
+        mv = (C.c_uint16 * max(k, 1))(*[m for m, _ in self.policy])
+        vis = (C.c_uint32 * max(k, 1))(*[v for _, v in self.policy])
+        return mv, vis, k
+
+    def to_tensors(self):
+        """Example::to_tensors: (inputs [8, C, n, n], pi [8, policy_size], z [8])."""
+        n = self.game.n
+        c, p = lib().orc_input_channels(n), lib().orc_policy_size(n)
+        inputs = np.zeros((8, c, n, n), dtype=np.float32)
+        pi = np.zeros((8, p), dtype=np.float32)
+        mv, vis, k = self._arrays()
+        lib().orc_example_to_tensors(self.game._h, mv, vis, k, self.result,
+                                     inputs.ctypes.data_as(C.POINTER(C.c_float)), pi.ctypes.data_as(C.POINTER(C.c_float)))
+        return inputs, pi, np.full(8, self.result, dtype=np.float32)
+
+    def __str__(self) -> str:
+        buf = C.create_string_buffer(1 << 14)
+        mv, vis, k = self._arrays()
+        if lib().orc_example_format(self.game._h, mv, vis, k, self.result, buf, len(buf)) < 0:
+            raise ValueError("example too long")
+        return buf.value.decode()
+
+    @classmethod
+    def parse(cls, text: str, n: int) -> "Example":
+        mv, vis = (C.c_uint16 * 512)(), (C.c_uint32 * 512)()
+        cnt, res = C.c_int(0), C.c_float(0)
+        h = lib().orc_example_parse(text.encode(), n, mv, vis, 512, C.byref(cnt), C.byref(res))
+        if not h:
+            raise ValueError("bad Example line")
+        return cls(Game(n, _handle=h), [(mv[i], vis[i]) for i in range(cnt.value)], res.value)

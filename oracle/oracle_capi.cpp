@@ -262,4 +262,40 @@ static size_t count_nodes(const Node& nd) {
 }
 uint64_t orc_search_node_count(void* s) { return count_nodes(static_cast<Search*>(s)->root); }
 
+// ---- Symmetry / Example (tak/src/symm.rs, alpha-tak/src/example.rs) ----
+int orc_symmetry_move(uint16_t move, int n, int k) { return symmetries_move(Move::decode(move, n), n)[k].encode(n); }
+void orc_symmetry_game(void* g, int k, tak_state_t* out) { to_state(symmetries_game(*static_cast<Game*>(g))[k], out); }
+static Example make_example(void* g, const uint16_t* moves, const uint32_t* visits, int count, float result) {
+    Example ex;
+    ex.game = *static_cast<Game*>(g);
+    ex.result = result;
+    for (int i = 0; i < count; ++i) ex.policy.push_back({Move::decode(moves[i], ex.game.n), visits[i]});
+    return ex;
+}
+void orc_example_to_tensors(void* g, const uint16_t* moves, const uint32_t* visits, int count, float result,
+                            float* inputs, float* pi) {
+    make_example(g, moves, visits, count, result).to_tensors(inputs, pi);
+}
+int orc_example_format(void* g, const uint16_t* moves, const uint32_t* visits, int count, float result, char* out,
+                       int cap) {
+    std::string s = make_example(g, moves, visits, count, result).to_string();
+    if (int(s.size()) >= cap) return -1;
+    std::memcpy(out, s.c_str(), s.size() + 1);
+    return int(s.size());
+}
+// returns the game handle (caller frees) or null; moves/visits/result through the out parameters
+void* orc_example_parse(const char* text, int n, uint16_t* moves, uint32_t* visits, int cap, int* count, float* result) {
+    Example ex;
+    ex.game = Game(n, 0);
+    if (!Example::from_string(text, n, ex)) return nullptr;
+    if (int(ex.policy.size()) > cap) return nullptr;
+    for (size_t i = 0; i < ex.policy.size(); ++i) {
+        moves[i] = ex.policy[i].first.encode(n);
+        visits[i] = ex.policy[i].second;
+    }
+    *count = int(ex.policy.size());
+    *result = ex.result;
+    return new Game(ex.game);
+}
+
 }  // extern "C"

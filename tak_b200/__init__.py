@@ -7,8 +7,10 @@ CUDA device every compute call raises.
 from ._lib import LIB_PATH, ReplayRecord, SelfplayStats, TakNativeError, TakState, load  # noqa: F401
 from .engine import (  # noqa: F401
     RESULT_BLACK, RESULT_DRAW, RESULT_FLAG, RESULT_ONGOING, RESULT_WHITE, Engine, Game, format_move,
-    input_channels, move_index, parse_move, policy_size, state_init, tps_format, tps_parse,
+    example_format, example_parse, input_channels, move_index, parse_move, policy_size, state_init, symmetry_move,
+    symmetry_state, tps_format, tps_parse,
 )
 
 __all__ = ["Engine", "Game", "TakState", "TakNativeError", "parse_move", "format_move", "move_index",
-           "policy_size", "input_channels", "state_init", "tps_format", "tps_parse", "load", "LIB_PATH"]
+           "policy_size", "input_channels", "state_init", "tps_format", "tps_parse", "load", "LIB_PATH",
+           "example_format", "example_parse", "symmetry_move", "symmetry_state"]

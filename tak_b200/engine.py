@@ -302,6 +302,49 @@ class Engine:
         return [arr[i] for i in range(cnt.value)]
 
 
+    # ---- alpha_tak::Example::to_tensors, batched (example.rs:63-78) -------------------------------------------
+    def examples_to_tensors(self, records: Sequence[ReplayRecord]):
+        """8-fold symmetry augmentation of replay records on the device:
+        (inputs [8k, C, n, n], pi [8k, policy_size], z [8k]) as host arrays, row 8e+s = symmetry s of example e."""
+        k = len(records)
+        arr = (ReplayRecord * max(k, 1))(*records)
+        c = input_channels(self.n)
+        inputs = np.zeros((8 * k, c, self.n, self.n), dtype=np.float32)
+        pi = np.zeros((8 * k, self.policy_size), dtype=np.float32)
+        z = np.zeros(8 * k, dtype=np.float32)
+        fp = C.POINTER(C.c_float)
+        check(self.lib.examples_to_tensors(self._h, arr, k, inputs.ctypes.data_as(fp), pi.ctypes.data_as(fp),
+                                           z.ctypes.data_as(fp), 0))
+        return inputs, pi, z
+
+
+# ---- alpha_tak::Example text format / tak::Symmetry (host side, cold) ------------------------------------------------
+def example_format(record: ReplayRecord) -> str:
+    """`Display for Example<N>` (alpha-tak/src/example.rs:81-100)."""
+    buf = C.create_string_buffer(1 << 14)
+    check(_lib.load().tak_example_format(C.byref(record), buf, len(buf)))
+    return buf.value.decode()
+
+
+def example_parse(text: str, n: int) -> ReplayRecord:
+    """`FromStr for Example<N>` (example.rs:102-133)."""
+    rec = ReplayRecord()
+    check(_lib.load().tak_example_parse(n, text.encode(), C.byref(rec)))
+    return rec
+
+
+def symmetry_move(move: int, n: int, k: int) -> int:
+    out = C.c_uint16()
+    check(_lib.load().tak_symmetry_move(n, move, k, C.byref(out)))
+    return out.value
+
+
+def symmetry_state(state: TakState, k: int) -> TakState:
+    out = TakState()
+    check(_lib.load().tak_symmetry_state(C.byref(state), k, C.byref(out)))
+    return out
+
+
 # ---- single-object mirrors of the Rust types --------------------------------------------------------------------
 class _Slots:
     """Lazily created per-board-size engines whose game slots back `Game` objects."""
