@@ -389,12 +389,12 @@ def run_b200(args):
             eng.rollouts(ids, R)                   # select -> encode -> Net6 -> backup, R times
             mv, vis, cnt = eng.children_batch(ids, stride)   # D2H: improved policy (visit counts) of every root
             picks = eng.pick_move(ids)             # D2H: the moves to play
-        return int(vis.sum()), picks
+        return mv, vis, cnt
 
     in_threads([lambda i=i: e2e_run(i, 1) for i in range(E)])
     barrier()
     t0 = time.perf_counter()
-    in_threads([lambda i=i: e2e_run(i, e2e_steps) for i in range(E)])
+    e2e_out = in_threads([lambda i=i: e2e_run(i, e2e_steps) for i in range(E)])
     barrier()
     e2e_t = max_over_ranks(time.perf_counter() - t0)
     e2e_value = world * G * e2e_steps / e2e_t
@@ -421,7 +421,15 @@ def run_b200(args):
     movegen = movegen_mnodes(engines[0], world, rank, dev, pk)
 
     # ---------------- replay augmentation (next row N2): Example::to_tensors x 8 symmetries on the device ------------
-    augment = augment_rate(engines[0], recs[:2048] if recs else [], dev, pk)
+    mv0, vis0, cnt0 = e2e_out[0]
+    aug_recs = []
+    for i in range(min(2048, Gr)):             # the e2e searches' (position, improved policy) pairs as Examples
+        r = tb.ReplayRecord()
+        r.state, r.result, r.n_children = host_states[0][i], 1.0 - 2.0 * (i & 1), int(cnt0[i])
+        C.memmove(r.moves, mv0[i].ctypes.data, 2 * r.n_children)
+        C.memmove(r.visits, vis0[i].ctypes.data, 4 * r.n_children)
+        aug_recs.append(r)
+    augment = augment_rate(engines[0], aug_recs, dev, pk)
 
     line = None
     if rank == 0:

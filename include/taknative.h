@@ -177,6 +177,12 @@ int32_t mcts_pending(tak_engine_t* e, int32_t* out_count, int32_t* out_game_ids,
                      int32_t cap);
 int32_t mcts_devirtualize(tak_engine_t* e);
 int32_t mcts_devirtualize_with(tak_engine_t* e, const float* policy, const float* value, int32_t count);
+/* Player's pipelining (alpha-tak/src/player.rs:98-110,130-133): `rollout` queues a NEW batch of virtual rollouts before it
+ * evaluates and backs up the PREVIOUS one.  mcts_reserve_pending sizes every game's leaf queue for k entries (two
+ * batches); mcts_devirtualize_first backs up, for game ids[i], only its oldest counts[i] queued leaves (queue order,
+ * mcts.rs:67-91) and leaves the newer ones -- and every other game's queue -- untouched. */
+int32_t mcts_reserve_pending(tak_engine_t* e, int32_t k);
+int32_t mcts_devirtualize_first(tak_engine_t* e, const int32_t* ids, int32_t n, const int32_t* counts);
 int32_t mcts_rollouts(tak_engine_t* e, const int32_t* ids, int32_t n, int32_t n_rollouts);
 int32_t mcts_children(tak_engine_t* e, int32_t id, uint16_t* out_moves, uint32_t* out_visits, float* out_priors,
                       float* out_rewards, int32_t cap, int32_t* out_count);

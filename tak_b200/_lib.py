@@ -134,6 +134,8 @@ SYMBOLS = {
     "selfplay_begin": (_i32, [_vp, _P(SelfplayConfig)]),
     "selfplay_step": (_i32, [_vp, _i32, _P(SelfplayStats)]),
     "selfplay_drain": (_i32, [_vp, _P(ReplayRecord), _i32, _P(_i32)]),
+    "mcts_reserve_pending": (_i32, [_vp, _i32]),
+    "mcts_devirtualize_first": (_i32, [_vp, _P(_i32), _i32, _P(_i32)]),
     "tak_example_format": (_i32, [_P(ReplayRecord), C.c_char_p, _i32]),
     "tak_example_parse": (_i32, [_i32, C.c_char_p, _P(ReplayRecord)]),
     "tak_symmetry_move": (_i32, [_i32, _u16, _i32, _P(_u16)]),

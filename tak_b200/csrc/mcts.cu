@@ -108,7 +108,8 @@ int mcts_launch_rollout(tak_engine* e, const int* d_ids, int n, int k, const uin
 
 int mcts_launch_compact(tak_engine* e) {
     MctsState& m = *e->mcts;
-    k_mcts_compact<<<1, 256, 0, e->stream>>>(m.pend_cnt.as<int>(), e->max_games, m.kcap, m.eval_index.as<int>(),
+    k_mcts_compact<<<1, 256, 0, e->stream>>>(m.pend_cnt.as<int>(), e->max_games, m.kcap, m.limits_on ? m.limits.as<int>() : nullptr,
+                                             m.eval_index.as<int>(),
                                               m.eval_slot.as<int>(), m.eval_count.as<int>());
     e->launches++;
     TB_CUDA(cudaGetLastError());
@@ -126,9 +127,10 @@ int mcts_read_eval_count(tak_engine* e, int* out) {
 int mcts_launch_backup(tak_engine* e, const PriorSource& ps) {
     MctsState& m = *e->mcts;
     TB_DISPATCH_N(e->n, (k_mcts_backup<N_><<<warp_blocks(e->max_games), GAME_THREADS, 0, e->stream>>>(
-                            m.view(), m.eval_slot.as<int>(), e->max_games, ps)));
+                            m.view(), m.eval_slot.as<int>(), e->max_games, ps,
+                            m.limits_on ? m.limits.as<int>() : nullptr, m.leaf_states.as<uint8_t>())));
     e->launches++;
-    m.queued = false;
+    m.queued = m.limits_on;  // a partial backup may leave newer leaves queued
     TB_CUDA(cudaGetLastError());
     return TAK_OK;
 }
@@ -183,6 +185,10 @@ int mcts_check_errors(tak_engine* e) {
         set_error("visit count beyond the exploration table (%d)", MCTS_EXPLO_TABLE);
         return TAK_ERR_CAPACITY;
     }
+    if (flags & MERR_QUEUED) {
+        set_error("mcts_play while leaves of that game are queued: call mcts_devirtualize first");
+        return TAK_ERR_BAD_ARG;
+    }
     if (flags & MERR_NAN) {
         set_error("tried comparing nan (NaN upper confidence bound) or select on a node without children");
         return TAK_ERR_BAD_ARG;
@@ -218,7 +224,7 @@ void mcts_destroy(tak_engine* e) {
     if (!e->mcts) return;
     MctsState& m = *e->mcts;
     for (DevBuf* b : {&m.stat, &m.link, &m.half, &m.top, &m.pend_cnt, &m.pend_leaf, &m.pend_plen, &m.pend_path,
-                      &m.leaf_states, &m.eval_index, &m.eval_slot, &m.eval_count, &m.explo, &m.move_table, &m.err,
+                      &m.leaf_states, &m.eval_index, &m.eval_slot, &m.eval_count, &m.explo, &m.move_table, &m.err, &m.limits,
                       &m.counters, &m.d_ids, &m.d_moves, &m.stage_policy, &m.stage_value, &m.stage_stat,
                       &m.stage_link, &m.stage_count})
         b->release();
@@ -297,6 +303,33 @@ int32_t mcts_devirtualize(tak_engine_t* e) {
     TB_CUDA(cudaSetDevice(e->device));
     if (int r = mcts_ensure(e, 1)) return r;
     if (int r = mcts_eval_and_backup(e)) return r;
+    return mcts_check_errors(e);
+}
+
+int32_t mcts_reserve_pending(tak_engine_t* e, int32_t k) {
+    TB_CHECK(e && k >= 1 && k <= 8192, TAK_ERR_BAD_ARG, "mcts_reserve_pending: bad argument");
+    TB_CUDA(cudaSetDevice(e->device));
+    return mcts_ensure(e, k);
+}
+
+int32_t mcts_devirtualize_first(tak_engine_t* e, const int32_t* ids, int32_t n, const int32_t* counts) {
+    TB_CHECK(e && ids && counts && n >= 0, TAK_ERR_BAD_ARG, "mcts_devirtualize_first: bad argument");
+    TB_CUDA(cudaSetDevice(e->device));
+    if (int r = mcts_ensure(e, 1)) return r;
+    MctsState& m = *e->mcts;
+    std::vector<int> lim(e->max_games, 0);
+    for (int i = 0; i < n; ++i) {
+        TB_CHECK(ids[i] >= 0 && ids[i] < e->max_games && counts[i] >= 0, TAK_ERR_BAD_ARG,
+                 "mcts_devirtualize_first: bad id / count");
+        lim[ids[i]] = counts[i];
+    }
+    TB_CUDA(m.limits.ensure(lim.size() * 4));
+    TB_CUDA(cudaMemcpyAsync(m.limits.p, lim.data(), lim.size() * 4, cudaMemcpyHostToDevice, e->stream));
+    TB_CUDA(cudaStreamSynchronize(e->stream));  // `lim` is a stack-lifetime host buffer
+    m.limits_on = true;
+    int r = mcts_eval_and_backup(e);
+    m.limits_on = false;
+    if (r) return r;
     return mcts_check_errors(e);
 }
 
@@ -442,7 +475,6 @@ int32_t mcts_play(tak_engine_t* e, const int32_t* ids, const uint16_t* moves, in
     if (int r = mcts_ensure(e, 1)) return r;
     if (n == 0) return TAK_OK;
     MctsState& m = *e->mcts;
-    TB_CHECK(!m.queued, TAK_ERR_BAD_ARG, "mcts_play while leaves are queued: call mcts_devirtualize first");
     const int* d_ids = nullptr;
     if (int r = upload_ids(e, ids, n, &d_ids)) return r;
     TB_CUDA(m.d_moves.ensure(size_t(n) * 2 + 2));

@@ -10,7 +10,8 @@ struct MctsState {
     int cap = 0;    // nodes per game per half
     int kcap = 0;   // queued leaves per game
     DevBuf stat, link, half, top, pend_cnt, pend_leaf, pend_plen, pend_path, leaf_states;
-    DevBuf eval_index, eval_slot, eval_count, explo, move_table, err, counters;
+    DevBuf eval_index, eval_slot, eval_count, explo, move_table, err, counters, limits;
+    bool limits_on = false;   // compact / backup take only the oldest limits[g] leaves of game g (mcts_devirtualize_first)
     DevBuf d_ids, d_moves, stage_policy, stage_value, stage_stat, stage_link, stage_count;
     int* h_pinned = nullptr;  // [4] pinned host words: eval count, error flags
     bool queued = false;      // leaves are waiting for devirtualize

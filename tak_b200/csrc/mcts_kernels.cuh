@@ -27,6 +27,7 @@ enum MctsErr : int {
     MERR_VISITS = 8,         // visit count beyond the exploration table
     MERR_BAD_MOVE = 16,      // mcts_play with a move that is not a child / unindexable move
     MERR_NAN = 32,           // NaN upper confidence bound (the reference panics)
+    MERR_QUEUED = 64,        // mcts_play on a game whose leaves are still queued
 };
 
 struct MctsView {
@@ -202,14 +203,16 @@ __global__ void __launch_bounds__(GAME_THREADS)
 
 // flat pending slot (gid*kcap + j) <-> compact evaluation index; single block
 static __global__ void __launch_bounds__(1024)
-    k_mcts_compact(const int* pend_cnt, int n_games, int kcap, int* eval_index, int* eval_slot, int* eval_count) {
+    k_mcts_compact(const int* pend_cnt, int n_games, int kcap, const int* limits, int* eval_index, int* eval_slot,
+                   int* eval_count) {
     __shared__ int s_warp[32];
     __shared__ int s_carry;
     if (threadIdx.x == 0) s_carry = 0;
     __syncthreads();
     for (int base = 0; base < n_games; base += blockDim.x) {
         const int g = base + threadIdx.x;
-        const int c = g < n_games ? pend_cnt[g] : 0;
+        // with `limits`, only the oldest limits[g] leaves of game g are taken (Player's pipelined batches)
+        const int c = g < n_games ? (limits ? min(pend_cnt[g], limits[g]) : pend_cnt[g]) : 0;
         int inc = c;
 #pragma unroll
         for (int s = 1; s < 32; s <<= 1) {
@@ -253,10 +256,13 @@ struct PriorSource {
 // Node::devirtualize_path (mcts.rs:67-91) for every queued leaf of every game, in queue order
 template <int N>
 __global__ void __launch_bounds__(GAME_THREADS)
-    k_mcts_backup(MctsView v, const int* eval_slot, int n_games, PriorSource ps) {
+    k_mcts_backup(MctsView v, const int* eval_slot, int n_games, PriorSource ps, const int* limits,
+                  uint8_t* leaf_states) {
     const int gid = warp_global_id();
     if (gid >= n_games) return;
-    const int cnt = v.pend_cnt[gid];
+    const int queued = v.pend_cnt[gid];
+    // Player's pipelining backs up the OLDER batch while a newer one stays queued
+    const int cnt = limits ? min(queued, limits[gid]) : queued;
     if (cnt == 0) return;
     const int l = threadIdx.x & 31;
     constexpr int NSQ = N * N;
@@ -312,7 +318,25 @@ __global__ void __launch_bounds__(GAME_THREADS)
         }
         __syncwarp();
     }
-    if (l == 0) v.pend_cnt[gid] = 0;
+    // leaves queued after the first `limit` stay queued: move them to the front of the game's queue
+    const int rest = queued - cnt;
+    if (rest > 0) {
+        constexpr int S = StateLayout<N>::S;
+        for (int j = 0; j < rest; ++j) {
+            const size_t dst = size_t(gid) * v.kcap + j, src = dst + cnt;
+            const int plen = v.pend_plen[src];
+            __syncwarp();
+            for (int d = l; d <= plen; d += 32) v.pend_path[dst * MCTS_MAX_DEPTH + d] = v.pend_path[src * MCTS_MAX_DEPTH + d];
+            for (int b = l * 16; b < S; b += 32 * 16)
+                *reinterpret_cast<uint4*>(leaf_states + dst * S + b) = *reinterpret_cast<const uint4*>(leaf_states + src * S + b);
+            if (l == 0) {
+                v.pend_leaf[dst] = v.pend_leaf[src];
+                v.pend_plen[dst] = plen;
+            }
+            __syncwarp();
+        }
+    }
+    if (l == 0) v.pend_cnt[gid] = rest;
 }
 
 // Node::pick_move(true) (play.rs:52-58): LAST child with the maximal visit count.  With `sample` != 0 the move is
@@ -393,6 +417,10 @@ static __global__ void __launch_bounds__(GAME_THREADS)
     if (w >= n) return;
     const int gid = ids ? ids[w] : w;
     const int l = threadIdx.x & 31;
+    if (v.pend_cnt[gid] != 0) {  // queued paths would dangle: the caller must devirtualize this game first
+        if (l == 0) atomicOr(v.err, MERR_QUEUED);
+        return;
+    }
     const int half = v.half[gid];
     const uint4* ostat = v.stat + arena_base(v, gid, half);
     const uint2* olink = v.link + arena_base(v, gid, half);

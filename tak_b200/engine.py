@@ -226,6 +226,15 @@ class Engine:
     def devirtualize(self):
         check(self.lib.mcts_devirtualize(self._h))
 
+    def reserve_pending(self, k: int):
+        check(self.lib.mcts_reserve_pending(self._h, k))
+
+    def devirtualize_first(self, ids, counts):
+        """Back up only the oldest counts[i] queued leaves of game ids[i]; everything else stays queued."""
+        p, k, _keep = _ids(ids)
+        c = (C.c_int32 * max(k, 1))(*[int(x) for x in counts])
+        check(self.lib.mcts_devirtualize_first(self._h, p, k, c))
+
     def devirtualize_with(self, policy: np.ndarray, value: np.ndarray):
         policy = np.ascontiguousarray(policy, dtype=np.float32)
         value = np.ascontiguousarray(value, dtype=np.float32)
@@ -441,3 +450,82 @@ class Game:
 
     def perft(self, depth: int) -> int:
         return self.engine.perft(self.state(), depth)
+
+
+class Player:
+    """Mirror of `alpha_tak::Player` (alpha-tak/src/player.rs:23-199) for ONE game slot of an engine.
+
+    The reference pipelines: a helper thread selects the NEXT batch of leaves (`request_batch`) while the caller
+    evaluates and backs up the PREVIOUS one (`consume_batch`), so a backup always lands after the following batch was
+    selected.  That order is kept deterministically here (the thread race itself is not reproduced): the
+    engine queues the new batch behind the outstanding one and `mcts_devirtualize_first` backs up only the older.
+    The game lives in slot `gid` of `engine`; `play_move` advances both the tree and the slot.
+    """
+
+    def __init__(self, engine: Engine, gid: int, batch: int, save_examples: bool = False,
+                 state: Optional[TakState] = None):
+        self.engine, self.gid, self.batch, self.save_examples = engine, gid, batch, save_examples
+        self.examples: List[Tuple[TakState, List[Tuple[int, int]]]] = []
+        self._outstanding: List[int] = []
+        engine.reserve_pending(2 * batch)
+        if state is not None:
+            engine.upload([gid], [state])
+        engine.tree_reset([gid])
+        self._request_batch()                      # player.rs:66-67
+
+    def _queued(self) -> int:
+        gids, _ = self.engine.pending(with_states=False)
+        return int((gids == self.gid).sum())
+
+    def _request_batch(self):                      # player.rs:98-100 (+ the rollout thread, :71-96)
+        before = self._queued()
+        self.engine.virtual_rollout([self.gid], self.batch)
+        self._outstanding.append(self._queued() - before)   # terminal leaves need no evaluation (:83-87)
+
+    def _consume_batch(self):                      # player.rs:102-110
+        self.engine.devirtualize_first([self.gid], [self._outstanding.pop(0)])
+
+    def rollout(self):                             # player.rs:130-133
+        self._request_batch()
+        self._consume_batch()
+
+    def add_noise(self, alpha: float, ratio: float, seed: int = 0):   # player.rs:123-127
+        self._consume_batch()
+        self.engine.apply_dirichlet([self.gid], alpha, ratio, seed)
+        self._request_batch()
+
+    def debug(self):
+        """(moves, visits, priors, rewards) of the root's children -- what NodeDebugInfo is built from."""
+        return self.engine.children(self.gid)
+
+    def pick_move(self, exploitation: bool = True, rng: Optional[np.random.Generator] = None) -> int:   # player.rs:136-138
+        if exploitation:
+            return int(self.engine.pick_move([self.gid])[0])
+        mv, vis, _, _ = self.engine.children(self.gid)        # play.rs:60-65: visit-weighted sample (thread_rng there)
+        rng = rng or np.random.default_rng()
+        return int(rng.choice(mv, p=vis / vis.sum()))
+
+    def play_move(self, move: int, with_info: bool = True):   # player.rs:141-171
+        self._consume_batch()                      # "rollout stale paths"
+        if self.save_examples and with_info:
+            mv, vis, _, _ = self.engine.children(self.gid)
+            self.examples.append((self.engine.download([self.gid])[0], list(zip(mv.tolist(), vis.tolist()))))
+        self.engine.tree_play([self.gid], [move])
+        if self.engine.play([self.gid], [move]).any():
+            raise TakNativeError(-1, "play_move: illegal move")
+        self._request_batch()
+
+    def get_examples(self, result: int) -> List[ReplayRecord]:    # player.rs:175-194
+        if (result & 3) == RESULT_ONGOING:
+            raise ValueError("cannot complete examples with ongoing game")
+        white = 1.0 if (result & 3) == RESULT_WHITE else -1.0 if (result & 3) == RESULT_BLACK else 0.0
+        out = []
+        for state, policy in self.examples:
+            r = ReplayRecord()
+            r.state, r.n_children = state, len(policy)
+            r.result = white if state.to_move == 0 else -white
+            for i, (m, v) in enumerate(policy):
+                r.moves[i], r.visits[i] = m, v
+            out.append(r)
+        self.examples = []
+        return out
