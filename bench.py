@@ -229,9 +229,9 @@ def movegen_mnodes(eng, world, rank, dev, pk):
             "nodes": total, "exact": total == PERFT6_D5, "ms": t_max, "materialised_states": int(mat_total),
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s",
                          "frac": gbs / pk["hbm"] if pk["hbm"] else None,
-                         "note": "interior levels only (13.7 M states materialised at depth <= 4); the 1.25e9 leaves are "
-                                 "counted from registers (closed-form move counts), so that level is issue-bound, not "
-                                 "HBM-bound",
+                         "note": "13.7 M states are materialised (depth <= 4: written once, read by the count and the "
+                                 "expand kernels); the 1.25e9 leaves are only counted, one thread per depth-4 parent from "
+                                 "the 96-byte tail of its record (closed-form move counts)",
                          "mean_branching_last_level": b}}
 
 

@@ -21,7 +21,7 @@ static void pack_t(const tak_state_t& s, uint8_t* rec) {
     std::memset(rec, 0, L::S);
     Col* cols = reinterpret_cast<Col*>(rec);
     uint8_t* hts = rec + L::HTS_OFF;
-    uint64_t walls = 0, caps = 0;
+    uint64_t walls = 0, caps = 0, occ = 0, blk = 0;
     for (int row = 0; row < N; ++row)
         for (int col = 0; col < N; ++col) {
             const int i = row * N + col, o = col * N + row;
@@ -31,10 +31,17 @@ static void pack_t(const tak_state_t& s, uint8_t* rec) {
             hts[o] = s.height[i];
             if (s.height[i] && s.top[i] == 1) walls |= 1ull << o;
             if (s.height[i] && s.top[i] == 2) caps |= 1ull << o;
+            if (s.height[i]) {
+                occ |= 1ull << o;
+                if ((c >> (s.height[i] - 1)) & 1) blk |= 1ull << o;
+            }
         }
     uint64_t* bb = reinterpret_cast<uint64_t*>(rec + L::BB_OFF);
     bb[0] = walls;
     bb[1] = caps;
+    uint64_t* der = reinterpret_cast<uint64_t*>(rec + L::DER_OFF);   // derived bitboards (tak_device.cuh)
+    der[0] = occ;
+    der[1] = blk;
     StateScalars sc{};
     sc.to_move = s.to_move; sc.ply = s.ply;
     sc.ws = s.white_stones; sc.wc = s.white_caps; sc.bs = s.black_stones; sc.bc = s.black_caps;
@@ -104,8 +111,7 @@ static int perft_level(tak_engine* e, const uint8_t* frontier, size_t n, int dep
         TB_CUDA(lv.offsets.ensure(n * 8));
         d_counts = lv.counts.as<uint32_t>();
     }
-    k_perft_count<N><<<warp_blocks(int(n)), GAME_THREADS, 0, e->stream>>>(frontier, int(n), last ? 1 : 0, d_counts,
-                                                                         d_leaves);
+    k_perft_count<N><<<(unsigned(n) + 255) / 256, 256, 0, e->stream>>>(frontier, int(n), last ? 1 : 0, d_counts, d_leaves);
     e->pf_launches++;
     TB_CUDA(cudaGetLastError());
     if (last) return TAK_OK;

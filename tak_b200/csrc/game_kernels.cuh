@@ -74,30 +74,33 @@ static __global__ void k_scatter_records(uint4* staging, uint4* states, const in
 // `leaves` accumulates what perf_count returns for parents that stop here:
 //   finished game -> 1 ; last level (depth_left == 1) -> number of legal moves.
 template <int N>
-__global__ void __launch_bounds__(GAME_THREADS)
+__global__ void __launch_bounds__(256)
     k_perft_count(const uint8_t* frontier, int n, int last_level, uint32_t* counts, unsigned long long* leaves) {
-    const int w = warp_global_id();
+    // one THREAD per parent (ThreadPos, tak_device.cuh): result + move count from the record's tail
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long add = 0;
     if (w < n) {
-        WarpGame<N> g;
+        ThreadPos<N> g;
         g.load(frontier + size_t(w) * StateLayout<N>::S);
         const uint8_t r = g.result();
         uint32_t c = 0;
         if (r != RES_ONGOING) {
             add = 1;
         } else {
-            const int total = g.count_total();
-            if (last_level) add = total; else c = uint32_t(total);
+            const uint32_t total = g.count_moves();
+            if (last_level) add = total; else c = total;
         }
-        if ((threadIdx.x & 31) == 0 && counts) counts[w] = c;
+        if (counts) counts[w] = c;
     }
-    // block reduction of `add` (lane 0 of every warp holds it)
-    __shared__ unsigned long long s_add[GAME_WARPS_PER_BLOCK];
+    // block reduction of `add`
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) add += __shfl_xor_sync(FULL, add, o);
+    __shared__ unsigned long long s_add[8];
     if ((threadIdx.x & 31) == 0) s_add[threadIdx.x >> 5] = add;
     __syncthreads();
     if (threadIdx.x == 0) {
         unsigned long long t = 0;
-        for (int i = 0; i < GAME_WARPS_PER_BLOCK; ++i) t += s_add[i];
+        for (int i = 0; i < 8; ++i) t += s_add[i];
         if (t) atomicAdd(leaves, t);
     }
 }

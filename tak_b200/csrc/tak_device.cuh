@@ -4,11 +4,13 @@
 // tile.rs:7-10) and the three hot functions possible_moves (move_gen.rs:7-102), play (game.rs:121-209) and
 // result (game.rs:220-267, board.rs:61-113).
 //
-// HBM record ("packed state", S bytes, S = 288/384/1120 for N = 5/6/8):
+// HBM record ("packed state", S bytes, S = 288/384/1152 for N = 5/6/8):
 //   cols[NSQ]   stack colours per square, bit i = piece i is Black (bit 0 = bottom); u64 for N<=6, u128 above
 //   hts[NSQ]    stack heights (u8)
 //   walls,caps  bitboards of the top-piece kind
 //   scalars     to_move, ply, reserves, half_komi, reversible_plies
+//   occ,blk     DERIVED bitboards (occupied squares, squares whose top piece is Black), rewritten by every store:
+//               a thread-per-state kernel can classify / count a position from the last 96 bytes of its record
 // Squares are stored in MOVE-GENERATION order o = col*N + row (the reference enumerates `for x {for y}`),
 // so a warp prefix sum over per-square move counts yields the reference's move order directly, and a
 // warp's loads/stores of cols[] are one coalesced 256-byte access.
@@ -35,7 +37,8 @@ struct StateLayout {
     static constexpr int HTS_BYTES = (NSQ + 15) / 16 * 16;
     static constexpr int BB_OFF = HTS_OFF + HTS_BYTES;   // walls, caps
     static constexpr int SC_OFF = BB_OFF + 16;           // 16 bytes of scalars
-    static constexpr int RAW = SC_OFF + 16;
+    static constexpr int DER_OFF = SC_OFF + 16;          // derived: occupied, black tops
+    static constexpr int RAW = DER_OFF + 16;
     static constexpr int S = (RAW + 31) / 32 * 32;
 };
 
@@ -103,10 +106,14 @@ struct WarpGame {
         uint8_t* hts = rec + L::HTS_OFF;
         if (l < NSQ) { cols[l] = c0; hts[l] = uint8_t(h0); }
         if (TWO && l + 32 < NSQ) { cols[l + 32] = c1; hts[l + 32] = uint8_t(h1); }
+        const uint64_t occ = occupied(), blk = black_tops();   // whole-warp ballots
         if (l == 0) {
             uint64_t* bb = reinterpret_cast<uint64_t*>(rec + L::BB_OFF);
             bb[0] = walls;
             bb[1] = caps;
+            uint64_t* der = reinterpret_cast<uint64_t*>(rec + L::DER_OFF);
+            der[0] = occ;
+            der[1] = blk;
             StateScalars sc{};
             sc.to_move = uint8_t(to_move); sc.ply = uint16_t(ply);
             sc.ws = uint8_t(ws); sc.wc = uint8_t(wc); sc.bs = uint8_t(bs); sc.bc = uint8_t(bc);
@@ -412,6 +419,96 @@ struct WarpGame {
         ply += 1;
         to_move ^= 1;
         return 0;
+    }
+};
+
+// ---- one THREAD per position: result and number of legal moves from the record's tail ---------------------------
+// perft's counting levels need only Game::result (game.rs:220-267) and possible_moves().len() (move_gen.rs:7-102), both
+// functions of {heights, walls, caps, occupied, black tops, scalars} = the last 96 bytes of a 6x6 record.  A warp per
+// position spends its 32 lanes on identical bitboard arithmetic; a thread per position does the same work once.
+// sum over p = 1..maxp of c_comp_le[p][f] / c_comp_flat[p][f]  (move counts of one stack in one direction)
+static __constant__ uint16_t c_sum_le[9][8] = {
+    {0, 0, 0, 0, 0, 0, 0, 0},       {0, 1, 1, 1, 1, 1, 1, 1},        {0, 2, 3, 3, 3, 3, 3, 3},
+    {0, 3, 6, 7, 7, 7, 7, 7},       {0, 4, 10, 14, 15, 15, 15, 15},  {0, 5, 15, 25, 30, 31, 31, 31},
+    {0, 6, 21, 41, 56, 62, 63, 63}, {0, 7, 28, 63, 98, 119, 126, 127}, {0, 8, 36, 92, 162, 218, 246, 254}};
+static __constant__ uint16_t c_sum_flat[9][8] = {
+    {0, 0, 0, 0, 0, 0, 0, 0}, {1, 0, 0, 0, 0, 0, 0, 0},  {1, 1, 0, 0, 0, 0, 0, 0},
+    {1, 2, 1, 0, 0, 0, 0, 0}, {1, 3, 3, 1, 0, 0, 0, 0},  {1, 4, 6, 4, 1, 0, 0, 0},
+    {1, 5, 10, 10, 5, 1, 0, 0}, {1, 6, 15, 20, 15, 6, 1, 0}, {1, 7, 21, 35, 35, 21, 7, 1}};
+
+template <int N>
+struct ThreadPos {
+    using L = StateLayout<N>;
+    static constexpr int NSQ = N * N;
+    static constexpr uint64_t ALL = NSQ == 64 ? ~0ull : ((1ull << NSQ) - 1);
+    const uint8_t* hts;
+    uint64_t walls, caps, occ, blk;
+    StateScalars sc;
+
+    __device__ __forceinline__ void load(const uint8_t* rec) {
+        hts = rec + L::HTS_OFF;
+        const uint4 b = *reinterpret_cast<const uint4*>(rec + L::BB_OFF);
+        const uint4 d = *reinterpret_cast<const uint4*>(rec + L::DER_OFF);
+        walls = uint64_t(b.x) | (uint64_t(b.y) << 32);
+        caps = uint64_t(b.z) | (uint64_t(b.w) << 32);
+        occ = uint64_t(d.x) | (uint64_t(d.y) << 32);
+        blk = uint64_t(d.z) | (uint64_t(d.w) << 32);
+        *reinterpret_cast<uint4*>(&sc) = *reinterpret_cast<const uint4*>(rec + L::SC_OFF);
+    }
+    // Game::result, as WarpGame::result
+    __device__ __forceinline__ uint8_t result() const {
+        const uint64_t wht = occ & ~blk;
+        const uint64_t road_w = wht & ~walls, road_b = blk & ~walls;
+        const int to_move = sc.to_move;
+        if (WarpGame<N>::has_road(to_move == 0 ? road_b : road_w))
+            return uint8_t((to_move == 0 ? RES_BLACK : RES_WHITE) | RES_FLAG);
+        if (WarpGame<N>::has_road(to_move == 0 ? road_w : road_b))
+            return uint8_t((to_move == 0 ? RES_WHITE : RES_BLACK) | RES_FLAG);
+        if ((sc.wc == 0 && sc.ws == 0) || (sc.bc == 0 && sc.bs == 0) || occ == ALL) {
+            const uint64_t flat = ~(walls | caps);
+            const int fd = __popcll(wht & flat) - __popcll(blk & flat);
+            const int k = sc.half_komi / 2;
+            if (fd > k) return RES_WHITE;
+            if (fd < k) return RES_BLACK;
+            return (sc.half_komi % 2 == 0) ? RES_DRAW : RES_BLACK;
+        }
+        if (sc.reversible >= 50) return uint8_t(RES_DRAW | RES_FLAG);
+        return RES_ONGOING;
+    }
+    // possible_moves().len(), as WarpGame::count_total
+    __device__ __forceinline__ uint32_t count_moves() const {
+        const int empties = __popcll(ALL & ~occ);
+        if (sc.ply < 2) return uint32_t(empties);
+        const int to_move = sc.to_move;
+        const int my_st = to_move == 0 ? sc.ws : sc.bs, my_cp = to_move == 0 ? sc.wc : sc.bc;
+        uint32_t total = uint32_t(empties) * uint32_t((my_st > 0 ? 2 : 0) + (my_cp > 0 ? 1 : 0));
+        const uint64_t blockers = walls | caps;
+        uint64_t mine = occ & (to_move == 1 ? blk : ~blk);
+        while (mine) {
+            const int o = __ffsll(static_cast<long long>(mine)) - 1;
+            mine &= mine - 1;
+            const int h = hts[o];
+            const int maxp = h < N ? h : N;
+            const bool is_cap = (caps >> o) & 1;
+            const int r = o % N, c = o / N;
+#pragma unroll
+            for (int d = 0; d < 4; ++d) {
+                const int dist = d == 0 ? N - 1 - r : d == 1 ? r : d == 2 ? c : N - 1 - c;
+                const int delta = d == 0 ? 1 : d == 1 ? -1 : d == 2 ? -N : N;
+                int free = 0, q = o;
+                bool wall_after = false;
+                for (int st = 0; st < dist; ++st) {
+                    q += delta;
+                    if ((blockers >> q) & 1) {
+                        wall_after = (walls >> q) & 1;
+                        break;
+                    }
+                    ++free;
+                }
+                total += c_sum_le[maxp][free] + ((wall_after && is_cap) ? c_sum_flat[maxp][free] : 0);
+            }
+        }
+        return total;
     }
 };
 
