@@ -190,6 +190,23 @@ int32_t mcts_children(tak_engine_t* e, int32_t id, uint16_t* out_moves, uint32_t
 int32_t mcts_children_batch(tak_engine_t* e, const int32_t* ids, int32_t n, uint16_t* out_moves, uint32_t* out_visits,
                             int32_t* out_counts, int32_t stride);
 int32_t mcts_root(tak_engine_t* e, int32_t id, uint32_t* out_visits, uint32_t* out_virtual, float* out_reward);
+/* Node::debug(depth) (alpha-tak/src/search/debug.rs:9-40): one MoveInfo per root child -- move, visits, expected
+ * reward, policy and the principal continuation (pick_move(true) repeated, at most min(depth, TAK_DEBUG_MAX_DEPTH) moves,
+ * each with the visit count of the node it leads to) -- sorted by descending visits as NodeDebugInfo is.  The reference
+ * sorts with sort_unstable_by_key + reverse, so the order among equal visit counts is unspecified there; here equal
+ * counts keep reverse move-generation order (what a stable ascending sort + reverse gives). */
+#define TAK_DEBUG_MAX_DEPTH 16
+typedef struct tak_move_info_t {
+    uint16_t move;
+    uint16_t cont_len;
+    uint32_t visits;
+    float reward;
+    float policy;
+    uint16_t cont_moves[TAK_DEBUG_MAX_DEPTH];
+    uint32_t cont_visits[TAK_DEBUG_MAX_DEPTH];
+} tak_move_info_t;
+int32_t mcts_debug(tak_engine_t* e, int32_t id, int32_t depth, tak_move_info_t* out, int32_t cap, int32_t* out_count);
+
 int32_t mcts_pick_move(tak_engine_t* e, const int32_t* ids, int32_t n, uint16_t* out_moves);
 int32_t mcts_play(tak_engine_t* e, const int32_t* ids, const uint16_t* moves, int32_t n);
 int32_t mcts_apply_dirichlet(tak_engine_t* e, const int32_t* ids, int32_t n, float alpha, float ratio,

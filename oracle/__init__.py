@@ -98,6 +98,9 @@ def lib():
                  C.POINTER(C.c_uint32), i32],
             ),
             "orc_search_root": (None, [vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(f32)]),
+            "orc_search_debug": (i32, [vp, i32, i32, C.POINTER(u16), C.POINTER(C.c_uint32), C.POINTER(f32),
+                                       C.POINTER(f32), C.POINTER(C.c_int32), C.POINTER(u16), C.POINTER(C.c_uint32),
+                                       i32]),
             "orc_search_pick": (i32, [vp, i32]),
             "orc_search_play": (i32, [vp, u16, i32]),
             "orc_search_reset": (None, [vp]),
@@ -268,6 +271,17 @@ class Search:
         return (np.array(mv[:k], dtype=np.uint16), np.array(vis[:k], dtype=np.uint32),
                 np.array(pri[:k], dtype=np.float32), np.array(rew[:k], dtype=np.float32),
                 np.array(virt[:k], dtype=np.uint32))
+
+    def debug(self, depth: int = 10):
+        """Node::debug(depth): [(move, visits, reward, policy, [(move, visits), ...])] in descending order of visits."""
+        cap = 4096
+        mv, vis = (C.c_uint16 * cap)(), (C.c_uint32 * cap)()
+        rew, pol = (C.c_float * cap)(), (C.c_float * cap)()
+        clen = (C.c_int32 * cap)()
+        cmv, cvis = (C.c_uint16 * (cap * 16))(), (C.c_uint32 * (cap * 16))()
+        k = lib().orc_search_debug(self._h, self.n, depth, mv, vis, rew, pol, clen, cmv, cvis, cap)
+        return [(mv[i], vis[i], rew[i], pol[i], [(cmv[i * 16 + j], cvis[i * 16 + j]) for j in range(min(16, clen[i]))])
+                for i in range(k)]
 
     def root(self):
         v, vv, r = C.c_uint32(), C.c_uint32(), C.c_float()

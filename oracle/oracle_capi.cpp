@@ -1,5 +1,6 @@
 // TEST INFRASTRUCTURE -- NOT PRODUCT CODE.  C ABI over the CPU oracle so tests/ and bench.py's cpu_baseline
 // leg can drive it through ctypes (oracle/liboracle.so).  See tak_oracle.hpp for the parity status.
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <deque>
@@ -226,6 +227,38 @@ int orc_search_children(void* s, int n, uint16_t* moves, uint32_t* visits, float
         if (virtuals) virtuals[i] = ch[i].second.virtual_visits;
     }
     return int(ch.size());
+}
+// Node::debug(depth) (debug.rs:9-24): per root child (move, visits, reward, policy, continuation), sorted by visits
+// ascending (stable here; the reference's sort is unstable) and reversed.  cont_* are [cap][16].
+int orc_search_debug(void* s, int n, int depth, uint16_t* moves, uint32_t* visits, float* rewards, float* policies,
+                     int32_t* cont_len, uint16_t* cont_moves, uint32_t* cont_visits, int cap) {
+    Search* se = static_cast<Search*>(s);
+    struct Info {
+        Move mov;
+        uint32_t visits;
+        float reward, policy;
+        std::vector<std::pair<Move, uint32_t>> cont;
+    };
+    std::vector<Info> infos;
+    for (auto& ch : se->root.children) {
+        Info in{ch.first, ch.second.visits, ch.second.expected_reward, ch.second.policy, {}};
+        ch.second.continuation(size_t(depth), in.cont);
+        infos.push_back(std::move(in));
+    }
+    std::stable_sort(infos.begin(), infos.end(), [](const Info& a, const Info& b) { return a.visits < b.visits; });
+    std::reverse(infos.begin(), infos.end());
+    for (size_t i = 0; i < infos.size() && int(i) < cap; ++i) {
+        moves[i] = infos[i].mov.encode(n);
+        visits[i] = infos[i].visits;
+        rewards[i] = infos[i].reward;
+        policies[i] = infos[i].policy;
+        cont_len[i] = int32_t(infos[i].cont.size());
+        for (size_t k = 0; k < infos[i].cont.size() && k < 16; ++k) {
+            cont_moves[i * 16 + k] = infos[i].cont[k].first.encode(n);
+            cont_visits[i * 16 + k] = infos[i].cont[k].second;
+        }
+    }
+    return int(infos.size());
 }
 void orc_search_root(void* s, uint32_t* visits, uint32_t* virtuals, float* reward) {
     Search* se = static_cast<Search*>(s);

@@ -11,6 +11,9 @@ from .engine import (  # noqa: F401
     symmetry_state, tps_format, tps_parse,
 )
 
-__all__ = ["Engine", "Game", "Player", "TakState", "TakNativeError", "parse_move", "format_move", "move_index",
+from .analysis import Analysis, MoveInfo, NodeDebugInfo  # noqa: E402,F401
+from .pit import PitResult, PlayerBatch, pit  # noqa: E402,F401
+
+__all__ = ["Analysis", "MoveInfo", "NodeDebugInfo", "PitResult", "PlayerBatch", "pit", "Engine", "Game", "Player", "TakState", "TakNativeError", "parse_move", "format_move", "move_index",
            "policy_size", "input_channels", "state_init", "tps_format", "tps_parse", "load", "LIB_PATH",
            "example_format", "example_parse", "symmetry_move", "symmetry_state"]

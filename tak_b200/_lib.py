@@ -74,6 +74,22 @@ class SelfplayStats(C.Structure):
     ]
 
 
+TAK_DEBUG_MAX_DEPTH = 16
+
+
+class MoveInfoRecord(C.Structure):
+    """tak_move_info_t: one root child of Node::debug (search/debug.rs:9-24)."""
+    _fields_ = [
+        ("move", C.c_uint16),
+        ("cont_len", C.c_uint16),
+        ("visits", C.c_uint32),
+        ("reward", C.c_float),
+        ("policy", C.c_float),
+        ("cont_moves", C.c_uint16 * TAK_DEBUG_MAX_DEPTH),
+        ("cont_visits", C.c_uint32 * TAK_DEBUG_MAX_DEPTH),
+    ]
+
+
 class ReplayRecord(C.Structure):
     _fields_ = [
         ("game_id", C.c_int32),
@@ -128,6 +144,7 @@ SYMBOLS = {
     "mcts_children": (_i32, [_vp, _i32, _P(_u16), _P(C.c_uint32), _P(_f32), _P(_f32), _i32, _P(_i32)]),
     "mcts_children_batch": (_i32, [_vp, _P(_i32), _i32, _P(_u16), _P(C.c_uint32), _P(_i32), _i32]),
     "mcts_root": (_i32, [_vp, _i32, _P(C.c_uint32), _P(C.c_uint32), _P(_f32)]),
+    "mcts_debug": (_i32, [_vp, _i32, _i32, _P(MoveInfoRecord), _i32, _P(_i32)]),
     "mcts_pick_move": (_i32, [_vp, _P(_i32), _i32, _P(_u16)]),
     "mcts_play": (_i32, [_vp, _P(_i32), _P(_u16), _i32]),
     "mcts_apply_dirichlet": (_i32, [_vp, _P(_i32), _i32, _f32, _f32, _u64]),

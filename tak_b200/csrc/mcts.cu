@@ -1,5 +1,6 @@
 // alpha_tak::Node part of the C ABI: batched device MCTS (one tree per game).
 // Reference: alpha-tak/src/search/{node,mcts,play,noise}.rs; schedule of train/src/self_play.rs:181-210.
+#include <algorithm>
 #include "mcts.hpp"
 
 #include <cmath>
@@ -439,6 +440,40 @@ int32_t mcts_children_batch(tak_engine_t* e, const int32_t* ids, int32_t n, uint
     for (int i = 0; i < n; ++i)
         TB_CHECK(out_counts[i] <= stride, TAK_ERR_CAPACITY, "game %d has %d root children (> stride %d)", ids[i],
                  out_counts[i], stride);
+    return TAK_OK;
+}
+
+int32_t mcts_debug(tak_engine_t* e, int32_t id, int32_t depth, tak_move_info_t* out, int32_t cap, int32_t* out_count) {
+    static_assert(sizeof(tak_move_info_t) == sizeof(MctsMoveInfo) && TAK_DEBUG_MAX_DEPTH == MCTS_DEBUG_DEPTH,
+                  "tak_move_info_t mirrors MctsMoveInfo");
+    TB_CHECK(e && out && out_count && cap >= 0 && depth >= 0, TAK_ERR_BAD_ARG, "mcts_debug: bad argument");
+    TB_CHECK(id >= 0 && id < e->max_games, TAK_ERR_BAD_ARG, "game id %d out of range", id);
+    TB_CUDA(cudaSetDevice(e->device));
+    if (int r = mcts_ensure(e, 1)) return r;
+    MctsState& m = *e->mcts;
+    const int kmax = 4096;   // >= the largest possible root fan-out the arena encodes per export (see export_root)
+    TB_CUDA(m.stage_stat.ensure(size_t(kmax) * sizeof(MctsMoveInfo)));
+    TB_CUDA(m.stage_count.ensure(16));
+    k_mcts_debug<<<(kmax + GAME_WARPS_PER_BLOCK - 1) / GAME_WARPS_PER_BLOCK, GAME_THREADS, 0, e->stream>>>(
+        m.view(), id, depth, m.stage_stat.as<MctsMoveInfo>(), kmax, m.stage_count.as<int>());
+    e->launches++;
+    TB_CUDA(cudaGetLastError());
+    TB_CUDA(cudaMemcpyAsync(m.h_pinned + 2, m.stage_count.p, 4, cudaMemcpyDeviceToHost, e->stream));
+    TB_CUDA(cudaStreamSynchronize(e->stream));
+    const int count = m.h_pinned[2];
+    *out_count = count;
+    TB_CHECK(count <= kmax, TAK_ERR_CAPACITY, "root has %d children", count);
+    TB_CHECK(count <= cap, TAK_ERR_CAPACITY, "root has %d children, caller buffer holds %d", count, cap);
+    if (count == 0) return TAK_OK;
+    std::vector<tak_move_info_t> tmp(static_cast<size_t>(count));
+    TB_CUDA(cudaMemcpyAsync(tmp.data(), m.stage_stat.p, tmp.size() * sizeof(tak_move_info_t), cudaMemcpyDeviceToHost,
+                            e->stream));
+    TB_CUDA(cudaStreamSynchronize(e->stream));
+    // debug.rs:22-23: sort by visits, then reverse
+    std::stable_sort(tmp.begin(), tmp.end(),
+                     [](const tak_move_info_t& a, const tak_move_info_t& b) { return a.visits < b.visits; });
+    std::reverse(tmp.begin(), tmp.end());
+    std::memcpy(out, tmp.data(), tmp.size() * sizeof(tak_move_info_t));
     return TAK_OK;
 }
 

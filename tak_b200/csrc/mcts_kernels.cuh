@@ -531,6 +531,65 @@ static __global__ void __launch_bounds__(GAME_THREADS)
     }
 }
 
+// Node::debug / Node::continuation (search/debug.rs:9-40): one warp per root child.  The record carries the child's
+// (move, visits, expected_reward, policy) and its principal continuation: from the child, repeatedly the child with the
+// most visits (pick_move(true): LAST maximum, play.rs:49-58) until `depth` moves or a childless node.
+constexpr int MCTS_DEBUG_DEPTH = 16;
+struct MctsMoveInfo {
+    uint16_t move;
+    uint16_t cont_len;
+    uint32_t visits;
+    float reward;
+    float policy;
+    uint16_t cont_moves[MCTS_DEBUG_DEPTH];
+    uint32_t cont_visits[MCTS_DEBUG_DEPTH];
+};
+static __global__ void __launch_bounds__(GAME_THREADS)
+    k_mcts_debug(MctsView v, int gid, int depth, MctsMoveInfo* out, int cap, int* out_count) {
+    const int w = warp_global_id();
+    const int l = threadIdx.x & 31;
+    const int half = v.half[gid];
+    const uint4* stat = v.stat + arena_base(v, gid, half);
+    const uint2* link = v.link + arena_base(v, gid, half);
+    const uint2 root = link[0];
+    const int nroot = int(root.y >> 16);
+    if (w == 0 && l == 0) *out_count = nroot;
+    if (w >= nroot || w >= cap) return;
+    uint32_t node = (root.x & 0xFFFFFFu) + uint32_t(w);
+    const uint4 s = stat[node];
+    if (l == 0) {
+        out[w].move = uint16_t(link[node].y & 0xFFFFu);
+        out[w].visits = s.z;
+        out[w].reward = __uint_as_float(s.y);
+        out[w].policy = __uint_as_float(s.x);
+    }
+    int len = 0;
+    for (; len < depth && len < MCTS_DEBUG_DEPTH; ++len) {
+        const uint2 lk = link[node];
+        const uint32_t base = lk.x & 0xFFFFFFu;
+        const int nchild = int(lk.y >> 16);
+        if (nchild == 0) break;
+        uint32_t best_v = 0;
+        int best_i = -1;
+        for (int i = l; i < nchild; i += 32) {
+            const uint32_t vis = stat[base + i].z;
+            if (best_i < 0 || vis >= best_v) { best_v = vis; best_i = i; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const uint32_t ov = __shfl_xor_sync(FULL, best_v, o);
+            const int oi = __shfl_xor_sync(FULL, best_i, o);
+            if (oi >= 0 && (best_i < 0 || ov > best_v || (ov == best_v && oi > best_i))) { best_v = ov; best_i = oi; }
+        }
+        node = base + uint32_t(best_i);
+        if (l == 0) {
+            out[w].cont_moves[len] = uint16_t(link[node].y & 0xFFFFu);
+            out[w].cont_visits[len] = best_v;
+        }
+    }
+    if (l == 0) out[w].cont_len = uint16_t(len);
+}
+
 // Node::apply_dirichlet (noise.rs:6-16): prior = noise*ratio + prior*(1-ratio), noise ~ Dirichlet(alpha) from a
 // counter-based RNG (Marsaglia-Tsang gamma with the alpha<1 boost); statistical, not bit-reproducible vs rand 0.8.
 __device__ __forceinline__ float u01(uint64_t& s) {

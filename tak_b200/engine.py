@@ -259,6 +259,16 @@ class Engine:
         k = cnt.value
         return mv[:k].copy(), vis[:k].copy(), pri[:k].copy(), rew[:k].copy()
 
+    def debug(self, gid: int, depth: int = 10):
+        """Node::debug(depth) (search/debug.rs:9-24) of game `gid`'s root -> analysis.NodeDebugInfo."""
+        from ._lib import MoveInfoRecord
+        from .analysis import MoveInfo, NodeDebugInfo
+        cap = 4096
+        buf = (MoveInfoRecord * cap)()
+        cnt = C.c_int32()
+        check(self.lib.mcts_debug(self._h, gid, depth, buf, cap, C.byref(cnt)))
+        return NodeDebugInfo([MoveInfo.from_record(buf[i], self.n) for i in range(cnt.value)])
+
     def children_batch(self, ids, stride: int = 256):
         """`Node::improved_policy` of many roots at once: (moves [n, stride], visits [n, stride], counts [n])."""
         p, k, _keep = _ids(ids)
@@ -463,14 +473,18 @@ class Player:
     """
 
     def __init__(self, engine: Engine, gid: int, batch: int, save_examples: bool = False,
-                 state: Optional[TakState] = None):
+                 state: Optional[TakState] = None, create_analysis: bool = False):
+        from .analysis import Analysis
         self.engine, self.gid, self.batch, self.save_examples = engine, gid, batch, save_examples
+        self.create_analysis = create_analysis
         self.examples: List[Tuple[TakState, List[Tuple[int, int]]]] = []
         self._outstanding: List[int] = []
         engine.reserve_pending(2 * batch)
         if state is not None:
             engine.upload([gid], [state])
         engine.tree_reset([gid])
+        st = engine.download([gid])[0]
+        self.analysis = Analysis(engine.n, int(st.half_komi), int(st.ply))   # player.rs:58
         self._request_batch()                      # player.rs:66-67
 
     def _queued(self) -> int:
@@ -494,9 +508,9 @@ class Player:
         self.engine.apply_dirichlet([self.gid], alpha, ratio, seed)
         self._request_batch()
 
-    def debug(self):
-        """(moves, visits, priors, rewards) of the root's children -- what NodeDebugInfo is built from."""
-        return self.engine.children(self.gid)
+    def debug(self, depth: int = 10):                         # player.rs:113-115
+        """NodeDebugInfo of the root: children sorted by visits, each with its principal continuation."""
+        return self.engine.debug(self.gid, depth)
 
     def pick_move(self, exploitation: bool = True, rng: Optional[np.random.Generator] = None) -> int:   # player.rs:136-138
         if exploitation:
@@ -510,10 +524,21 @@ class Player:
         if self.save_examples and with_info:
             mv, vis, _, _ = self.engine.children(self.gid)
             self.examples.append((self.engine.download([self.gid])[0], list(zip(mv.tolist(), vis.tolist()))))
+        if self.create_analysis:                   # player.rs:155-161
+            from .analysis import MAX_BRANCH_LENGTH
+            if with_info:
+                self.analysis.update(self.engine.debug(self.gid, MAX_BRANCH_LENGTH), move)
+            else:
+                self.analysis.add_move_without_info(move)
         self.engine.tree_play([self.gid], [move])
         if self.engine.play([self.gid], [move]).any():
             raise TakNativeError(-1, "play_move: illegal move")
         self._request_batch()
+
+    def get_analysis(self):                                    # player.rs:196-198
+        from .analysis import Analysis
+        out, self.analysis = self.analysis, Analysis(self.engine.n, 0, 0)
+        return out
 
     def get_examples(self, result: int) -> List[ReplayRecord]:    # player.rs:175-194
         if (result & 3) == RESULT_ONGOING:

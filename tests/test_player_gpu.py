@@ -47,6 +47,23 @@ class OraclePlayer:
         self.request()
 
 
+def _oracle_debug_info(osearch, n, depth):
+    from tak_b200.analysis import MoveInfo, NodeDebugInfo
+    return NodeDebugInfo([MoveInfo(m, v, r, p, list(c), n) for m, v, r, p, c in osearch.debug(depth)])
+
+
+def _same_debug(eng, gid, osearch, n, depth):
+    """mcts_debug == Node::debug(depth) (search/debug.rs:9-40): order, stats bit for bit, continuations."""
+    d, o = eng.debug(gid, depth), _oracle_debug_info(osearch, n, depth)
+    assert len(d.moves) == len(o.moves)
+    for a, b in zip(d.moves, o.moves):
+        assert (a.mov, a.visits, a.continuation) == (b.mov, b.visits, b.continuation)
+        assert np.float32(a.reward).view(np.uint32) == np.float32(b.reward).view(np.uint32)
+        assert np.float32(a.policy).view(np.uint32) == np.float32(b.policy).view(np.uint32)
+    assert d.format(5) == o.format(5)
+    return o
+
+
 def _same_tree(eng, gid, osearch):
     mv, vis, pri, rew = eng.children(gid)
     omv, ovis, opri, orew, _ = osearch.children()
@@ -70,8 +87,10 @@ def test_player_pipelined_batches_match_oracle(n, arch, batch):
     g = oracle.Game(n, 4)
     for m in ("a1", f"{'abcdefgh'[n - 1]}{n}"):
         g.play(m)
-    p = tb.Player(eng, gid, batch, save_examples=True, state=to_tb_state(g.state()))
+    from tak_b200.analysis import Analysis, MAX_BRANCH_LENGTH
+    p = tb.Player(eng, gid, batch, save_examples=True, state=to_tb_state(g.state()), create_analysis=True)
     o = OraclePlayer(n, eng, batch, g.clone())
+    o_analysis = Analysis(n, 4, 2)
     plies = 0
     while o.game.result() == 0 and plies < 6:
         for _ in range(5):
@@ -79,9 +98,14 @@ def test_player_pipelined_batches_match_oracle(n, arch, batch):
             o.rollout()
             # trees carry the virtual visits of the still-outstanding batch on both sides
             _same_tree(eng, gid, o.search)
+        for depth in (0, 1, 3, MAX_BRANCH_LENGTH, 16):
+            _same_debug(eng, gid, o.search, n, depth)
         mv = p.pick_move(True)
         assert mv == o.search.pick_move()
         p.play_move(mv)
+        o.consume()                               # play_move's "rollout stale paths" happens before the analysis update
+        o.outstanding.insert(0, 0)
+        o_analysis.update(_oracle_debug_info(o.search, n, MAX_BRANCH_LENGTH), mv)
         o.play_move(mv)
         _same_tree(eng, gid, o.search)
         assert eng.download([gid])[0].key() == bytes(o.game.state())
@@ -91,6 +115,9 @@ def test_player_pipelined_batches_match_oracle(n, arch, batch):
     assert len(p.examples) == len(o.examples) == plies
     for (st, pol), (ost, opol) in zip(p.examples, o.examples):
         assert bytes(st) == ost and pol == opol
+    text = str(p.get_analysis())
+    assert text == str(o_analysis) and text.startswith(f'[Size "{n}"]\n[Komi "2"]\n2. ')
+    assert p.analysis.played_moves == []
     recs = p.get_examples(tb.RESULT_WHITE | tb.RESULT_FLAG)
     assert [r.result for r in recs] == [1.0 if r.state.to_move == 0 else -1.0 for r in recs]
     assert p.examples == []
