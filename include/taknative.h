@@ -158,6 +158,28 @@ int32_t net_forward_timed(tak_engine_t* e, int32_t first, int32_t count, int32_t
  * (CUDA events around each conv launch), out[2] = conv launches per forward, out[3] = algorithmic FLOP per forward */
 int32_t net_forward_profile(tak_engine_t* e, int32_t first, int32_t count, int32_t reps, double* out4);
 
+/* ---- Network::train (alpha-tak/src/model/network.rs:37-97), Net6 ------------------------------------------------
+ * net_train_begin   allocate the training state for chunks of up to max_boards positions; fp32 master weights start from
+ *                   the blob last loaded with net_load_weights (VarStore of a fresh or loaded network); Adam moments 0
+ * net_train_chunk   train_inner for one chunk (network.rs:59-97): inputs [b][C][n][n], pi [b][policy_size], z [b] fp32
+ *                   (the tensors Example::to_tensors yields; host pointers, or device pointers with on_device = 1);
+ *                   forward_training (BatchNorm on batch statistics, running statistics updated), loss_p =
+ *                   -sum(pi*log_softmax)/b and loss_z = sum((z-v)^2)/b -> out_loss2, backward; gradients ACCUMULATE
+ * net_train_step    opt.step() + opt.zero_grad() (network.rs:91-95): Adam(beta 0.9/0.999, eps 1e-8, L2 weight decay
+ *                   folded into the gradient, as tch's nn::Adam over libtorch) on every trainable tensor
+ * net_train_get     copy out the blob-shaped fp32 state: 0 weights (incl. BN running statistics), 1 gradients,
+ *                   2 / 3 Adam first / second moments.  Feed `0` to net_load_weights to search with the new network.
+ * net_train_grad_ptr device pointer of the gradient blob (data-parallel training: all-reduce it in place before the step)
+ * The reference trains only Net6 (train/src/main.rs:42-43); other architectures return TAK_ERR_BAD_ARG.            */
+int32_t net_train_begin(tak_engine_t* e, int32_t max_boards);
+int32_t net_train_chunk(tak_engine_t* e, const float* inputs, const float* pi, const float* z, int32_t boards,
+                        int32_t on_device, float* out_loss2);
+int32_t net_train_step(tak_engine_t* e, float lr, float weight_decay);
+int32_t net_train_get(tak_engine_t* e, int32_t what, float* out, int64_t elems);
+int32_t net_train_grad_ptr(tak_engine_t* e, void** out_device_ptr, int64_t* out_elems);
+int32_t net_train_stats(tak_engine_t* e, double* out_ms_last_chunk, int32_t* out_chunks_pending, int32_t* out_steps);
+int32_t net_train_end(tak_engine_t* e);
+
 /* ---- alpha_tak::Node (one search tree per game id) --------------------------------------------------
  * mcts_tree_reset        Node::default()
  * mcts_virtual_rollout   Node::virtual_rollout x k per game (mcts.rs:26-65), leaves queued in order

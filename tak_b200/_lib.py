@@ -135,6 +135,13 @@ SYMBOLS = {
     "net_policy_eval": (_i32, [_vp, _P(TakState), _i32, _P(_f32), _P(_f32)]),
     "net_forward_timed": (_i32, [_vp, _i32, _i32, _i32, _P(C.c_double)]),
     "net_forward_profile": (_i32, [_vp, _i32, _i32, _i32, _P(C.c_double)]),
+    "net_train_begin": (_i32, [_vp, _i32]),
+    "net_train_chunk": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _P(_f32)]),
+    "net_train_step": (_i32, [_vp, _f32, _f32]),
+    "net_train_get": (_i32, [_vp, _i32, _P(_f32), C.c_int64]),
+    "net_train_grad_ptr": (_i32, [_vp, _P(_vp), _P(C.c_int64)]),
+    "net_train_stats": (_i32, [_vp, _P(C.c_double), _P(_i32), _P(_i32)]),
+    "net_train_end": (_i32, [_vp]),
     "mcts_tree_reset": (_i32, [_vp, _P(_i32), _i32]),
     "mcts_virtual_rollout": (_i32, [_vp, _P(_i32), _i32, _i32]),
     "mcts_pending": (_i32, [_vp, _P(_i32), _P(_i32), _P(TakState), _i32]),

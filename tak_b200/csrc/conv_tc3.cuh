@@ -67,7 +67,7 @@ constexpr int C3_STAGE_BYTES = C3_SLAB_BYTES + C3_W_SLAB_BYTES;  // 48640
 constexpr int C3_STAGES = 4;                               // ring depth (one stage = one K-slab: activations + weights)
 constexpr int C3_MAX_SLABS = 8;                            // 128 input channels
 constexpr int C3_THREADS = 320;
-constexpr int C3_SMEM_BYTES = C3_STAGES * C3_STAGE_BYTES + 2048;
+constexpr int C3_SMEM_BYTES = C3_STAGES * C3_STAGE_BYTES + 3072;
 constexpr size_t C3_W_LAYER_ELEMS = size_t(C3_MAX_SLABS) * 9 * 2 * 128 * 8;  // bf16 elements per packed layer
 constexpr int C3_TILE_ALIGN = 1;
 
@@ -75,6 +75,11 @@ enum ConvMode : int {
     CONV_RELU = 0,        // out = relu(conv + bias)                     -> bf16 strip planes
     CONV_RES_RELU = 1,    // out = relu(conv + bias + res)               -> bf16 strip planes
     CONV_LOGITS_F32 = 2,  // out = conv + bias  (no activation)          -> fp32 [channel][slot] + softmax partials
+    // training build of the kernel only (conv3x3_tc3_kernel<true>):
+    CONV_LINEAR = 3,      // out = conv + bias (+ res if res != nullptr), no activation -> bf16 strip planes; if
+                          // stats != nullptr, per-channel sum / sum of squares of the fp32 values over the real squares
+                          // (forward_training's batch statistics, net6.rs:72-76 with train = true; dgrad uses it with
+                          // a zero bias and no stats)
 };
 
 // one convolution of the tower
@@ -92,6 +97,7 @@ struct ConvLayerDesc {
     int out_ch_valid;           // mode 2: number of real channels in this group (<=128)
     int group;                  // mode 2: group index for `partials`
     int pad_;
+    double* stats;              // mode 3: [2][128] {sum, sum of squares} per output channel, accumulated (or nullptr)
 };
 
 constexpr int C3_MAX_LAYERS = 36;   // Net6: 1 + 2*16 trunk convs + 2 policy groups
@@ -155,6 +161,7 @@ struct TowerWalk {
     __device__ int group_size(int g) const { return base + (g < rem ? 1 : 0); }
 };
 
+template <bool TRAIN>
 static __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc3_kernel(const __grid_constant__ ConvParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* stage_buf = smem;                               // C3_STAGES x {activation slab, weight slab}
@@ -162,6 +169,10 @@ static __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc3_kernel(const
     uint64_t* bars = reinterpret_cast<uint64_t*>(tail);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail + C3B_COUNT * 8);
     float* s_bias = reinterpret_cast<float*>(tail + C3B_COUNT * 8 + 16);   // [2][128]
+    float* s_stats = s_bias + 256;                                         // [2][128] (TRAIN: per-CTA batch statistics)
+    if (TRAIN) {
+        for (int i = threadIdx.x; i < 256; i += C3_THREADS) s_stats[i] = 0.f;
+    }
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -345,7 +356,15 @@ static __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc3_kernel(const
                         }
                     };
                     uint4 res[2][4];
-                    if (mode == CONV_RES_RELU) load_res(0, res[0]);
+                    const bool has_res = mode == CONV_RES_RELU || (TRAIN && mode == CONV_LINEAR && ld.res != nullptr);
+                    const bool relu = !(TRAIN && mode == CONV_LINEAR);
+                    const bool want_stats = TRAIN && mode == CONV_LINEAR && ld.stats != nullptr;
+                    float st_sum[8], st_sq[8];
+                    if (TRAIN) {
+#pragma unroll
+                        for (int b = 0; b < 8; ++b) st_sum[b] = st_sq[b] = 0.f;
+                    }
+                    if (has_res) load_res(0, res[0]);
                     float bias8[8];
 #pragma unroll
                     for (int b = 0; b < 8; ++b) bias8[b] = bias_s[chunk * 8 + b];
@@ -364,7 +383,7 @@ static __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc3_kernel(const
 #pragma unroll
                     for (int cc = 0; cc < 4; ++cc) {
                         tmem_ld32(taddr + cc * 32, x);   // 8 epilogue warps hide each other's TMEM latency
-                        if (mode == CONV_RES_RELU && cc < 3) load_res(cc + 1, res[(cc + 1) & 1]);
+                        if (has_res && cc < 3) load_res(cc + 1, res[(cc + 1) & 1]);
                         tmem_ld_wait();
                         if (mode == CONV_LOGITS_F32) {
                             // logits straight from the un-transposed registers: one channel, 32 consecutive slots
@@ -419,7 +438,7 @@ static __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc3_kernel(const
                                 float v[8];
 #pragma unroll
                                 for (int b = 0; b < 8; ++b) v[b] = __uint_as_float(x[8 * i + b]) + bias8[b];
-                                if (mode == CONV_RES_RELU) {
+                                if (has_res) {
                                     const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&res[cc & 1][i]);
 #pragma unroll
                                     for (int b = 0; b < 4; ++b) {
@@ -432,11 +451,39 @@ static __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc3_kernel(const
                                 __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&ov);
 #pragma unroll
                                 for (int b = 0; b < 4; ++b) {
-                                    float lo = valid ? fmaxf(v[2 * b], 0.0f) : 0.0f;
-                                    float hi = valid ? fmaxf(v[2 * b + 1], 0.0f) : 0.0f;
+                                    float lo = valid ? (relu ? fmaxf(v[2 * b], 0.0f) : v[2 * b]) : 0.0f;
+                                    float hi = valid ? (relu ? fmaxf(v[2 * b + 1], 0.0f) : v[2 * b + 1]) : 0.0f;
                                     ob[b] = __floats2bfloat162_rn(lo, hi);
                                 }
+                                if (TRAIN) {
+                                    if (want_stats && valid) {
+#pragma unroll
+                                        for (int b = 0; b < 8; ++b) {
+                                            st_sum[b] += v[b];
+                                            st_sq[b] += v[b] * v[b];
+                                        }
+                                    }
+                                }
                                 *reinterpret_cast<uint4*>(ld.out + (static_cast<size_t>(chunk) * p.S + slot0 + 32 * cc + 8 * i) * 8) = ov;
+                            }
+                        }
+                    }
+                    if (TRAIN) {
+                        if (want_stats) {   // the 8 lanes of a channel chunk hold different slots of the same 8 channels
+#pragma unroll
+                            for (int b = 0; b < 8; ++b) {
+#pragma unroll
+                                for (int o = 1; o < 8; o <<= 1) {
+                                    st_sum[b] += __shfl_xor_sync(0xffffffffu, st_sum[b], o);
+                                    st_sq[b] += __shfl_xor_sync(0xffffffffu, st_sq[b], o);
+                                }
+                            }
+                            if (j == 0) {
+#pragma unroll
+                                for (int b = 0; b < 8; ++b) {
+                                    atomicAdd(&s_stats[chunk * 8 + b], st_sum[b]);
+                                    atomicAdd(&s_stats[128 + chunk * 8 + b], st_sq[b]);
+                                }
                             }
                         }
                     }
@@ -456,16 +503,24 @@ static __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc3_kernel(const
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, 512);
+    if (TRAIN) {
+        // one flush of this CTA's batch statistics per launch (a training launch is ONE layer: the next layer's
+        // BatchNorm needs the statistics of the whole batch first)
+        double* gs = p.layers[p.n_layers - 1].stats;
+        if (gs != nullptr && threadIdx.x < 256) atomicAdd(&gs[threadIdx.x], double(s_stats[threadIdx.x]));
+    }
 }
 
 // Host-side launch (layers 0..n_layers-1 over tiles [tile_begin, tile_end)). `stream` is the engine's stream.
+template <bool TRAIN = false>
 inline cudaError_t conv3x3_tc3_launch(const ConvParams& p, int num_sms, cudaStream_t stream) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv3x3_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    // Set on every launch (a sub-microsecond host call): the kernel has internal linkage, so each translation unit that
+    // includes this header owns its own copy of it, while a function-local `static bool` of this inline function would
+    // be shared between them.
+    {
+        cudaError_t e = cudaFuncSetAttribute(conv3x3_tc3_kernel<TRAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              C3_SMEM_BYTES);
         if (e != cudaSuccess) return e;
-        attr_set = true;
     }
     const int tiles = p.tile_end - p.tile_begin;
     const int grid = tiles < num_sms ? tiles : num_sms;
@@ -481,7 +536,7 @@ inline cudaError_t conv3x3_tc3_launch(const ConvParams& p, int num_sms, cudaStre
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, conv3x3_tc3_kernel, p);
+    return cudaLaunchKernelEx(&cfg, conv3x3_tc3_kernel<TRAIN>, p);
 }
 
 // fill the layout fields of ConvParams for board size n

@@ -116,6 +116,7 @@ int net_load_blob(tak_engine* e, const float* blob, int64_t elems) {
         TB_CUDA(cudaStreamSynchronize(e->stream));
     }
     TB_CHECK(p - blob == elems, TAK_ERR_BAD_ARG, "internal: blob walk mismatch");
+    if (ns.blob_host.data() != blob) ns.blob_host.assign(blob, blob + elems);
     ns.loaded = true;
     return TAK_OK;
 }
@@ -237,6 +238,7 @@ int net_forward(tak_engine* e, const uint8_t* d_states, const int* d_index, int 
 
 void net_destroy(tak_engine* e) {
     if (!e->net) return;
+    train_destroy(e);
     NetState& ns = *e->net;
     for (auto& L : ns.layers) { L.w.release(); L.bias.release(); }
     for (auto& L : ns.policy_layers) { L.w.release(); L.bias.release(); }

@@ -41,6 +41,8 @@ struct NetState {
     const __nv_bfloat16* trunk_out = nullptr;
     // staging for the host-facing API
     DevBuf stage_states, stage_policy, stage_repr;
+    std::vector<float> blob_host;          // the fp32 weight blob last loaded (net_train_begin starts from it)
+    void* train = nullptr;                 // TrainState (train.cu), owned; released by train_destroy
 };
 
 // Evaluate `boards` packed states (d_states[index[i]] or d_states[i] if index == nullptr) on the engine stream.
@@ -49,5 +51,6 @@ int net_forward(tak_engine* e, const uint8_t* d_states, const int* d_index, int 
 int net_ensure_capacity(tak_engine* e, int boards);
 int net_load_blob(tak_engine* e, const float* blob, int64_t elems);
 int64_t net_blob_elems(const NetState& ns);
+void train_destroy(tak_engine* e);   // train.cu
 
 }  // namespace tb

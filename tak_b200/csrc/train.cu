@@ -1,0 +1,465 @@
+// Network::train for Net6 on the device: alpha-tak/src/model/network.rs:37-97 (train / train_inner:
+// loss = -sum(pi*logp)/B + sum((z-v)^2)/B accumulated over chunks, Adam lr 1e-4 wd 1e-4 every CHUNKS_IN_STEP chunks) over
+// forward_training (net6.rs:111-122; BatchNorm on batch statistics) and its backward pass, which the reference gets from
+// libtorch autograd.  fp32 master weights / gradients / Adam moments in the weight-blob layout (net6.rs:39-57), bf16
+// operand images for the tensor-core kernels, bf16 activations saved for backward.
+//   forward conv / dgrad : conv3x3_tc3_kernel<true> (CONV_LINEAR; dgrad = conv with the transposed, rotated filter)
+//   wgrad                : wgrad_tc_kernel (tcgen05, MN-major operands)
+//   BN / ReLU / heads / Adam : train_kernels.cuh (HBM-bound passes)
+#include <algorithm>
+#include <cmath>
+
+#include "conv_tc3.cuh"
+#include "net.hpp"
+#include "net_kernels.cuh"
+#include "train_kernels.cuh"
+#include "wgrad_tc.cuh"
+
+namespace tb {
+
+struct TrainLayer {
+    size_t w_off = 0, b_off = 0, gamma_off = 0, beta_off = 0, rm_off = 0, rv_off = 0;
+    int c_in = 128;
+    DevBuf w_fwd, bias_fwd, w_dgrad;
+    DevBuf y, z;   // raw conv output (pre-BN) and the layer's output after BN / residual / ReLU
+};
+
+struct TrainState {
+    int n = 6, c_in = 0, blocks = 16, policy_ch = 251, nsq = 36;
+    int64_t elems = 0;
+    size_t pw_off = 0, pb_off = 0, vw_off = 0, vb_off = 0;
+    std::vector<TrainLayer> layers;                 // 1 + 2 * blocks
+    DevBuf pol_w_fwd[2], pol_bias[2], pol_w_dgrad[2];
+    DevBuf master, grad, adam_m, adam_v, zero_bias;
+    DevBuf x0, g[2], dy, dt, g2, dlogits;
+    DevBuf bn_sums, bn_mean, bn_rstd, bn_a, bn_b, bwd_sums, bwd_c1, bwd_c2;
+    DevBuf logits, partials, stats, values, dpre, loss, wg_scratch;
+    DevBuf in_stage, pi_stage, z_stage;
+    int cap_boards = 0, S = 0;
+    int steps = 0;          // Adam steps taken
+    int chunks = 0;         // chunks accumulated since the last step
+    double last_ms = 0;
+    uint64_t launches = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<std::pair<size_t, size_t>> trainable;   // (offset, count) of every tensor Adam updates
+};
+
+static TrainState* train_of(tak_engine* e);
+
+static int tiles_for6(int boards) { return SlotMap<6>::tiles(boards); }
+
+static void build_layout(TrainState& t) {
+    size_t off = 0;
+    t.layers.resize(1 + 2 * t.blocks);
+    auto tensor = [&](size_t count, bool trainable) {
+        const size_t o = off;
+        off += count;
+        if (trainable) t.trainable.emplace_back(o, count);
+        return o;
+    };
+    auto bn = [&](TrainLayer& L) {
+        L.gamma_off = tensor(128, true);
+        L.beta_off = tensor(128, true);
+        L.rm_off = tensor(128, false);
+        L.rv_off = tensor(128, false);
+    };
+    {   // initial conv + BN (net6.rs:39-40)
+        TrainLayer& L = t.layers[0];
+        L.c_in = t.c_in;
+        L.w_off = tensor(size_t(128) * t.c_in * 9, true);
+        L.b_off = tensor(128, true);
+        bn(L);
+    }
+    for (int blk = 0; blk < t.blocks; ++blk) {   // conv1, conv2, bn1, bn2 in creation order (net6.rs:43-54)
+        TrainLayer& L1 = t.layers[1 + 2 * blk];
+        TrainLayer& L2 = t.layers[2 + 2 * blk];
+        L1.w_off = tensor(size_t(128) * 128 * 9, true);
+        L1.b_off = tensor(128, true);
+        L2.w_off = tensor(size_t(128) * 128 * 9, true);
+        L2.b_off = tensor(128, true);
+        bn(L1);
+        bn(L2);
+    }
+    t.pw_off = tensor(size_t(t.policy_ch) * 128 * 9, true);
+    t.pb_off = tensor(size_t(t.policy_ch), true);
+    t.vw_off = tensor(size_t(128) * t.nsq, true);
+    t.vb_off = tensor(1, true);
+    t.elems = int64_t(off);
+}
+
+// fp32 master -> bf16 operand images (forward and dgrad) of every conv
+static int repack(tak_engine* e, TrainState& t) {
+    const float* m = t.master.as<float>();
+    const int blocks = int((C3_W_LAYER_ELEMS + 255) / 256);
+    for (size_t l = 0; l < t.layers.size(); ++l) {
+        TrainLayer& L = t.layers[l];
+        k_pack_conv_train<<<blocks, 256, 0, e->stream>>>(m + L.w_off, 128, L.c_in, 0, 0, 0, L.w_fwd.as<__nv_bfloat16>());
+        k_pack_bias_train<<<1, 128, 0, e->stream>>>(m + L.b_off, 128, 0, L.bias_fwd.as<float>());
+        if (l > 0)
+            k_pack_conv_train<<<blocks, 256, 0, e->stream>>>(m + L.w_off, 128, 128, 0, 0, 1, L.w_dgrad.as<__nv_bfloat16>());
+        t.launches += 3;
+    }
+    for (int grp = 0; grp < 2; ++grp) {
+        k_pack_conv_train<<<blocks, 256, 0, e->stream>>>(m + t.pw_off, t.policy_ch, 128, grp * 128, 0, 0,
+                                                         t.pol_w_fwd[grp].as<__nv_bfloat16>());
+        k_pack_bias_train<<<1, 128, 0, e->stream>>>(m + t.pb_off, t.policy_ch, grp * 128, t.pol_bias[grp].as<float>());
+        // dgrad of the policy conv: 128 outputs (trunk channels), K = policy channels grp*128 .. grp*128+127
+        k_pack_conv_train<<<blocks, 256, 0, e->stream>>>(m + t.pw_off, t.policy_ch, 128, 0, grp * 128, 1,
+                                                         t.pol_w_dgrad[grp].as<__nv_bfloat16>());
+        t.launches += 3;
+    }
+    TB_CUDA(cudaGetLastError());
+    return TAK_OK;
+}
+
+static int ensure_capacity(tak_engine* e, TrainState& t, int boards) {
+    if (boards <= t.cap_boards) return TAK_OK;
+    const int tiles = tiles_for6(boards);
+    const int S = tiles * C3_TILE_M;
+    const size_t plane = size_t(S) * 256;   // 16 chunks x S slots x 16 B
+    auto planes = [&](DevBuf& b, int stacks) -> cudaError_t {
+        cudaError_t r = b.ensure(plane * stacks);
+        if (r != cudaSuccess) return r;
+        return cudaMemsetAsync(b.p, 0, plane * stacks, e->stream);
+    };
+    TB_CUDA(planes(t.x0, 1));
+    for (auto& L : t.layers) {
+        TB_CUDA(planes(L.y, 1));
+        TB_CUDA(planes(L.z, 1));
+    }
+    TB_CUDA(planes(t.g[0], 1));
+    TB_CUDA(planes(t.g[1], 1));
+    TB_CUDA(planes(t.dy, 1));
+    TB_CUDA(planes(t.dt, 1));
+    TB_CUDA(planes(t.g2, 1));
+    TB_CUDA(planes(t.dlogits, 2));
+    TB_CUDA(t.logits.ensure(size_t(256) * S * 4));
+    TB_CUDA(t.partials.ensure(size_t(8) * S * 8));
+    TB_CUDA(t.stats.ensure(size_t(boards) * 8));
+    TB_CUDA(t.values.ensure(size_t(boards) * 4));
+    TB_CUDA(t.dpre.ensure(size_t(boards) * 4));
+    t.cap_boards = boards;
+    t.S = S;
+    return TAK_OK;
+}
+
+template <int N>
+static int train_chunk_t(tak_engine* e, TrainState& t, const float* d_in, const float* d_pi, const float* d_z, int B) {
+    const int tiles = tiles_for6(B);
+    const int S = t.S;
+    float* master = t.master.as<float>();
+    float* grad = t.grad.as<float>();
+    const int nl = int(t.layers.size());
+    const double count = double(B) * N * N;
+    const int ew_blocks = int((size_t(16) * S + 255) / 256);
+    using bf = __nv_bfloat16;
+    auto conv_lin = [&](const bf* in, const bf* w, const float* bias, const bf* res, bf* out, double* stats, int slabs) -> int {
+        ConvParams p{};
+        conv_params_set_layout(p, N);
+        p.S = S; p.tile_begin = 0; p.tile_end = tiles; p.n_boards = B; p.n_layers = 1;
+        ConvLayerDesc& d = p.layers[0];
+        d.in = in; d.res = res; d.out = out; d.w = w; d.bias = bias; d.slabs = slabs; d.mode = CONV_LINEAR;
+        d.out_ch_valid = 128; d.stats = stats;
+        TB_CUDA(conv3x3_tc3_launch<true>(p, e->num_sms, e->stream));
+        t.launches++;
+        return TAK_OK;
+    };
+    auto wgrad = [&](const bf* dy, const bf* x, int c_in, size_t w_off, int co_base, int co_valid) -> int {
+        TB_CUDA(wgrad_tc_launch(dy, x, S, tiles, SlotMap<N>::PITCH, c_in, t.wg_scratch.as<float>(), grad + w_off, co_base,
+                                co_valid, 1, e->num_sms, e->stream));
+        t.launches += 2;
+        return TAK_OK;
+    };
+
+    // ------------------------------------------------ forward_training ------------------------------------------------
+    k_nchw_to_planes<N><<<ew_blocks, 256, 0, e->stream>>>(d_in, B, t.c_in, t.x0.as<bf>(), S);
+    t.launches++;
+    TB_CUDA(cudaMemsetAsync(t.bn_sums.p, 0, size_t(nl) * 256 * 8, e->stream));
+    for (int l = 0; l < nl; ++l) {
+        TrainLayer& L = t.layers[l];
+        const bf* in = l == 0 ? t.x0.as<bf>() : t.layers[l - 1].z.as<bf>();
+        double* sums = t.bn_sums.as<double>() + size_t(l) * 256;
+        if (int r = conv_lin(in, L.w_fwd.as<bf>(), L.bias_fwd.as<float>(), nullptr, L.y.as<bf>(), sums,
+                             l == 0 ? (t.c_in + 15) / 16 : C3_MAX_SLABS))
+            return r;
+        float* mean = t.bn_mean.as<float>() + l * 128;
+        float* rstd = t.bn_rstd.as<float>() + l * 128;
+        float* a = t.bn_a.as<float>() + l * 128;
+        float* b = t.bn_b.as<float>() + l * 128;
+        k_bn_finalize<<<1, 128, 0, e->stream>>>(sums, count, master + L.gamma_off, master + L.beta_off, master + L.rm_off,
+                                                master + L.rv_off, mean, rstd, a, b);
+        // conv2 of a block adds the block input before the ReLU (res_block.rs:21-22)
+        const bool is_conv2 = l >= 2 && (l % 2) == 0;
+        const bf* res = is_conv2 ? t.layers[l - 2].z.as<bf>() : nullptr;
+        k_bn_apply<N><<<ew_blocks, 256, 0, e->stream>>>(L.y.as<bf>(), res, a, b, B, S, L.z.as<bf>());
+        t.launches += 2;
+    }
+    const bf* trunk = t.layers[nl - 1].z.as<bf>();
+    {   // policy conv -> fp32 logits + per-slot softmax partials (net6.rs:113-116); value head (net6.rs:117-121)
+        ConvParams p{};
+        conv_params_set_layout(p, N);
+        p.S = S; p.tile_begin = 0; p.tile_end = tiles; p.n_boards = B;
+        for (int grp = 0; grp < 2; ++grp) {
+            ConvLayerDesc& d = p.layers[p.n_layers++];
+            d.in = trunk; d.out_f32 = t.logits.as<float>(); d.partials = t.partials.as<float2>();
+            d.w = t.pol_w_fwd[grp].as<bf>(); d.bias = t.pol_bias[grp].as<float>();
+            d.slabs = C3_MAX_SLABS; d.mode = CONV_LOGITS_F32; d.out_ch_offset = grp * 128;
+            d.out_ch_valid = std::min(128, t.policy_ch - grp * 128); d.group = grp;
+        }
+        TB_CUDA(conv3x3_tc3_launch<false>(p, e->num_sms, e->stream));
+        const int wblocks = (B + 7) / 8;
+        k_policy_stats_conv<N><<<wblocks, 256, 0, e->stream>>>(t.partials.as<float2>(), S, 8, B, t.stats.as<float2>());
+        k_value_train<N><<<wblocks, 256, 0, e->stream>>>(trunk, S, master + t.vw_off, master + t.vb_off, B,
+                                                         t.values.as<float>());
+        t.launches += 3;
+    }
+    // ------------------------------------------------ loss and head gradients -----------------------------------------
+    TB_CUDA(cudaMemsetAsync(t.loss.p, 0, 16, e->stream));
+    TB_CUDA(cudaMemsetAsync(t.dlogits.p, 0, size_t(S) * 512, e->stream));
+    k_policy_loss_grad<N><<<B, 256, 0, e->stream>>>(t.logits.as<float>(), S, t.policy_ch, t.stats.as<float2>(), d_pi, B,
+                                                    t.dlogits.as<bf>(), t.loss.as<double>());
+    k_planes_colsum<<<dim3(BNR_SPLIT, 32), 256, 0, e->stream>>>(t.dlogits.as<bf>(), S, t.policy_ch, grad + t.pb_off);
+    k_value_loss_grad<<<(B + 255) / 256, 256, 0, e->stream>>>(t.values.as<float>(), d_z, B, t.dpre.as<float>(),
+                                                              t.loss.as<double>(), grad + t.vb_off);
+    k_value_wgrad<N><<<dim3(16 * N * N, 16), 128, 0, e->stream>>>(t.dpre.as<float>(), trunk, B, S, grad + t.vw_off);
+    bf* g = t.g[0].as<bf>();
+    bf* g_alt = t.g[1].as<bf>();
+    k_value_bwd_trunk<N><<<ew_blocks, 256, 0, e->stream>>>(t.dpre.as<float>(), master + t.vw_off, B, S, g);
+    t.launches += 5;
+    TB_CUDA(cudaGetLastError());
+    // policy conv: wgrad per 128-channel group, dgrad in two K passes accumulated through the residual input
+    const bf* dl0 = t.dlogits.as<bf>();
+    const bf* dl1 = dl0 + size_t(16) * S * 8;
+    if (int r = wgrad(dl0, trunk, 128, t.pw_off, 0, 128)) return r;
+    if (int r = wgrad(dl1, trunk, 128, t.pw_off, 128, t.policy_ch - 128)) return r;
+    if (int r = conv_lin(dl0, t.pol_w_dgrad[0].as<bf>(), t.zero_bias.as<float>(), g, g_alt, nullptr, C3_MAX_SLABS)) return r;
+    if (int r = conv_lin(dl1, t.pol_w_dgrad[1].as<bf>(), t.zero_bias.as<float>(), g_alt, g, nullptr, C3_MAX_SLABS)) return r;
+    // ------------------------------------------------ trunk backward --------------------------------------------------
+    // bn_backward(l, upstream gradient w.r.t. the layer's post-ReLU output) -> dy (gradient w.r.t. the raw conv output);
+    // optionally the ReLU-masked upstream gradient (the residual connection's share)
+    auto bn_backward = [&](int l, const bf* gin, bf* dy_out, bf* gmasked) -> int {
+        TrainLayer& L = t.layers[l];
+        const float* mean = t.bn_mean.as<float>() + l * 128;
+        const float* rstd = t.bn_rstd.as<float>() + l * 128;
+        TB_CUDA(cudaMemsetAsync(t.bwd_sums.p, 0, 256 * 8, e->stream));
+        k_bn_bwd_reduce<<<dim3(BNR_SPLIT, 16), 256, 0, e->stream>>>(gin, L.z.as<bf>(), L.y.as<bf>(), mean, rstd, S,
+                                                                    t.bwd_sums.as<double>());
+        k_bn_bwd_finalize<<<1, 128, 0, e->stream>>>(t.bwd_sums.as<double>(), count, grad + L.gamma_off, grad + L.beta_off,
+                                                    t.bwd_c1.as<float>(), t.bwd_c2.as<float>());
+        k_bn_bwd_apply<N><<<ew_blocks, 256, 0, e->stream>>>(gin, L.z.as<bf>(), L.y.as<bf>(), mean, rstd,
+                                                            master + L.gamma_off, t.bwd_c1.as<float>(),
+                                                            t.bwd_c2.as<float>(), B, S, dy_out, gmasked);
+        t.launches += 3;
+        return TAK_OK;
+    };
+    for (int blk = t.blocks - 1; blk >= 0; --blk) {
+        const int l1 = 1 + 2 * blk, l2 = 2 + 2 * blk;
+        const bf* xin = t.layers[l1 - 1].z.as<bf>();
+        // out = relu(bn2(conv2(t)) + x): g2 = g * (out > 0) goes to both branches
+        if (int r = bn_backward(l2, g, t.dy.as<bf>(), t.g2.as<bf>())) return r;
+        if (int r = wgrad(t.dy.as<bf>(), t.layers[l1].z.as<bf>(), 128, t.layers[l2].w_off, 0, 128)) return r;
+        if (int r = conv_lin(t.dy.as<bf>(), t.layers[l2].w_dgrad.as<bf>(), t.zero_bias.as<float>(), nullptr, t.dt.as<bf>(),
+                             nullptr, C3_MAX_SLABS))
+            return r;
+        if (int r = bn_backward(l1, t.dt.as<bf>(), t.dy.as<bf>(), nullptr)) return r;
+        if (int r = wgrad(t.dy.as<bf>(), xin, 128, t.layers[l1].w_off, 0, 128)) return r;
+        // gradient w.r.t. the block input = dgrad(conv1) + the residual share
+        if (int r = conv_lin(t.dy.as<bf>(), t.layers[l1].w_dgrad.as<bf>(), t.zero_bias.as<float>(), t.g2.as<bf>(), g_alt,
+                             nullptr, C3_MAX_SLABS))
+            return r;
+        std::swap(g, g_alt);
+    }
+    if (int r = bn_backward(0, g, t.dy.as<bf>(), nullptr)) return r;
+    if (int r = wgrad(t.dy.as<bf>(), t.x0.as<bf>(), t.c_in, t.layers[0].w_off, 0, 128)) return r;
+    // conv biases feed a BatchNorm on batch statistics: their gradient is identically zero (sum of dy over the batch
+    // vanishes), so only the weight decay term reaches them in Adam -- nothing to accumulate here.
+    TB_CUDA(cudaGetLastError());
+    return TAK_OK;
+}
+
+}  // namespace tb
+
+using namespace tb;
+
+// the TrainState hangs off the NetState through an opaque pointer (net.hpp keeps no training types)
+namespace tb {
+static TrainState* train_of(tak_engine* e) { return e->net ? static_cast<TrainState*>(e->net->train) : nullptr; }
+void train_destroy(tak_engine* e) {
+    TrainState* t = train_of(e);
+    if (!t) return;
+    for (auto& L : t->layers)
+        for (DevBuf* b : {&L.w_fwd, &L.bias_fwd, &L.w_dgrad, &L.y, &L.z}) b->release();
+    for (int i = 0; i < 2; ++i)
+        for (DevBuf* b : {&t->pol_w_fwd[i], &t->pol_bias[i], &t->pol_w_dgrad[i], &t->g[i]}) b->release();
+    for (DevBuf* b : {&t->master, &t->grad, &t->adam_m, &t->adam_v, &t->zero_bias, &t->x0, &t->dy, &t->dt, &t->g2,
+                      &t->dlogits, &t->bn_sums, &t->bn_mean, &t->bn_rstd, &t->bn_a, &t->bn_b, &t->bwd_sums, &t->bwd_c1,
+                      &t->bwd_c2, &t->logits, &t->partials, &t->stats, &t->values, &t->dpre, &t->loss, &t->wg_scratch,
+                      &t->in_stage, &t->pi_stage, &t->z_stage})
+        b->release();
+    if (t->ev0) cudaEventDestroy(t->ev0);
+    if (t->ev1) cudaEventDestroy(t->ev1);
+    delete t;
+    e->net->train = nullptr;
+}
+}  // namespace tb
+
+extern "C" {
+
+int32_t net_train_begin(tak_engine_t* e, int32_t max_boards) {
+    TB_CHECK(e && e->net, TAK_ERR_NO_NETWORK, "no network: call net_create first");
+    NetState& ns = *e->net;
+    TB_CHECK(ns.arch == 6 && e->n == 6, TAK_ERR_BAD_ARG,
+             "training is implemented for Net6 (the reference trains only 6x6: train/src/main.rs:42-43)");
+    TB_CHECK(ns.loaded && int64_t(ns.blob_host.size()) == net_blob_elems(ns), TAK_ERR_NO_NETWORK,
+             "load weights (net_load_weights) before net_train_begin");
+    TB_CHECK(max_boards > 0, TAK_ERR_BAD_ARG, "max_boards must be positive");
+    TB_CUDA(cudaSetDevice(e->device));
+    train_destroy(e);
+    TrainState* t = new TrainState();
+    ns.train = t;
+    t->c_in = ns.c_in;
+    t->blocks = ns.blocks;
+    t->policy_ch = ns.policy_ch;
+    t->nsq = e->nsq;
+    build_layout(*t);
+    TB_CHECK(t->elems == net_blob_elems(ns), TAK_ERR_BAD_ARG, "internal: training layout does not match the blob");
+    const size_t bytes = size_t(t->elems) * 4;
+    for (DevBuf* b : {&t->master, &t->grad, &t->adam_m, &t->adam_v}) {
+        TB_CUDA(b->ensure(bytes));
+        TB_CUDA(cudaMemsetAsync(b->p, 0, bytes, e->stream));
+    }
+    TB_CUDA(cudaMemcpyAsync(t->master.p, ns.blob_host.data(), bytes, cudaMemcpyHostToDevice, e->stream));
+    TB_CUDA(t->zero_bias.ensure(512));
+    TB_CUDA(cudaMemsetAsync(t->zero_bias.p, 0, 512, e->stream));
+    for (auto& L : t->layers) {
+        TB_CUDA(L.w_fwd.ensure(C3_W_LAYER_ELEMS * 2));
+        TB_CUDA(L.w_dgrad.ensure(C3_W_LAYER_ELEMS * 2));
+        TB_CUDA(L.bias_fwd.ensure(512));
+    }
+    for (int i = 0; i < 2; ++i) {
+        TB_CUDA(t->pol_w_fwd[i].ensure(C3_W_LAYER_ELEMS * 2));
+        TB_CUDA(t->pol_w_dgrad[i].ensure(C3_W_LAYER_ELEMS * 2));
+        TB_CUDA(t->pol_bias[i].ensure(512));
+    }
+    const size_t nl = t->layers.size();
+    TB_CUDA(t->bn_sums.ensure(nl * 256 * 8));
+    for (DevBuf* b : {&t->bn_mean, &t->bn_rstd, &t->bn_a, &t->bn_b}) TB_CUDA(b->ensure(nl * 128 * 4));
+    TB_CUDA(t->bwd_sums.ensure(256 * 8));
+    TB_CUDA(t->bwd_c1.ensure(512));
+    TB_CUDA(t->bwd_c2.ensure(512));
+    TB_CUDA(t->loss.ensure(16));
+    TB_CUDA(t->wg_scratch.ensure(wgrad_scratch_elems(e->num_sms) * 4));
+    TB_CUDA(cudaEventCreate(&t->ev0));
+    TB_CUDA(cudaEventCreate(&t->ev1));
+    if (int r = ensure_capacity(e, *t, max_boards)) return r;
+    if (int r = repack(e, *t)) return r;
+    TB_CUDA(cudaStreamSynchronize(e->stream));
+    return TAK_OK;
+}
+
+int32_t net_train_chunk(tak_engine_t* e, const float* inputs, const float* pi, const float* z, int32_t boards,
+                        int32_t on_device, float* out_loss2) {
+    TB_CHECK(e && e->net && inputs && pi && z && boards > 0, TAK_ERR_BAD_ARG, "net_train_chunk: bad argument");
+    TrainState* t = train_of(e);
+    TB_CHECK(t, TAK_ERR_NO_NETWORK, "call net_train_begin first");
+    TB_CHECK(boards <= t->cap_boards, TAK_ERR_CAPACITY, "chunk of %d boards, net_train_begin reserved %d", boards,
+             t->cap_boards);
+    TB_CUDA(cudaSetDevice(e->device));
+    const size_t in_elems = size_t(boards) * t->c_in * t->nsq, pi_elems = size_t(boards) * t->policy_ch * t->nsq;
+    const float *d_in = inputs, *d_pi = pi, *d_z = z;
+    TB_CUDA(cudaEventRecord(t->ev0, e->stream));
+    if (!on_device) {
+        TB_CUDA(t->in_stage.ensure(in_elems * 4));
+        TB_CUDA(t->pi_stage.ensure(pi_elems * 4));
+        TB_CUDA(t->z_stage.ensure(size_t(boards) * 4));
+        TB_CUDA(cudaMemcpyAsync(t->in_stage.p, inputs, in_elems * 4, cudaMemcpyHostToDevice, e->stream));
+        TB_CUDA(cudaMemcpyAsync(t->pi_stage.p, pi, pi_elems * 4, cudaMemcpyHostToDevice, e->stream));
+        TB_CUDA(cudaMemcpyAsync(t->z_stage.p, z, size_t(boards) * 4, cudaMemcpyHostToDevice, e->stream));
+        d_in = t->in_stage.as<float>(); d_pi = t->pi_stage.as<float>(); d_z = t->z_stage.as<float>();
+    }
+    const uint64_t before = t->launches;
+    if (int r = train_chunk_t<6>(e, *t, d_in, d_pi, d_z, boards)) return r;
+    e->launches += t->launches - before;
+    TB_CUDA(cudaEventRecord(t->ev1, e->stream));
+    double loss[2] = {0, 0};
+    TB_CUDA(cudaMemcpyAsync(loss, t->loss.p, 16, cudaMemcpyDeviceToHost, e->stream));
+    TB_CUDA(cudaStreamSynchronize(e->stream));
+    float ms = 0;
+    TB_CUDA(cudaEventElapsedTime(&ms, t->ev0, t->ev1));
+    t->last_ms = ms;
+    t->chunks++;
+    if (out_loss2) {
+        out_loss2[0] = float(loss[0]);
+        out_loss2[1] = float(loss[1]);
+    }
+    return TAK_OK;
+}
+
+int32_t net_train_step(tak_engine_t* e, float lr, float weight_decay) {
+    TB_CHECK(e && e->net, TAK_ERR_BAD_ARG, "net_train_step: bad argument");
+    TrainState* t = train_of(e);
+    TB_CHECK(t, TAK_ERR_NO_NETWORK, "call net_train_begin first");
+    TB_CUDA(cudaSetDevice(e->device));
+    t->steps++;
+    const float beta1 = 0.9f, beta2 = 0.999f, eps = 1e-8f;
+    const float bc1 = float(1.0 - std::pow(double(beta1), t->steps));
+    const float bc2s = float(std::sqrt(1.0 - std::pow(double(beta2), t->steps)));
+    for (auto& tr : t->trainable) {
+        const int count = int(tr.second);
+        k_adam<<<(count + 255) / 256, 256, 0, e->stream>>>(t->master.as<float>() + tr.first, t->grad.as<float>() + tr.first,
+                                                           t->adam_m.as<float>() + tr.first,
+                                                           t->adam_v.as<float>() + tr.first, count, lr, weight_decay,
+                                                           beta1, beta2, eps, bc1, bc2s);
+        e->launches++;
+    }
+    TB_CUDA(cudaGetLastError());
+    TB_CUDA(cudaMemsetAsync(t->grad.p, 0, size_t(t->elems) * 4, e->stream));   // opt.zero_grad() (network.rs:94)
+    t->chunks = 0;
+    if (int r = repack(e, *t)) return r;
+    TB_CUDA(cudaStreamSynchronize(e->stream));
+    return TAK_OK;
+}
+
+int32_t net_train_get(tak_engine_t* e, int32_t what, float* out, int64_t elems) {
+    TB_CHECK(e && e->net && out, TAK_ERR_BAD_ARG, "net_train_get: bad argument");
+    TrainState* t = train_of(e);
+    TB_CHECK(t, TAK_ERR_NO_NETWORK, "call net_train_begin first");
+    TB_CHECK(elems == t->elems, TAK_ERR_BAD_ARG, "blob has %lld elements, caller passed %lld", (long long)t->elems,
+             (long long)elems);
+    TB_CHECK(what >= 0 && what <= 3, TAK_ERR_BAD_ARG, "what: 0 weights, 1 gradients, 2 Adam m, 3 Adam v");
+    TB_CUDA(cudaSetDevice(e->device));
+    const DevBuf* src[4] = {&t->master, &t->grad, &t->adam_m, &t->adam_v};
+    TB_CUDA(cudaMemcpyAsync(out, src[what]->p, size_t(elems) * 4, cudaMemcpyDeviceToHost, e->stream));
+    TB_CUDA(cudaStreamSynchronize(e->stream));
+    return TAK_OK;
+}
+
+int32_t net_train_grad_ptr(tak_engine_t* e, void** out_device_ptr, int64_t* out_elems) {
+    TB_CHECK(e && e->net && out_device_ptr && out_elems, TAK_ERR_BAD_ARG, "net_train_grad_ptr: bad argument");
+    TrainState* t = train_of(e);
+    TB_CHECK(t, TAK_ERR_NO_NETWORK, "call net_train_begin first");
+    TB_CUDA(cudaSetDevice(e->device));
+    TB_CUDA(cudaStreamSynchronize(e->stream));   // the caller (NCCL all-reduce on its own stream) may touch it now
+    *out_device_ptr = t->grad.p;
+    *out_elems = t->elems;
+    return TAK_OK;
+}
+
+int32_t net_train_stats(tak_engine_t* e, double* out_ms_last_chunk, int32_t* out_chunks_pending, int32_t* out_steps) {
+    TB_CHECK(e && e->net, TAK_ERR_BAD_ARG, "net_train_stats: bad argument");
+    TrainState* t = train_of(e);
+    TB_CHECK(t, TAK_ERR_NO_NETWORK, "call net_train_begin first");
+    if (out_ms_last_chunk) *out_ms_last_chunk = t->last_ms;
+    if (out_chunks_pending) *out_chunks_pending = t->chunks;
+    if (out_steps) *out_steps = t->steps;
+    return TAK_OK;
+}
+
+int32_t net_train_end(tak_engine_t* e) {
+    TB_CHECK(e && e->net, TAK_ERR_BAD_ARG, "net_train_end: bad argument");
+    TB_CUDA(cudaSetDevice(e->device));
+    train_destroy(e);
+    return TAK_OK;
+}
+
+}  // extern "C"

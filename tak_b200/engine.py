@@ -80,6 +80,7 @@ class Engine:
         self.lib = _lib.load()
         self.n = n
         self.max_games = max_games
+        self.device = device
         cfg = EngineConfig(device=device, n=n, max_games=max_games, nodes_per_game=nodes_per_game,
                            max_batch=max_batch)
         h = C.c_void_p()
@@ -204,6 +205,57 @@ class Engine:
         return {"ms_forward": out[0], "ms_conv": out[1], "conv_launches": int(out[2]), "flop": out[3]}
 
     # ---- alpha_tak::Node, batched -------------------------------------------------------------------------------
+    # ---- Network::train (network.rs:37-97), Net6 ----
+    def train_begin(self, max_boards: int):
+        check(self.lib.net_train_begin(self._h, max_boards))
+
+    def train_chunk(self, inputs, pi, z):
+        """train_inner for one chunk: numpy host arrays [b,C,n,n] / [b,P] / [b], or torch CUDA tensors of those shapes
+        (passed by device pointer).  Returns (loss_p, loss_z); gradients accumulate until train_step."""
+        on_device = hasattr(inputs, "data_ptr")
+        if on_device:
+            for t in (inputs, pi, z):
+                assert t.is_cuda and t.is_contiguous() and t.dtype.is_floating_point and t.element_size() == 4
+            b = int(inputs.shape[0])
+            ptrs = [t.data_ptr() for t in (inputs, pi, z)]
+        else:
+            inputs = np.ascontiguousarray(inputs, dtype=np.float32)
+            pi = np.ascontiguousarray(pi, dtype=np.float32)
+            z = np.ascontiguousarray(z, dtype=np.float32)
+            b = int(inputs.shape[0])
+            ptrs = [a.ctypes.data for a in (inputs, pi, z)]
+        assert pi.shape[0] == b and z.shape[0] == b
+        out = (C.c_float * 2)()
+        check(self.lib.net_train_chunk(self._h, ptrs[0], ptrs[1], ptrs[2], b, 1 if on_device else 0, out))
+        return float(out[0]), float(out[1])
+
+    def train_step(self, lr: float = 1e-4, weight_decay: float = 1e-4):       # network.rs:14-15
+        check(self.lib.net_train_step(self._h, lr, weight_decay))
+
+    def train_get(self, what: int = 0) -> np.ndarray:
+        """0 weights (load them with net_load_weights to search with the trained network), 1 gradients, 2/3 Adam m/v."""
+        out = np.zeros(self.net_weights_size(), dtype=np.float32)
+        check(self.lib.net_train_get(self._h, what, out.ctypes.data_as(C.POINTER(C.c_float)), out.size))
+        return out
+
+    def train_grad_tensor(self):
+        """The gradient blob as a zero-copy torch CUDA tensor (for torch.distributed.all_reduce in data-parallel runs)."""
+        import torch
+        ptr, n = C.c_void_p(), C.c_int64()
+        check(self.lib.net_train_grad_ptr(self._h, C.byref(ptr), C.byref(n)))
+
+        class _Mem:
+            __cuda_array_interface__ = {"shape": (n.value,), "typestr": "<f4", "data": (ptr.value, False), "version": 2}
+        return torch.as_tensor(_Mem(), device=torch.device("cuda", self.device))
+
+    def train_stats(self):
+        ms, chunks, steps = C.c_double(), C.c_int32(), C.c_int32()
+        check(self.lib.net_train_stats(self._h, C.byref(ms), C.byref(chunks), C.byref(steps)))
+        return {"ms_last_chunk": ms.value, "chunks_pending": chunks.value, "steps": steps.value}
+
+    def train_end(self):
+        check(self.lib.net_train_end(self._h))
+
     def tree_reset(self, ids):
         p, k, _keep = _ids(ids)
         check(self.lib.mcts_tree_reset(self._h, p, k))

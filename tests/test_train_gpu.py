@@ -1,0 +1,182 @@
+"""GPU parity of the training step (Network::train_inner + Adam, alpha-tak/src/model/network.rs:37-97,
+forward_training net6.rs:111-122) against the fp32 PyTorch restatement oracle/net_ref.py:RefTrainer on the same weights
+and the same chunk of examples.  The device path computes in bf16 (operands and saved activations) with fp32
+accumulation, fp32 master weights and fp32 gradients; tolerances are written next to each check."""
+import numpy as np
+import pytest
+
+import oracle
+import tak_b200 as tb
+from oracle.net_ref import RefTrainer
+from tak_b200 import weights as W
+from util import random_positions, splitmix, to_tb_state
+
+pytestmark = pytest.mark.gpu
+
+
+def make_chunk(n_pos, seed):
+    """(inputs [b,92,6,6], pi [b,9036], z [b]) from oracle positions: pi = normalised pseudo-random visit counts over the
+    legal moves, z in {-1, 0, 1}."""
+    games = random_positions(6, n_pos, seed=seed, max_ply=60)
+    P = oracle.policy_size(6)
+    x = np.stack([g.repr() for g in games]).astype(np.float32)
+    pi = np.zeros((n_pos, P), dtype=np.float32)
+    z = np.zeros(n_pos, dtype=np.float32)
+    for i, g in enumerate(games):
+        moves = g.possible_moves()
+        v = np.array([1 + splitmix(seed * 31 + i * 1009 + k) % 50 for k in range(len(moves))], dtype=np.float64)
+        v[splitmix(seed + i) % len(moves)] += 400                         # a peaked visit distribution
+        for m, c in zip(moves, v / v.sum()):
+            pi[i, oracle.move_index(m, 6)] = c
+        z[i] = float(splitmix(seed * 17 + i) % 3) - 1.0
+    return x, pi, z
+
+
+def rel_err(a, b):
+    return float(np.linalg.norm(a.astype(np.float64) - b.astype(np.float64)) / max(1e-30, np.linalg.norm(b.astype(np.float64))))
+
+
+@pytest.fixture(scope="module")
+def trained():
+    blob = W.random_weights(6, seed=11)
+    eng = tb.Engine(6, 8, nodes_per_game=1 << 10, max_batch=8)
+    eng.net_create(6)
+    eng.net_load_weights(blob)
+    eng.train_begin(256)
+    ref = RefTrainer(6, blob, device="cuda")
+    emu = RefTrainer(6, blob, device="cuda", emulate_bf16=True)
+    chunks = [make_chunk(200, 3), make_chunk(131, 4)]                     # ragged: the second chunk is smaller
+    losses, ref_losses = [], []
+    for x, pi, z in chunks:
+        losses.append(eng.train_chunk(x, pi, z))
+        ref_losses.append(ref.chunk(x, pi, z))
+        emu.chunk(x, pi, z)
+    out = {"eng": eng, "ref": ref, "blob": blob, "losses": losses, "ref_losses": ref_losses,
+           "grads": eng.train_get(1), "ref_grads": ref.grads(), "emu_grads": emu.grads(), "chunks": chunks}
+    yield out
+    eng.close()
+
+
+def test_losses_match(trained):
+    # bf16 forward through 33 convolutions: |loss - ref| <= 2e-2 * |ref| (measured ~3e-3)
+    for (lp, lz), (rp, rz) in zip(trained["losses"], trained["ref_losses"]):
+        assert abs(lp - rp) <= 2e-2 * abs(rp), (lp, rp)
+        assert abs(lz - rz) <= 2e-2 * max(abs(rz), 0.1), (lz, rz)
+
+
+def test_gradients_match_autograd(trained):
+    """Accumulated gradient (2 chunks) per tensor, relative L2 error against autograd.
+
+    Measured (this test prints the table): the heads agree with fp32 autograd to 1e-3 .. 8e-3; going down the tower the
+    error grows by about 1.5 % per residual block to ~0.27 at the first layers -- and a PyTorch autograd run that merely
+    ROUNDS the stored activations / activation gradients / conv operands to bf16 (RefTrainer(emulate_bf16=True)) is
+    just as far from fp32 (0.27): ReLU masks and BatchNorm statistics of a 33-layer random-init tower amplify bf16
+    storage noise.  So the criterion is: the device path is as close to fp32 autograd as bf16-rounding autograd is
+    (<= 1.5x its error + 3e-2), the heads are tight, and the gradient direction is kept (cosine >= 0.93 per tensor)."""
+    g = W.split(trained["grads"], 6)
+    r = W.split(trained["ref_grads"], 6)
+    m = W.split(trained["emu_grads"], 6)
+    print("\nrel L2 error per tensor: device vs fp32 | device vs bf16-emulating autograd | emulation vs fp32 | cosine")
+    bad = {}
+    for name in g:
+        if name.endswith("running_mean") or name.endswith("running_var"):
+            continue
+        if name.endswith("conv1.bias") or name.endswith("conv2.bias") or name == "initial_conv.bias":
+            # a conv bias feeding a batch-statistics BatchNorm has a mathematically zero gradient: autograd returns fp32
+            # rounding noise, the device path exactly 0
+            assert float(np.abs(g[name]).max()) == 0.0
+            assert float(np.abs(r[name]).max()) <= 1e-4 * float(np.abs(r["value_fc.weight"]).max() + 1.0)
+            continue
+        e_dev, e_emu, e_de = rel_err(g[name], r[name]), rel_err(m[name], r[name]), rel_err(g[name], m[name])
+        a, b = g[name].astype(np.float64).ravel(), r[name].astype(np.float64).ravel()
+        cos = float(a @ b / max(1e-300, np.linalg.norm(a) * np.linalg.norm(b)))
+        print(f"  {name:28s} {e_dev:9.4f} {e_de:9.4f} {e_emu:9.4f} {cos:9.4f}")
+        if not (e_dev <= 1.5 * e_emu + 3e-2 and e_de <= 1.5 * e_emu + 3e-2 and cos >= 0.93):
+            bad[name] = (e_dev, e_de, e_emu, cos)
+    assert not bad, f"gradient mismatch: {bad}"
+    for name in ("policy_conv.weight", "policy_conv.bias", "value_fc.weight", "value_fc.bias"):
+        assert rel_err(g[name], r[name]) <= 2e-2, name
+    # the last residual block sits one step behind the heads: still tight
+    for name in ("block15.conv2.weight", "block15.bn2.weight", "block15.bn2.bias"):
+        assert rel_err(g[name], r[name]) <= 5e-2, name
+
+
+def test_training_reduces_the_loss_like_the_reference():
+    """End to end: 12 Adam steps (lr 1e-3) on one fixed chunk drive the loss down on the device path as they do in the
+    fp32 reference (same start, same data): both fall by > 25 % and end within 10 % of each other."""
+    blob = W.random_weights(6, seed=21)
+    x, pi, z = make_chunk(160, 9)
+    eng = tb.Engine(6, 8, nodes_per_game=1 << 10, max_batch=8)
+    eng.net_create(6)
+    eng.net_load_weights(blob)
+    eng.train_begin(160)
+    ref = RefTrainer(6, blob, device="cuda", lr=1e-3, wd=1e-4)
+    dev_loss, ref_loss = [], []
+    for _ in range(12):
+        dev_loss.append(sum(eng.train_chunk(x, pi, z)))
+        eng.train_step(1e-3, 1e-4)
+        ref_loss.append(sum(ref.chunk(x, pi, z)))
+        ref.step()
+    print("\nloss device:", [round(v, 3) for v in dev_loss], "\nloss fp32  :", [round(v, 3) for v in ref_loss])
+    assert dev_loss[-1] < 0.75 * dev_loss[0] and ref_loss[-1] < 0.75 * ref_loss[0]
+    assert abs(dev_loss[-1] - ref_loss[-1]) <= 0.10 * ref_loss[-1]
+    eng.train_end()
+    eng.close()
+
+
+def test_running_statistics_updated(trained):
+    w = W.split(trained["eng"].train_get(0), 6)
+    r = W.split(trained["ref"].blob(), 6)
+    for name in w:
+        if name.endswith("running_mean"):
+            assert np.abs(w[name] - r[name]).max() <= 2e-2 * max(1.0, float(np.abs(r[name]).max())), name
+        if name.endswith("running_var"):
+            assert rel_err(w[name], r[name]) <= 3e-2, name
+
+
+def test_adam_step_matches_torch_on_the_same_gradients(trained):
+    """Adam itself is exact arithmetic on fp32: feed torch.optim.Adam the DEVICE gradients and compare the updated weights
+    (two steps, so the moment estimates and bias corrections are exercised): max abs diff <= 2e-7."""
+    eng, blob = trained["eng"], trained["blob"]
+    ref = RefTrainer(6, blob, device="cuda")
+    for step in range(2):
+        if step == 1:
+            x, pi, z = trained["chunks"][1]
+            eng.train_chunk(x, pi, z)
+        ref.set_grads(eng.train_get(1))
+        # keep the reference's BN running statistics out of the comparison: only trainable tensors are stepped
+        eng.train_step(1e-4, 1e-4)
+        ref.step()
+        assert float(np.abs(eng.train_get(1)).max()) == 0.0               # zero_grad
+        w, r = W.split(eng.train_get(0), 6), W.split(ref.blob(), 6)
+        for name in w:
+            if "running_" in name:
+                continue
+            assert float(np.abs(w[name] - r[name]).max()) <= 2e-7, (step, name)
+    st = eng.train_stats()
+    assert st["steps"] == 2 and st["chunks_pending"] == 0
+    # the stepped weights can be searched with: load them into the inference path
+    new_blob = eng.train_get(0)
+    assert np.isfinite(new_blob).all() and float(np.abs(new_blob - blob).max()) > 0
+    eng.net_load_weights(new_blob)
+    g = oracle.Game(6, 4)
+    pol, val = eng.policy_eval([to_tb_state(g.state())])
+    assert abs(float(pol.sum()) - 1.0) < 1e-3 and np.isfinite(val).all()
+
+
+def test_device_tensors_and_grad_view(trained):
+    """net_train_chunk with device pointers == with host pointers; the zero-copy gradient tensor aliases the blob."""
+    import torch
+    eng = trained["eng"]
+    x, pi, z = trained["chunks"][0]
+    a = eng.train_chunk(x, pi, z)
+    g_host = eng.train_get(1)
+    gt = eng.train_grad_tensor()
+    assert gt.shape[0] == g_host.size and np.array_equal(gt.cpu().numpy(), g_host)
+    gt.zero_()
+    assert float(np.abs(eng.train_get(1)).max()) == 0.0
+    b = eng.train_chunk(torch.from_numpy(x).cuda(), torch.from_numpy(pi).cuda(), torch.from_numpy(z).cuda())
+    assert a[0] == b[0] and a[1] == b[1]
+    # not bit-identical run to run: the split-K partial sums and double atomics are order dependent
+    assert rel_err(eng.train_get(1), g_host) < 1e-3
+    gt.zero_()
