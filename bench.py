@@ -243,7 +243,7 @@ def augment_rate(eng, recs, dev, pk):
     from tak_b200._lib import check
 
     if not recs:
-        return None
+        return None, None
     k = len(recs)
     arr = (tb.ReplayRecord * k)(*recs)
     c, p, n = tb.input_channels(6), tb.policy_size(6), 6
@@ -263,7 +263,55 @@ def augment_rate(eng, recs, dev, pk):
     out_bytes = 8 * k * (c * n * n + p + 1) * 4 + 8 * k * p * 4   # tensors written + the zero fill of pi
     return {"value": k / dt, "unit": "examples/s", "examples": k, "rows_out": 8 * k, "ms": 1e3 * dt,
             "what": "host replay records -> H2D -> 8 symmetries x (game_repr, pi, z) in HBM, host-timed incl. the copy",
-            "hbm_write_gbs": out_bytes / dt / 1e9, "hbm_peak_gbs": pk["hbm"]}
+            "hbm_write_gbs": out_bytes / dt / 1e9, "hbm_peak_gbs": pk["hbm"]}, (inputs, pi, z)
+
+
+def train_rate(eng, tensors, world, dist, dev, pk):
+    """Network::train_inner + Adam (next row N1, network.rs:37-97) on the augmented examples of this run: chunks of
+    500 examples x 8 symmetries = 4000 positions (CHUNK_SIZE, network.rs:19), inputs resident in HBM; with N ranks every
+    rank trains its own chunks and the fp32 gradient blob is all-reduced over NCCL before the Adam step."""
+    import torch
+
+    from tak_b200 import weights as W
+
+    inputs, pi, z = tensors
+    B = min(4000, inputs.shape[0])
+    x, p, zz = inputs[:B].contiguous(), pi[:B].contiguous(), z[:B].contiguous()
+    eng.train_begin(B)
+    for _ in range(2):
+        eng.train_chunk(x, p, zz)
+    chunks = 4
+    ms, loss = [], None
+    for _ in range(chunks):
+        loss = eng.train_chunk(x, p, zz)
+        ms.append(eng.train_stats()["ms_last_chunk"])
+    g = eng.train_grad_tensor()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    if dist:
+        dist.all_reduce(g)
+        torch.cuda.synchronize()
+    t_ar = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    eng.train_step(1e-4, 1e-4)
+    t_step = time.perf_counter() - t0
+    ms_chunk = float(np.mean(ms))
+    ms_max = par_max(ms_chunk, dev)
+    flop = 3.0 * FLOP_PER_EVAL_NET6 * B          # forward + dgrad + wgrad
+    out = {"value": world * B / (ms_max * 1e-3), "unit": "positions/s", "positions_per_chunk": B,
+           "ms_per_chunk": ms_max, "allreduce_ms": 1e3 * t_ar, "adam_step_ms": 1e3 * t_step,
+           "grad_bytes": int(W.blob_size(6)) * 4, "loss_p": loss[0], "loss_z": loss[1],
+           "tflops": flop / (ms_max * 1e-3) / 1e12, "tensor_peak": pk["bf16_sustained"],
+           "frac_of_tensor_peak": flop / (ms_max * 1e-3) / 1e12 / pk["bf16_sustained"],
+           "what": "train_inner on 4000 augmented positions (forward_training + loss + backward, CUDA events on the engine "
+                   "stream), then NCCL all-reduce of the gradient blob and the Adam step"}
+    eng.train_end()
+    return out
+
+
+def par_max(x, dev):
+    from tak_b200 import parallel as par
+    return par.max_over_ranks(x, dev)
 
 
 def run_b200(args):
@@ -429,7 +477,10 @@ def run_b200(args):
         C.memmove(r.moves, mv0[i].ctypes.data, 2 * r.n_children)
         C.memmove(r.visits, vis0[i].ctypes.data, 4 * r.n_children)
         aug_recs.append(r)
-    augment = augment_rate(engines[0], aug_recs, dev, pk)
+    augment, aug_tensors = augment_rate(engines[0], aug_recs, dev, pk)
+
+    # ---------------- training step (next row N1): train_inner + all-reduce + Adam on those examples -----------------
+    train = train_rate(engines[0], aug_tensors, world, dist, dev, pk) if aug_tensors is not None else None
 
     line = None
     if rank == 0:
@@ -455,6 +506,7 @@ def run_b200(args):
             "roofline": roofline,
             "movegen": movegen,
             "augment": augment,
+            "train": train,
             "cpu_baseline": {"value": cpu["value"], "unit": UNIT, "cores": cpu["cores"], "kind": "port",
                              "sample": cpu["sample"]} if cpu else None,
             "clocks": clocks,
