@@ -272,6 +272,7 @@ def train_rate(eng, tensors, world, dist, dev, pk):
     rank trains its own chunks and the fp32 gradient blob is all-reduced over NCCL before the Adam step."""
     import torch
 
+    from tak_b200 import parallel as par_mod
     from tak_b200 import weights as W
 
     inputs, pi, z = tensors
@@ -289,7 +290,7 @@ def train_rate(eng, tensors, world, dist, dev, pk):
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     if dist:
-        dist.all_reduce(g)
+        par_mod.allreduce_gradients(g)
         torch.cuda.synchronize()
     t_ar = time.perf_counter() - t0
     t0 = time.perf_counter()

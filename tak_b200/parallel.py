@@ -4,6 +4,9 @@ Games never interact, so each rank owns a contiguous block of global game ids, i
 replica; the rollout loop has no collective.  Exactly two exchanges exist:
   * `broadcast_weights`  rank 0's fp32 weight blob -> every rank (NCCL broadcast over NVLink; gloo in CPU tests)
   * `gather_replay`      fixed-size replay records of all ranks -> every rank (all_gather of padded byte tensors)
+The training step (next row N1) adds the one collective data-parallel training needs:
+  * `allreduce_gradients` sum of every rank's fp32 gradient blob, in place, before the Adam step -- every rank then takes
+                          the identical step, which is the reference's single-process step over world x as many chunks
 The reference has no distributed code (single process, single GPU: alpha-tak/src/lib.rs:21-23).
 """
 from __future__ import annotations
@@ -54,6 +57,15 @@ def gather_replay(records: Sequence, record_type, device: torch.device) -> List:
         buf = gathered[r][: c * size].cpu().numpy().tobytes()
         out += [record_type.from_buffer_copy(buf[i * size:(i + 1) * size]) for i in range(c)]
     return out
+
+
+def allreduce_gradients(grad: torch.Tensor) -> torch.Tensor:
+    """In-place sum over ranks of the gradient blob (`Engine.train_grad_tensor()`: a zero-copy view of the engine's
+    accumulator).  Gradients of chunks ADD in the reference (`total_loss.backward()` per chunk, one `opt.step()` per
+    CHUNKS_IN_STEP chunks, network.rs:84-95), so the sum over ranks is the single-process gradient of all their chunks."""
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(grad, op=dist.ReduceOp.SUM)
+    return grad
 
 
 def max_over_ranks(x: float, device: torch.device) -> float:

@@ -44,6 +44,13 @@ def _worker(rank, world, port, out_q):
     allr = par.gather_replay(recs, tb.ReplayRecord, dev)
     ids = [r.game_id for r in allr]
     ok_r = ids == [0, 1, 2, 16, 17, 18, 19, 20] and [r.visits[0] for r in allr][3] == 100
+    g = torch.full((1000,), float(rank + 1))
+    g[rank] += 10.0
+    par.allreduce_gradients(g)          # in place: both ranks end with the sum
+    want = torch.full((1000,), 3.0)
+    want[0] += 10.0
+    want[1] += 10.0
+    ok_r = ok_r and bool(torch.equal(g, want))
     mx = par.max_over_ranks(float(rank + 1), dev)
     sm = par.sum_over_ranks(float(rank + 1), dev)
     out_q.put((rank, ok_w, ok_r, mx, sm))
