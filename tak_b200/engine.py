@@ -374,12 +374,25 @@ class Engine:
 
 
     # ---- alpha_tak::Example::to_tensors, batched (example.rs:63-78) -------------------------------------------
-    def examples_to_tensors(self, records: Sequence[ReplayRecord]):
+    def examples_to_tensors(self, records: Sequence[ReplayRecord], on_device: bool = False):
         """8-fold symmetry augmentation of replay records on the device:
-        (inputs [8k, C, n, n], pi [8k, policy_size], z [8k]) as host arrays, row 8e+s = symmetry s of example e."""
+        (inputs [8k, C, n, n], pi [8k, policy_size], z [8k]), row 8e+s = symmetry s of example e -- as host arrays, or
+        with on_device as torch CUDA tensors left in HBM (what train_chunk consumes without a host round trip)."""
         k = len(records)
         arr = (ReplayRecord * max(k, 1))(*records)
         c = input_channels(self.n)
+        if on_device:
+            import torch
+            dev = torch.device("cuda", self.device)
+            inputs = torch.empty((8 * k, c, self.n, self.n), dtype=torch.float32, device=dev)
+            pi = torch.empty((8 * k, self.policy_size), dtype=torch.float32, device=dev)
+            z = torch.empty(8 * k, dtype=torch.float32, device=dev)
+            torch.cuda.synchronize(dev)
+            fp = C.POINTER(C.c_float)
+            check(self.lib.examples_to_tensors(self._h, arr, k, C.cast(inputs.data_ptr(), fp), C.cast(pi.data_ptr(), fp),
+                                               C.cast(z.data_ptr(), fp), 1))
+            self.sync()
+            return inputs, pi, z
         inputs = np.zeros((8 * k, c, self.n, self.n), dtype=np.float32)
         pi = np.zeros((8 * k, self.policy_size), dtype=np.float32)
         z = np.zeros(8 * k, dtype=np.float32)

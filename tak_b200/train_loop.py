@@ -1,0 +1,100 @@
+"""The `train` binary's loop on the device engines (train/src/main.rs:82-123, alpha-tak/src/model/network.rs:37-57):
+
+    loop { if examples: new = copy(network); new.train(examples); if pit(new, network).win_rate() > 0.55: network = new
+           examples += self_play_parallel(network) }
+
+`train_network` is `Network::train` (fresh Adam, shuffled references, chunks_exact(CHUNK_SIZE), a step every
+CHUNKS_IN_STEP chunks -- gradients of a trailing partial group are dropped, as in the reference); `training_iteration` is
+one turn of `training_loop`.  Everything heavy runs behind the C ABI (self-play, augmentation, train_inner, Adam, pit);
+this file is the cold control flow.  File output of the reference (`_models/*.model`, `_examples/*.data`) is reduced to
+`save_examples` (same text format, example.rs:81-100) and the weight blob as .npy.
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Sequence
+
+import numpy as np
+
+from ._lib import ReplayRecord
+from .engine import Engine, example_format
+from .pit import PitResult, pit
+
+CHUNK_SIZE = 500            # network.rs:19
+CHUNKS_IN_STEP = 20         # network.rs:20
+LEARNING_RATE = 1e-4        # network.rs:14
+WEIGHT_DECAY = 1e-4         # network.rs:15
+MAX_EXAMPLES = 400_000      # train/src/main.rs:25
+WIN_RATE_THRESHOLD = 0.55   # train/src/main.rs:27
+
+
+def train_network(eng: Engine, examples: Sequence[ReplayRecord], rng: np.random.Generator,
+                  chunk_size: int = CHUNK_SIZE, chunks_in_step: int = CHUNKS_IN_STEP, lr: float = LEARNING_RATE,
+                  weight_decay: float = WEIGHT_DECAY, allreduce: Optional[Callable] = None,
+                  log: Callable = print) -> np.ndarray:
+    """`Network::train(&mut self, examples)` starting from the weights last loaded into `eng`; returns the new blob
+    (weights incl. BatchNorm running statistics).  `allreduce(grad_tensor)` is called before every step in data-parallel
+    runs (parallel.allreduce_gradients)."""
+    log(f"starting training with {len(examples)} examples")
+    eng.train_begin(8 * chunk_size)                       # Adam { wd, ..Default }.build(vs, lr): fresh moments
+    order = rng.permutation(len(examples))                # refs.shuffle(&mut thread_rng())
+    losses = []
+    for i in range(len(examples) // chunk_size):          # chunks_exact(CHUNK_SIZE)
+        recs = [examples[j] for j in order[i * chunk_size:(i + 1) * chunk_size]]
+        inputs, pi, z = eng.examples_to_tensors(recs, on_device=True)    # flat_map(|ex| ex.to_tensors())
+        lp, lz = eng.train_chunk(inputs, pi, z)
+        losses.append((lp, lz))
+        log(f"p={lp:.4f}\t z={lz:.4f}")
+        if (i + 1) % chunks_in_step == 0:
+            if allreduce is not None:
+                allreduce(eng.train_grad_tensor())
+            log("making step!")
+            eng.train_step(lr, weight_decay)
+    blob = eng.train_get(0)
+    eng.train_end()
+    train_network.last_losses = losses
+    return blob
+
+
+def collect_self_play(eng: Engine, min_examples: int, max_steps: int = 10_000, **selfplay_cfg) -> List[ReplayRecord]:
+    """`self_play_parallel(&network)` until at least `min_examples` completed-game records exist (the reference plays a
+    fixed number of games; the device loop keeps every slot busy and hands back the records of finished games)."""
+    eng.selfplay_begin(**selfplay_cfg)
+    out: List[ReplayRecord] = []
+    for _ in range(max_steps):
+        eng.selfplay_step(1)
+        out += eng.selfplay_drain(16 * eng.max_games)
+        if len(out) >= min_examples:
+            break
+    return out
+
+
+def save_examples(path: str, examples: Sequence[ReplayRecord]) -> None:
+    with open(path, "w") as f:
+        for ex in examples:
+            f.write(example_format(ex) + "\n")
+
+
+def training_iteration(current: Engine, candidate: Engine, blob: np.ndarray, examples: List[ReplayRecord],
+                       rng: np.random.Generator, pit_games: int = 128, pit_rollouts: int = 50, pit_batch: int = 16,
+                       min_new_examples: int = 1000, train_kw: Optional[dict] = None,
+                       selfplay_kw: Optional[dict] = None, log: Callable = print):
+    """One turn of `training_loop` (train/src/main.rs:82-123).  `current` holds the accepted network (weights `blob`),
+    `candidate` is a second engine for the copy being trained and pitted.  Returns (blob, examples, PitResult | None)."""
+    result: Optional[PitResult] = None
+    if examples:
+        candidate.net_load_weights(blob)                  # copy(&network)
+        new_blob = train_network(candidate, examples, rng, log=log, **(train_kw or {}))
+        candidate.net_load_weights(new_blob)
+        log("pitting two networks against each other")
+        result = pit(candidate, current, games=pit_games, batch=pit_batch, rollouts=pit_rollouts,
+                     seed=int(rng.integers(1 << 31)))
+        log(repr(result))
+        if result.win_rate() > WIN_RATE_THRESHOLD:
+            blob = new_blob
+            current.net_load_weights(blob)
+            log("saving model")
+        if len(examples) > MAX_EXAMPLES:
+            examples = examples[-MAX_EXAMPLES:]
+    log("starting self-play")
+    examples = list(examples) + collect_self_play(current, min_new_examples, **(selfplay_kw or {}))
+    return blob, examples, result
