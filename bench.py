@@ -191,8 +191,9 @@ PERFT6_D5 = 1_253_506_520  # tak/tests/perft.rs:98 (the value the reference keep
 
 def movegen_mnodes(eng, world, rank, dev, pk):
     """The metric's second half: movegen + play + result throughput as perft(5) of the 6x6 opening position through the
-    C ABI (tak_perft), breadth-first on the device.  With N ranks the 36 root moves are dealt round-robin and the counts
-    are summed with one all-reduce."""
+    C ABI (tak_perft), breadth-first on the device.  With N ranks the 1 260 positions two plies below the root are dealt
+    round-robin (tak_perft_multi expands a rank's share as one frontier) and the counts are summed with one all-reduce
+    (SURVEY.md section 8e)."""
     from tak_b200 import parallel as par
 
     depth = 5
@@ -205,16 +206,14 @@ def movegen_mnodes(eng, world, rank, dev, pk):
         st = eng.perft_stats()
         ms, mat = st["ms"], st["materialised"]
     else:
-        moves = eng.possible_moves([0])[0]
-        for i, mv in enumerate(moves):
-            if i % world != rank:
-                continue
-            eng.upload([0], [root])
-            assert not eng.play([0], [int(mv)]).any()
-            nodes += eng.perft(eng.download([0])[0], depth - 1)
-            st = eng.perft_stats()
-            ms += st["ms"]
-            mat += st["materialised"]
+        # every rank builds the depth-2 frontier (1 260 positions, host-driven, untimed), takes every world-th position
+        # and expands its share in ONE breadth-first perft of the remaining depth
+        front, ended = eng.frontier(root, 2)
+        mine = front[rank::world]
+        eng.perft_multi(mine, depth - 2)     # warm-up: arenas sized for this share
+        nodes = eng.perft_multi(mine, depth - 2) + (ended if rank == 0 else 0)
+        st = eng.perft_stats()
+        ms, mat = st["ms"], st["materialised"]
     total = int(par.sum_over_ranks(float(nodes), dev))
     t_max = par.max_over_ranks(ms, dev)
     mat_total = par.sum_over_ranks(float(mat), dev)

@@ -118,6 +118,9 @@ int32_t tak_possible_moves(tak_engine_t* e, const int32_t* ids, int32_t n, uint1
 int32_t tak_play(tak_engine_t* e, const int32_t* ids, const uint16_t* moves, int32_t n, int32_t* out_status);
 int32_t tak_result(tak_engine_t* e, const int32_t* ids, int32_t n, uint8_t* out_results);
 int32_t tak_perft(tak_engine_t* e, const tak_state_t* root, int32_t depth, uint64_t* out_nodes);
+/* the same count summed over n_roots independent roots in ONE breadth-first expansion (multi-GPU perft: every rank takes a
+ * share of a shallow frontier) */
+int32_t tak_perft_multi(tak_engine_t* e, const tak_state_t* roots, int32_t n_roots, int32_t depth, uint64_t* out_nodes);
 /* timing hook for bench.py: device milliseconds (CUDA events on the engine stream) of the last tak_perft, and
  * the number of child states it materialised / kernels it launched */
 int32_t tak_perft_stats(tak_engine_t* e, double* out_ms, uint64_t* out_materialised, uint64_t* out_launches);

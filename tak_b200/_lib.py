@@ -118,6 +118,7 @@ SYMBOLS = {
     "tak_play": (_i32, [_vp, _P(_i32), _P(_u16), _i32, _P(_i32)]),
     "tak_result": (_i32, [_vp, _P(_i32), _i32, _P(C.c_uint8)]),
     "tak_perft": (_i32, [_vp, _P(TakState), _i32, _P(_u64)]),
+    "tak_perft_multi": (_i32, [_vp, _P(TakState), _i32, _i32, _P(_u64)]),
     "tak_perft_stats": (_i32, [_vp, _P(C.c_double), _P(_u64), _P(_u64)]),
     "tak_move_index": (_i32, [_i32, _u16, _P(_i32)]),
     "tak_policy_size": (_i32, [_i32, _P(_i32)]),

@@ -372,16 +372,23 @@ int32_t tak_result(tak_engine_t* e, const int32_t* ids, int32_t n, uint8_t* out_
 }
 
 int32_t tak_perft(tak_engine_t* e, const tak_state_t* root, int32_t depth, uint64_t* out_nodes) {
-    TB_CHECK(e && root && out_nodes && depth >= 0, TAK_ERR_BAD_ARG, "tak_perft: bad argument");
-    TB_CHECK(root->n == e->n, TAK_ERR_BAD_ARG, "root has board size %d, engine has %d", root->n, e->n);
+    return tak_perft_multi(e, root, 1, depth, out_nodes);
+}
+
+int32_t tak_perft_multi(tak_engine_t* e, const tak_state_t* roots, int32_t n_roots, int32_t depth, uint64_t* out_nodes) {
+    TB_CHECK(e && roots && out_nodes && depth >= 0 && n_roots >= 0, TAK_ERR_BAD_ARG, "tak_perft: bad argument");
     TB_CHECK(depth <= 12, TAK_ERR_BAD_ARG, "depth %d too large", depth);
     TB_CUDA(cudaSetDevice(e->device));
-    if (depth == 0) { *out_nodes = 1; return TAK_OK; }
-    std::vector<uint8_t> rec(e->state_bytes);
-    pack_state(e->n, *root, rec.data());
-    TB_CUDA(e->pf_root.ensure(e->state_bytes));
+    if (depth == 0 || n_roots == 0) { *out_nodes = uint64_t(n_roots); return TAK_OK; }
+    std::vector<uint8_t> rec(size_t(e->state_bytes) * n_roots);
+    for (int i = 0; i < n_roots; ++i) {
+        TB_CHECK(roots[i].n == e->n, TAK_ERR_BAD_ARG, "root %d has board size %d, engine has %d", i, roots[i].n, e->n);
+        pack_state(e->n, roots[i], rec.data() + size_t(i) * e->state_bytes);
+    }
+    TB_CUDA(e->pf_root.ensure(rec.size()));
     TB_CUDA(e->pf_leaves.ensure(8));
-    TB_CUDA(cudaMemcpyAsync(e->pf_root.p, rec.data(), e->state_bytes, cudaMemcpyHostToDevice, e->stream));
+    TB_CUDA(cudaMemcpyAsync(e->pf_root.p, rec.data(), rec.size(), cudaMemcpyHostToDevice, e->stream));
+    TB_CUDA(cudaStreamSynchronize(e->stream));   // `rec` is a stack-lifetime host buffer
     TB_CUDA(cudaMemsetAsync(e->pf_leaves.p, 0, 8, e->stream));
     e->pf_materialised = 0;
     e->pf_launches = 0;
@@ -390,7 +397,7 @@ int32_t tak_perft(tak_engine_t* e, const tak_state_t* root, int32_t depth, uint6
     TB_CUDA(cudaEventCreate(&e1));
     TB_CUDA(cudaEventRecord(e0, e->stream));
     int r = TAK_OK;
-    TB_DISPATCH_N(e->n, r = perft_level<N_>(e, e->pf_root.as<uint8_t>(), 1, depth, 0,
+    TB_DISPATCH_N(e->n, r = perft_level<N_>(e, e->pf_root.as<uint8_t>(), n_roots, depth, 0,
                                             e->pf_leaves.as<unsigned long long>()));
     if (r == TAK_OK) {
         cudaEventRecord(e1, e->stream);

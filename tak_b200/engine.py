@@ -153,6 +153,42 @@ class Engine:
         check(self.lib.tak_perft(self._h, C.byref(root), depth, C.byref(out)))
         return out.value
 
+    def perft_multi(self, roots: Sequence[TakState], depth: int) -> int:
+        """Sum of perft(root, depth) over `roots`, expanded together (one frontier)."""
+        arr = (TakState * max(len(roots), 1))(*roots)
+        out = C.c_uint64()
+        check(self.lib.tak_perft_multi(self._h, arr, len(roots), depth, C.byref(out)))
+        return out.value
+
+    def frontier(self, root: TakState, depth: int):
+        """(positions `depth` plies below `root` in move-generation order, number of lines that ended earlier).
+        perft.rs:3-18 counts a finished game as 1 at whatever depth it ends, so
+            perft(root, d) == ended + perft_multi(positions, d - depth).
+        Host-driven through result / possible_moves / play on the engine's slots; meant for shallow depths."""
+        level, ended = [root], 0
+        for _ in range(depth):
+            nxt: List[TakState] = []
+            for lo in range(0, len(level), self.max_games):
+                part = level[lo:lo + self.max_games]
+                ids = list(range(len(part)))
+                self.upload(ids, part)
+                res = self.result(ids)
+                lists = self.possible_moves(ids)
+                parents, moves = [], []
+                for st, r, mv in zip(part, res, lists):
+                    if (int(r) & 3) != RESULT_ONGOING:
+                        ended += 1
+                        continue
+                    parents += [st] * len(mv)
+                    moves += [int(m) for m in mv]
+                for lo2 in range(0, len(parents), self.max_games):
+                    ids2 = list(range(min(self.max_games, len(parents) - lo2)))
+                    self.upload(ids2, parents[lo2:lo2 + len(ids2)])
+                    assert not self.play(ids2, moves[lo2:lo2 + len(ids2)]).any()
+                    nxt += self.download(ids2)
+            level = nxt
+        return level, ended
+
     def perft_stats(self):
         ms, mat, launches = C.c_double(), C.c_uint64(), C.c_uint64()
         check(self.lib.tak_perft_stats(self._h, C.byref(ms), C.byref(mat), C.byref(launches)))

@@ -26,6 +26,28 @@ def test_perft_known_answers(golden):
             assert game.perft(depth) == expect, (case["name"], depth)
 
 
+def test_perft_multi_shares_a_frontier(golden):
+    """tak_perft_multi (multi-GPU perft): perft(root, d) == lines that ended above the cut +
+    sum over ranks of perft_multi(every world-th position of the depth-k frontier, d - k) -- on the reference's
+    positional cases (endgame_perft ends lines early) and on the openings."""
+    eng = tb.Engine(5, 4096, nodes_per_game=64)
+    eng6 = tb.Engine(6, 2048, nodes_per_game=64)
+    for case in golden["perft"]:
+        e = eng if case["n"] == 5 else eng6
+        game = tb.Game.from_ptn_moves(case["n"], case["moves"])
+        depth, expect = max((d, x) for d, x in case["expect"] if x < 5_000_000)
+        for cut in (1, 2):
+            if cut > depth:
+                continue
+            front, ended = e.frontier(game.state(), cut)
+            for world in (1, 3):
+                total = ended + sum(e.perft_multi(front[r::world], depth - cut) for r in range(world))
+                assert total == expect, (case["name"], depth, cut, world)
+    assert eng.perft_multi([], 3) == 0
+    eng.close()
+    eng6.close()
+
+
 def test_perft_6x6_depth5():
     # the value the reference keeps commented out (perft.rs:98)
     assert tb.Game.default(6).perft(5) == 1_253_506_520
