@@ -224,7 +224,9 @@ def movegen_mnodes(eng, world, rank, dev, pk):
     algo_bytes = mat_total * (3 * S + 2)
     gbs = algo_bytes / (t_max * 1e-3) / 1e9 if t_max else 0.0
     return {"value": total / (t_max * 1e-3) / 1e6 if t_max else None, "unit": "Mnodes/s",
-            "workload": "6x6 perft depth 5 from the opening via tak_perft (movegen + play + result, bit-exact count)",
+            "workload": "6x6 perft depth 5 from the opening via tak_perft (movegen + play + result, bit-exact count)"
+                        + ("" if world == 1 else f"; the 1260 positions two plies down are dealt round-robin over {world} ranks "
+                           "(that shallow frontier is built on the host, untimed), each rank's share is one tak_perft_multi"),
             "nodes": total, "exact": total == PERFT6_D5, "ms": t_max, "materialised_states": int(mat_total),
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s",
                          "frac": gbs / pk["hbm"] if pk["hbm"] else None,
@@ -535,10 +537,17 @@ def main():
     ap.add_argument("--rollouts", type=int, default=800)
     ap.add_argument("--nodes-per-game", type=int, default=1 << 18)
     args = ap.parse_args()
+    # Native libraries may write to fd 1 (NCCL prints its version banner there when NCCL_DEBUG is set): everything but the
+    # ONE JSON line goes to stderr.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w", buffering=1)
     if args.impl == "reference":
         run_reference(args)
     else:
         run_b200(args)
+    sys.stdout.flush()
 
 
 if __name__ == "__main__":
