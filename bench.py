@@ -267,7 +267,7 @@ def augment_rate(eng, recs, dev, pk):
             "hbm_write_gbs": out_bytes / dt / 1e9, "hbm_peak_gbs": pk["hbm"]}, (inputs, pi, z)
 
 
-def train_rate(eng, tensors, world, dist, dev, pk):
+def train_rate(eng, tensors, world, dist, dev, pk, host_recs=None):
     """Network::train_inner + Adam (next row N1, network.rs:37-97) on the augmented examples of this run: chunks of
     500 examples x 8 symmetries = 4000 positions (CHUNK_SIZE, network.rs:19), inputs resident in HBM; with N ranks every
     rank trains its own chunks and the fp32 gradient blob is all-reduced over NCCL before the Adam step."""
@@ -287,6 +287,22 @@ def train_rate(eng, tensors, world, dist, dev, pk):
     for _ in range(chunks):
         loss = eng.train_chunk(x, p, zz)
         ms.append(eng.train_stats()["ms_last_chunk"])
+    # end to end through the public API with HOST examples: replay records -> examples_to_tensors (H2D + 8 symmetries
+    # on the device) -> train_chunk -> losses back on the host, wall clock
+    e2e = None
+    if host_recs and len(host_recs) * 8 >= B:
+        recs = host_recs[:B // 8]
+        eng.train_chunk(*eng.examples_to_tensors(recs, on_device=True))
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        reps = 3
+        for _ in range(reps):
+            eng.train_chunk(*eng.examples_to_tensors(recs, on_device=True))
+        torch.cuda.synchronize()
+        dt = par_max((time.perf_counter() - t0) / reps, dev)
+        e2e = {"value": world * B / dt, "unit": "positions/s", "ms_per_chunk": 1e3 * dt,
+               "h2d_bytes_per_step": len(recs) * C.sizeof(type(recs[0])), "d2h_bytes_per_step": 8,
+               "what": "host replay records -> examples_to_tensors(on_device) -> net_train_chunk -> (loss_p, loss_z)"}
     g = eng.train_grad_tensor()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -304,7 +320,7 @@ def train_rate(eng, tensors, world, dist, dev, pk):
            "ms_per_chunk": ms_max, "allreduce_ms": 1e3 * t_ar, "adam_step_ms": 1e3 * t_step,
            "grad_bytes": int(W.blob_size(6)) * 4, "loss_p": loss[0], "loss_z": loss[1],
            "tflops": flop / (ms_max * 1e-3) / 1e12, "tensor_peak": pk["bf16_sustained"],
-           "frac_of_tensor_peak": flop / (ms_max * 1e-3) / 1e12 / pk["bf16_sustained"],
+           "frac_of_tensor_peak": flop / (ms_max * 1e-3) / 1e12 / pk["bf16_sustained"], "e2e": e2e,
            "what": "train_inner on 4000 augmented positions (forward_training + loss + backward, CUDA events on the engine "
                    "stream), then NCCL all-reduce of the gradient blob and the Adam step"}
     eng.train_end()
@@ -482,7 +498,7 @@ def run_b200(args):
     augment, aug_tensors = augment_rate(engines[0], aug_recs, dev, pk)
 
     # ---------------- training step (next row N1): train_inner + all-reduce + Adam on those examples -----------------
-    train = train_rate(engines[0], aug_tensors, world, dist, dev, pk) if aug_tensors is not None else None
+    train = train_rate(engines[0], aug_tensors, world, dist, dev, pk, aug_recs) if aug_tensors is not None else None
 
     line = None
     if rank == 0:

@@ -385,6 +385,14 @@ static __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc3_kernel(const
                         tmem_ld32(taddr + cc * 32, x);   // 8 epilogue warps hide each other's TMEM latency
                         if (has_res && cc < 3) load_res(cc + 1, res[(cc + 1) & 1]);
                         tmem_ld_wait();
+                        if (cc == 3) {
+                            // the accumulator is in registers now: hand it back to the MMA issuer BEFORE the stores of
+                            // this tile are issued and made visible (the fence below waits for them; in a one-layer
+                            // launch with outputs going to HBM that wait used to sit on the tensor pipe's critical path)
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(BAR(C3B_ACC_EMPTY + as));
+                        }
                         if (mode == CONV_LOGITS_F32) {
                             // logits straight from the un-transposed registers: one channel, 32 consecutive slots
                             const int ch = 32 * q + lane;
@@ -487,14 +495,11 @@ static __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc3_kernel(const
                             }
                         }
                     }
-                    tc_fence_before();
-                    // the stores above are read back by the bulk-copy engine (async proxy) for the next layer
-                    asm volatile("fence.proxy.async;" ::: "memory");
+                    // the stores above are read back by the bulk-copy engine (async proxy) when a later layer of THIS
+                    // launch consumes them; the last layer's outputs are published by kernel completion
+                    if (L + 1 < p.n_layers) asm volatile("fence.proxy.async;" ::: "memory");
                     __syncwarp();
-                    if (lane == 0) {
-                        mbar_arrive(BAR(C3B_ACC_EMPTY + as));
-                        mbar_arrive(BAR(C3B_READY + jj));
-                    }
+                    if (lane == 0) mbar_arrive(BAR(C3B_READY + jj));
                 }
             }
         }
