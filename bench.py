@@ -267,6 +267,42 @@ def augment_rate(eng, recs, dev, pk):
             "hbm_write_gbs": out_bytes / dt / 1e9, "hbm_peak_gbs": pk["hbm"]}, (inputs, pi, z)
 
 
+def interactive_rates(local, blob_ptr, elems, states):
+    """The `analysis` / `playtak` / `pit` regime (one game, small batches): latency of Network::policy_eval through the
+    host-buffer ABI (alpha-tak/src/model/network.rs:34) and the rollouts/s of a single `Player` with batch 32
+    (analysis/src/main.rs prints the same figure as nps)."""
+    import tak_b200 as tb
+
+    # a search of one game for a second grows a tree of millions of nodes: its own engine with a deep node pool
+    eng = tb.Engine(6, 2, device=local, nodes_per_game=1 << 23, max_batch=256)
+    eng.net_create(6)
+    eng.net_load_weights_device(blob_ptr, elems)
+    out = {"policy_eval_ms": {}, "what": "net_policy_eval(host states -> full softmax [b, 9036] + value on the host), "
+                                         "median of 20 calls; Player(batch 32).rollout() on one game for 1 s"}
+    for b in (1, 32, 256):
+        st = states[:b]
+        eng.policy_eval(st)
+        ts = []
+        for _ in range(20):
+            t0 = time.perf_counter()
+            eng.policy_eval(st)
+            ts.append(time.perf_counter() - t0)
+        out["policy_eval_ms"][str(b)] = 1e3 * float(np.median(ts))
+    gid, batch = 0, 32
+    eng.reset(gid, 1, 4)
+    pl = tb.Player(eng, gid, batch)
+    for _ in range(5):
+        pl.rollout()
+    t0, n = time.perf_counter(), 0
+    while time.perf_counter() - t0 < 1.0 and n * batch < 60_000:
+        pl.rollout()
+        n += 1
+    out["player_nps"] = n * batch / (time.perf_counter() - t0)
+    out["player_batch"] = batch
+    eng.close()
+    return out
+
+
 def train_rate(eng, tensors, world, dist, dev, pk, host_recs=None):
     """Network::train_inner + Adam (next row N1, network.rs:37-97) on the augmented examples of this run: chunks of
     500 examples x 8 symmetries = 4000 positions (CHUNK_SIZE, network.rs:19), inputs resident in HBM; with N ranks every
@@ -497,6 +533,9 @@ def run_b200(args):
         aug_recs.append(r)
     augment, aug_tensors = augment_rate(engines[0], aug_recs, dev, pk)
 
+    # ---------------- small-batch regime of the analysis / playtak / pit callers (rank 0's first replica) ---------------
+    interactive = interactive_rates(local, blob_dev.data_ptr(), elems, host_states[0]) if rank == 0 else None
+
     # ---------------- training step (next row N1): train_inner + all-reduce + Adam on those examples -----------------
     train = train_rate(engines[0], aug_tensors, world, dist, dev, pk, aug_recs) if aug_tensors is not None else None
 
@@ -525,6 +564,7 @@ def run_b200(args):
             "movegen": movegen,
             "augment": augment,
             "train": train,
+            "interactive": interactive,
             "cpu_baseline": {"value": cpu["value"], "unit": UNIT, "cores": cpu["cores"], "kind": "port",
                              "sample": cpu["sample"]} if cpu else None,
             "clocks": clocks,
