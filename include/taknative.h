@@ -208,6 +208,10 @@ int32_t mcts_devirtualize_with(tak_engine_t* e, const float* policy, const float
  * mcts.rs:67-91) and leaves the newer ones -- and every other game's queue -- untouched. */
 int32_t mcts_reserve_pending(tak_engine_t* e, int32_t k);
 int32_t mcts_devirtualize_first(tak_engine_t* e, const int32_t* ids, int32_t n, const int32_t* counts);
+/* Player::rollout x reps for every listed game, fused (player.rs:130-133): each repetition queues a new batch of `batch`
+ * virtual rollouts per game and then evaluates + backs up the batch that was already outstanding -- with no host round
+ * trip in between (the interactive analysis / playtak / pit regime). */
+int32_t mcts_player_rollouts(tak_engine_t* e, const int32_t* ids, int32_t n, int32_t batch, int32_t reps);
 int32_t mcts_rollouts(tak_engine_t* e, const int32_t* ids, int32_t n, int32_t n_rollouts);
 int32_t mcts_children(tak_engine_t* e, int32_t id, uint16_t* out_moves, uint32_t* out_visits, float* out_priors,
                       float* out_rewards, int32_t cap, int32_t* out_count);

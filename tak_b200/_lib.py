@@ -149,6 +149,7 @@ SYMBOLS = {
     "mcts_devirtualize": (_i32, [_vp]),
     "mcts_devirtualize_with": (_i32, [_vp, _P(_f32), _P(_f32), _i32]),
     "mcts_rollouts": (_i32, [_vp, _P(_i32), _i32, _i32]),
+    "mcts_player_rollouts": (_i32, [_vp, _P(_i32), _i32, _i32, _i32]),
     "mcts_children": (_i32, [_vp, _i32, _P(_u16), _P(C.c_uint32), _P(_f32), _P(_f32), _i32, _P(_i32)]),
     "mcts_children_batch": (_i32, [_vp, _P(_i32), _i32, _P(_u16), _P(C.c_uint32), _P(_i32), _i32]),
     "mcts_root": (_i32, [_vp, _i32, _P(C.c_uint32), _P(C.c_uint32), _P(_f32)]),

@@ -334,6 +334,33 @@ int32_t mcts_devirtualize_first(tak_engine_t* e, const int32_t* ids, int32_t n, 
     return mcts_check_errors(e);
 }
 
+int32_t mcts_player_rollouts(tak_engine_t* e, const int32_t* ids, int32_t n, int32_t batch, int32_t reps) {
+    TB_CHECK(e && ids && n >= 0 && batch >= 1 && batch <= 4096 && reps >= 0, TAK_ERR_BAD_ARG,
+             "mcts_player_rollouts: bad argument");
+    TB_CUDA(cudaSetDevice(e->device));
+    if (int r = mcts_ensure(e, 2 * batch)) return r;
+    if (n == 0 || reps == 0) return TAK_OK;
+    MctsState& m = *e->mcts;
+    const int* d_ids = nullptr;
+    if (int r = upload_ids(e, ids, n, &d_ids)) return r;
+    TB_CUDA(m.limits.ensure(size_t(e->max_games) * 4));
+    int r = TAK_OK;
+    for (int rep = 0; rep < reps && r == TAK_OK; ++rep) {
+        // request_batch: the new batch is selected on trees that still carry the virtual visits of the outstanding one
+        TB_CUDA(cudaMemsetAsync(m.limits.p, 0, size_t(e->max_games) * 4, e->stream));
+        k_mcts_snapshot_limits<<<(n + 127) / 128, 128, 0, e->stream>>>(m.pend_cnt.as<int>(), d_ids, n, m.limits.as<int>());
+        e->launches++;
+        r = mcts_launch_rollout(e, d_ids, n, batch);
+        if (r) break;
+        // consume_batch: evaluate and back up the OLDER batch only
+        m.limits_on = true;
+        r = mcts_eval_and_backup(e);
+        m.limits_on = false;
+    }
+    if (r) return r;
+    return mcts_check_errors(e);
+}
+
 int32_t mcts_devirtualize_with(tak_engine_t* e, const float* policy, const float* value, int32_t count) {
     TB_CHECK(e && policy && value && count >= 0, TAK_ERR_BAD_ARG, "mcts_devirtualize_with: bad argument");
     TB_CUDA(cudaSetDevice(e->device));

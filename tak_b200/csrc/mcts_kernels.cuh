@@ -531,6 +531,14 @@ static __global__ void __launch_bounds__(GAME_THREADS)
     }
 }
 
+// Player::rollout (player.rs:130-133) keeps ONE batch in flight: limits[g] = leaves game g has queued right now, i.e. the
+// batch requested by the previous call -- exactly what the consume half of this call must back up after the new batch
+// has been selected.  (limits[] is zeroed first: games not listed keep their queues untouched.)
+static __global__ void k_mcts_snapshot_limits(const int* pend_cnt, const int* ids, int n, int* limits) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) limits[ids[i]] = pend_cnt[ids[i]];
+}
+
 // Node::debug / Node::continuation (search/debug.rs:9-40): one warp per root child.  The record carries the child's
 // (move, visits, expected_reward, policy) and its principal continuation: from the child, repeatedly the child with the
 // most visits (pick_move(true): LAST maximum, play.rs:49-58) until `depth` moves or a childless node.

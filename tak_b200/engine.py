@@ -329,6 +329,11 @@ class Engine:
         check(self.lib.mcts_devirtualize_with(self._h, policy.ctypes.data_as(C.POINTER(C.c_float)),
                                               value.ctypes.data_as(C.POINTER(C.c_float)), value.size))
 
+    def player_rollouts(self, ids, batch: int, reps: int = 1):
+        """Player::rollout x reps, fused: queue a new batch per game, then back up the batch already outstanding."""
+        p, k, _keep = _ids(ids)
+        check(self.lib.mcts_player_rollouts(self._h, p, k, batch, reps))
+
     def rollouts(self, ids, n_rollouts: int):
         p, k, _keep = _ids(ids)
         check(self.lib.mcts_rollouts(self._h, p, k, n_rollouts))
@@ -579,7 +584,6 @@ class Player:
         self.engine, self.gid, self.batch, self.save_examples = engine, gid, batch, save_examples
         self.create_analysis = create_analysis
         self.examples: List[Tuple[TakState, List[Tuple[int, int]]]] = []
-        self._outstanding: List[int] = []
         engine.reserve_pending(2 * batch)
         if state is not None:
             engine.upload([gid], [state])
@@ -588,21 +592,16 @@ class Player:
         self.analysis = Analysis(engine.n, int(st.half_komi), int(st.ply))   # player.rs:58
         self._request_batch()                      # player.rs:66-67
 
-    def _queued(self) -> int:
-        gids, _ = self.engine.pending(with_states=False)
-        return int((gids == self.gid).sum())
-
+    # Exactly one batch is outstanding between calls (every method below ends with a request), so "consume" is: back up
+    # every leaf this game has queued.
     def _request_batch(self):                      # player.rs:98-100 (+ the rollout thread, :71-96)
-        before = self._queued()
-        self.engine.virtual_rollout([self.gid], self.batch)
-        self._outstanding.append(self._queued() - before)   # terminal leaves need no evaluation (:83-87)
+        self.engine.virtual_rollout([self.gid], self.batch)   # terminal leaves need no evaluation (:83-87)
 
     def _consume_batch(self):                      # player.rs:102-110
-        self.engine.devirtualize_first([self.gid], [self._outstanding.pop(0)])
+        self.engine.devirtualize_first([self.gid], [1 << 30])
 
-    def rollout(self):                             # player.rs:130-133
-        self._request_batch()
-        self._consume_batch()
+    def rollout(self, reps: int = 1):              # player.rs:130-133, `reps` calls fused into one ABI call
+        self.engine.player_rollouts([self.gid], self.batch, reps)
 
     def add_noise(self, alpha: float, ratio: float, seed: int = 0):   # player.rs:123-127
         self._consume_batch()

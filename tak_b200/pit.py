@@ -29,31 +29,22 @@ class PlayerBatch:
     def __init__(self, engine: Engine, gids: Sequence[int], batch: int):
         self.engine, self.batch = engine, batch
         self.gids = [int(g) for g in gids]
-        self.outstanding = {g: [] for g in self.gids}     # per game: sizes of the batches still queued (oldest first)
         engine.reserve_pending(2 * batch)
         engine.tree_reset(self.gids)
         self.request(self.gids)                           # player.rs:66-67
 
-    def _queued(self) -> np.ndarray:
-        gids, _ = self.engine.pending(with_states=False)
-        return np.bincount(gids, minlength=self.engine.max_games)
-
+    # exactly one batch per game is outstanding between calls, so "consume" = back up everything the game has queued
     def request(self, gids: Sequence[int]):               # player.rs:98-100 + the rollout thread (:71-96)
-        if not len(gids):
-            return
-        before = self._queued()
-        self.engine.virtual_rollout(gids, self.batch)
-        after = self._queued()
-        for g in gids:                                    # terminal leaves need no evaluation (:83-87)
-            self.outstanding[g].append(int(after[g] - before[g]))
+        if len(gids):
+            self.engine.virtual_rollout(gids, self.batch)
 
     def consume(self, gids: Sequence[int]):               # player.rs:102-110
         if len(gids):
-            self.engine.devirtualize_first(gids, [self.outstanding[g].pop(0) for g in gids])
+            self.engine.devirtualize_first(gids, [1 << 30] * len(gids))
 
-    def rollout(self, gids: Sequence[int]):               # player.rs:130-133
-        self.request(gids)
-        self.consume(gids)
+    def rollout(self, gids: Sequence[int], reps: int = 1):   # player.rs:130-133 (x reps, fused into one ABI call)
+        if len(gids):
+            self.engine.player_rollouts(gids, self.batch, reps)
 
     def pick_move(self, gids: Sequence[int]) -> np.ndarray:   # player.rs:136-138, exploitation = true
         return self.engine.pick_move(gids)
@@ -142,8 +133,7 @@ def pit(new: Engine, old: Engine, games: int = PIT_GAMES, batch: int = BATCH_SIZ
         picks = {}
         for k in (0, 1):                                  # the player to move searches (pit.rs:71-83)
             if side[k]:
-                for _r in range(rollouts):
-                    players[k].rollout(side[k])
+                players[k].rollout(side[k], rollouts)
                 for g, m in zip(side[k], players[k].pick_move(side[k])):
                     picks[g] = int(m)
         mv = [picks[g] for g in live]
