@@ -421,6 +421,10 @@ def run_b200(args):
     def sum_over_ranks(x: float) -> float:
         return par.sum_over_ranks(x, dev)
 
+    # the conv tower timed ALONE on a cool GPU (3 launches, CUDA events) -> compared with the burst peak below
+    engines[0].reset(0, Gr, 4)
+    prof_alone = engines[0].net_forward_profile(0, Gr, 3)
+
     # ---------------- device-resident self-play: `value` ----------------
     for r, eng in enumerate(engines):
         eng.selfplay_begin(rollouts=R, half_komi=4, instant_win=1, exploit_ply=40, noise_ply=80, noise_alpha=0.2,
@@ -502,19 +506,28 @@ def run_b200(args):
     e2e_value = world * G * e2e_steps / e2e_t
 
     # ---------------- roofline of the dominant kernel (conv3x3_tc3_kernel = the whole conv tower), measured live -------
+    # Timed right after the self-play steps, 10 launches back to back on the hot, power-capped GPU: the conditions of the
+    # timed region (per-launch events INSIDE the region would also count the other replica's kernels sharing the SMs), so
+    # the denominator is the SUSTAINED peak; the same kernel timed alone before the run goes against the BURST peak.
     prof = engines[0].net_forward_profile(0, Gr, 10)
-    conv_flop = prof["flop"] - Gr * (2.0 * 128 * 36)  # all but the value FC runs in the conv kernel
+    value_fc_flop = Gr * (2.0 * 128 * 36)            # all but the value FC runs in the conv kernel
+    conv_flop = prof["flop"] - value_fc_flop
     achieved = conv_flop / (prof["ms_conv"] * 1e-3) / 1e12
+    alone = (prof_alone["flop"] - value_fc_flop) / (prof_alone["ms_conv"] * 1e-3) / 1e12
     roofline = {
-        "bound": "tensor", "kernel": "conv3x3_tc3_kernel", "achieved": achieved, "peak": pk["bf16_burst"],
-        "unit": "TFLOP/s", "frac": achieved / pk["bf16_burst"],
+        "bound": "tensor", "kernel": "conv3x3_tc3_kernel", "achieved": achieved, "peak": pk["bf16_sustained"],
+        "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"],
         # dram__bytes_read.sum + dram__bytes_write.sum of one tower launch over 5328 boards (ncu --set full,
         # profiles/r01_conv_tc3_ncu_full.txt), scaled to this launch's boards: logits + write-backs of the activations
-        "traffic": 1_799_644_848 * Gr / 5328,
-        "peak_kind": "burst bf16 (kernel timed alone, CUDA events around each launch), " + pk["source"],
+        "traffic": 1_804_369_024 * Gr / 5328,
+        "peak_kind": "sustained bf16 (kernel timed in a back-to-back loop under the step's power cap, CUDA events around "
+                     "each launch), " + pk["source"],
         "avg_launch_us": 1e3 * prof["ms_conv"] / prof["conv_launches"],
         "algorithmic_flop_per_launch": conv_flop / prof["conv_launches"],
         "boards_per_launch": Gr,
+        "alone": {"achieved": alone, "peak": pk["bf16_burst"], "frac": alone / pk["bf16_burst"],
+                  "avg_launch_us": 1e3 * prof_alone["ms_conv"] / prof_alone["conv_launches"],
+                  "peak_kind": "burst bf16: the same launch timed alone on the cool GPU before the run"},
         "step_frac_sustained": (value / world) * R * FLOP_PER_EVAL_NET6 / (pk["bf16_sustained"] * 1e12),
         "forward_ms": prof["ms_forward"], "conv_share_of_forward": prof["ms_conv"] / prof["ms_forward"],
     }

@@ -350,6 +350,9 @@ static __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc3_kernel(const
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
                             dst[i] = make_uint4(0, 0, 0, 0);
+#if defined(CONV_EXP) && (CONV_EXP & 32)
+                            if (p.S == -7)                            // experiment: no residual loads
+#endif
                             if ((valid_mask >> (cc * 4 + i)) & 1)
                                 dst[i] = *reinterpret_cast<const uint4*>(
                                     ld.res + (static_cast<size_t>(chunk) * p.S + slot0 + 32 * cc + 8 * i) * 8);
@@ -415,9 +418,11 @@ static __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc3_kernel(const
                         }
                         // 8x8 block transpose across the 8 lanes of a channel chunk: x[8i+b] (channel j, slot 8i+b) ->
                         // x[8i+b] (channel b, slot 8i+j)
+#if !(defined(CONV_EXP) && (CONV_EXP & 16))
                         transpose8_stage<4>(x, j);
                         transpose8_stage<2>(x, j);
                         transpose8_stage<1>(x, j);
+#endif
                         if (mode == CONV_LOGITS_F32) {
                             // per-slot softmax partial over this warp's 32 channels: 8 in-thread, then the 4 lane groups
 #pragma unroll
@@ -472,6 +477,9 @@ static __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc3_kernel(const
                                         }
                                     }
                                 }
+#if defined(CONV_EXP) && (CONV_EXP & 8)
+                                if (ov.x == 0x12345678u && p.S == -7)   // experiment: no output stores
+#endif
                                 *reinterpret_cast<uint4*>(ld.out + (static_cast<size_t>(chunk) * p.S + slot0 + 32 * cc + 8 * i) * 8) = ov;
                             }
                         }

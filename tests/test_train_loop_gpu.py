@@ -46,6 +46,7 @@ def test_training_loop_iteration():
     losses = TL.train_network.last_losses
     assert all(np.isfinite(l).all() for l in losses)
     first, last = np.mean([sum(l) for l in losses[:3]]), np.mean([sum(l) for l in losses[-3:]])
+    print("\ntraining loss, first / last 3 chunks:", first, last)
     assert last < first, (first, last)                    # the steps taken reduce the training loss
     accepted = res.win_rate() > TL.WIN_RATE_THRESHOLD
     assert np.array_equal(blob2, blob1) != accepted
