@@ -340,6 +340,8 @@ def train_rate(eng, tensors, world, dist, dev, pk, host_recs=None):
                "h2d_bytes_per_step": len(recs) * C.sizeof(type(recs[0])), "d2h_bytes_per_step": 8,
                "what": "host replay records -> examples_to_tensors(on_device) -> net_train_chunk -> (loss_p, loss_z)"}
     g = eng.train_grad_tensor()
+    if dist:                                  # untimed: NCCL builds its rings / buffers for this size on first use
+        par_mod.allreduce_gradients(torch.zeros_like(g))
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     if dist:
