@@ -86,3 +86,136 @@ def random_weights(arch: int, seed: int = 0, trained_like: bool = True) -> np.nd
             raise AssertionError(name)
         parts.append(v.astype(np.float32))
     return np.concatenate(parts)
+
+
+# ---- tch-rs `.model` files: Network::save / Network::load (net6.rs:87-96, net5.rs:95-104) -----------
+# `VarStore::save` hands every variable to libtorch's `torch::serialize::OutputArchive` (tch 0.7.2 torch_api.cpp
+# `at_save_multi`), i.e. the file is a TorchScript module archive whose PARAMETERS are the variables.  All layers of Net5 /
+# Net6 are built on `vs.root()`, so the names are just `weight`, `bias`, `running_mean`, `running_var`; a name that is
+# already taken gets the suffix `__<number of variables created so far>` (tch `Path::add`) -- which is what lets the
+# creation order be recovered although the file itself is written in HashMap order.  The loader only relies on: that
+# suffix rule, the layer creation order of net6.rs:39-57 / net5.rs:39-62, and base names within a layer (it does NOT
+# assume whether a conv creates its bias before its weight, or a BatchNorm its running statistics before gamma / beta).
+# No `.model` file ships with the reference, so this is parity-unpinned against a real tch file;
+# tests/test_weights_cpu.py round-trips through `save_tch_model` under every ordering convention.
+_BASES = ("weight", "bias", "running_mean", "running_var")
+
+
+def _creation_order(names):
+    """{name: creation index} from tch's de-duplication suffixes."""
+    idx, plain = {}, []
+    for nm in names:
+        base, sep, suffix = nm.rpartition("__")
+        if sep and base in _BASES and suffix.isdigit():
+            idx[nm] = int(suffix)
+        elif nm in _BASES:
+            plain.append(nm)
+        else:
+            raise ValueError(f"unexpected variable name {nm!r} in a Net5/Net6 VarStore")
+    free = sorted(set(range(len(names))) - set(idx.values()))
+    if len(free) != len(plain) or len(set(idx.values())) != len(idx):
+        raise ValueError("variable names do not follow tch's `name__<count>` de-duplication rule")
+    # first use of each name: the conv's two variables come before the BatchNorm's running statistics
+    first_use = [n for n in ("weight", "bias") if n in plain] + [n for n in ("running_mean", "running_var") if n in plain]
+    if len(first_use) != len(plain):
+        raise ValueError("duplicate unsuffixed variable names")
+    wb = sorted(n for n in first_use if n in ("weight", "bias"))
+    # `weight` / `bias` share the first conv (either order), the running statistics follow in mean, var order
+    for nm, i in zip(wb + [n for n in first_use if n.startswith("running")], free):
+        idx[nm] = i
+    return idx
+
+
+def blob_from_named_tensors(named: dict, arch: int) -> np.ndarray:
+    """The weight blob (`spec(arch)` order) from {tch variable name: array}."""
+    order = _creation_order(list(named))
+    seq = sorted(named, key=lambda nm: order[nm])
+    base_of = lambda nm: nm.rpartition("__")[0] if "__" in nm else nm
+    pos, parts = 0, {}
+
+    def take(k, want):
+        nonlocal pos
+        grp = {base_of(nm): np.asarray(named[nm], dtype=np.float32) for nm in seq[pos:pos + k]}
+        if sorted(grp) != sorted(want):
+            raise ValueError(f"layer {pos}: expected variables {want}, file has {sorted(grp)}")
+        pos += k
+        return grp
+
+    sp = spec(arch)
+    i = 0
+    while i < len(sp):
+        name, shape = sp[i]
+        layer = name.rsplit(".", 1)[0]
+        if ".bn" in name or name.startswith("initial_bn"):
+            grp = take(4, _BASES)
+            for k in _BASES:
+                parts[f"{layer}.{k}"] = grp[k]
+            i += 4
+        else:
+            grp = take(2, ("weight", "bias"))
+            parts[f"{layer}.weight"], parts[f"{layer}.bias"] = grp["weight"], grp["bias"]
+            i += 2
+    if pos != len(seq):
+        raise ValueError(f"{len(seq) - pos} variables left over: not a Net{arch} VarStore")
+    out = []
+    for name, shape in sp:
+        a = parts[name]
+        if tuple(a.shape) != tuple(shape):
+            raise ValueError(f"{name}: shape {tuple(a.shape)} in the file, Net{arch} needs {tuple(shape)}")
+        out.append(a.reshape(-1))
+    return np.concatenate(out).astype(np.float32)
+
+
+def load_tch_model(path: str, arch: int) -> np.ndarray:
+    """`Network::load(path)` -> the fp32 weight blob `net_load_weights` takes."""
+    import torch
+    mod = torch.jit.load(path, map_location="cpu")
+    named = {n: p.detach().float().numpy() for n, p in mod.named_parameters()}
+    named.update({n: b.detach().float().numpy() for n, b in mod.named_buffers()})
+    return blob_from_named_tensors(named, arch)
+
+
+def tch_variable_names(arch: int, conv_bias_first: bool = True, bn_stats_first: bool = True):
+    """[(tch variable name, blob tensor name)] in creation order, as `Net5/Net6::default()` would register them."""
+    out, used = [], set()
+
+    def add(base, blob_name):
+        nm = base if base not in used else f"{base}__{len(out)}"
+        used.add(base)
+        out.append((nm, blob_name))
+
+    sp = [name for name, _ in spec(arch)]
+    i = 0
+    while i < len(sp):
+        layer = sp[i].rsplit(".", 1)[0]
+        if ".bn" in sp[i] or sp[i].startswith("initial_bn"):
+            seq = ("running_mean", "running_var", "weight", "bias") if bn_stats_first else _BASES
+            for b in seq:
+                add(b, f"{layer}.{b}")
+            i += 4
+        else:
+            for b in (("bias", "weight") if conv_bias_first else ("weight", "bias")):
+                add(b, f"{layer}.{b}")
+            i += 2
+    return out
+
+
+def save_tch_model(blob: np.ndarray, arch: int, path: str, conv_bias_first: bool = True, bn_stats_first: bool = True,
+                   shuffle_seed: int = 0) -> None:
+    """`Network::save(path)`: the blob as a TorchScript parameter archive with tch's variable names, written in an
+    arbitrary (seeded) order like the HashMap iteration of `VarStore::save`."""
+    import torch
+    tensors = split(np.asarray(blob, dtype=np.float32), arch)
+    names = tch_variable_names(arch, conv_bias_first, bn_stats_first)
+    order = np.random.default_rng(shuffle_seed).permutation(len(names))
+
+    class VarStore(torch.nn.Module):
+        pass
+
+    m = VarStore()
+    for k in order:
+        nm, blob_name = names[k]
+        trainable = "running_" not in nm
+        m.register_parameter(nm, torch.nn.Parameter(torch.from_numpy(np.ascontiguousarray(tensors[blob_name])).clone(),
+                                                    requires_grad=trainable))
+    torch.jit.script(m).save(path)
