@@ -6,8 +6,9 @@
 `train_network` is `Network::train` (fresh Adam, shuffled references, chunks_exact(CHUNK_SIZE), a step every
 CHUNKS_IN_STEP chunks -- gradients of a trailing partial group are dropped, as in the reference); `training_iteration` is
 one turn of `training_loop`.  Everything heavy runs behind the C ABI (self-play, augmentation, train_inner, Adam, pit);
-this file is the cold control flow.  File output of the reference (`_models/*.model`, `_examples/*.data`) is reduced to
-`save_examples` (same text format, example.rs:81-100) and the weight blob as .npy.
+this file is the cold control flow.  With `save_dir` the reference's files are written too: `_models/<time>.model` (tch
+VarStore archive, weights.save_tch_model) when a candidate is accepted and `_examples/<time>.data` (one Example per line,
+example.rs:81-100) after every self-play round.
 """
 from __future__ import annotations
 
@@ -77,7 +78,7 @@ def save_examples(path: str, examples: Sequence[ReplayRecord]) -> None:
 def training_iteration(current: Engine, candidate: Engine, blob: np.ndarray, examples: List[ReplayRecord],
                        rng: np.random.Generator, pit_games: int = 128, pit_rollouts: int = 50, pit_batch: int = 16,
                        min_new_examples: int = 1000, train_kw: Optional[dict] = None,
-                       selfplay_kw: Optional[dict] = None, log: Callable = print):
+                       selfplay_kw: Optional[dict] = None, log: Callable = print, save_dir: Optional[str] = None):
     """One turn of `training_loop` (train/src/main.rs:82-123).  `current` holds the accepted network (weights `blob`),
     `candidate` is a second engine for the copy being trained and pitted.  Returns (blob, examples, PitResult | None)."""
     result: Optional[PitResult] = None
@@ -93,8 +94,21 @@ def training_iteration(current: Engine, candidate: Engine, blob: np.ndarray, exa
             blob = new_blob
             current.net_load_weights(blob)
             log("saving model")
+            if save_dir:                                  # network.save("_models/<unix time>.model") (main.rs:104)
+                import os
+                import time
+
+                from . import weights as W
+                os.makedirs(os.path.join(save_dir, "_models"), exist_ok=True)
+                W.save_tch_model(blob, current.n, os.path.join(save_dir, "_models", f"{int(time.time())}.model"))
         if len(examples) > MAX_EXAMPLES:
             examples = examples[-MAX_EXAMPLES:]
     log("starting self-play")
-    examples = list(examples) + collect_self_play(current, min_new_examples, **(selfplay_kw or {}))
+    new_examples = collect_self_play(current, min_new_examples, **(selfplay_kw or {}))
+    if save_dir:                                          # "_examples/<unix time>.data" (self_play.rs:98,253-255)
+        import os
+        import time
+        os.makedirs(os.path.join(save_dir, "_examples"), exist_ok=True)
+        save_examples(os.path.join(save_dir, "_examples", f"{int(time.time())}.data"), new_examples)
+    examples = list(examples) + new_examples
     return blob, examples, result

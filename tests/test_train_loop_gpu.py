@@ -11,7 +11,7 @@ from tak_b200 import weights as W
 pytestmark = pytest.mark.gpu
 
 
-def test_training_loop_iteration():
+def test_training_loop_iteration(tmp_path):
     G = 64
     blob = W.random_weights(6, seed=5)
     cur = tb.Engine(6, G, nodes_per_game=1 << 12, max_batch=G)
@@ -24,7 +24,13 @@ def test_training_loop_iteration():
     rng = np.random.default_rng(0)
     # first turn: no examples yet -> self-play only
     blob1, examples, res = TL.training_iteration(cur, cand, blob, [], rng, min_new_examples=200, selfplay_kw=sp,
-                                                 log=lines.append)
+                                                 log=lines.append, save_dir=str(tmp_path))
+    import os
+    data = [f for f in os.listdir(tmp_path / "_examples") if f.endswith(".data")]
+    assert len(data) == 1
+    with open(tmp_path / "_examples" / data[0]) as f:
+        text = f.read().split("\n")
+    assert len(text) - 1 == len(examples) and tb.example_parse(text[0], 6).n_children == examples[0].n_children
     assert res is None and np.array_equal(blob1, blob) and len(examples) >= 200
     assert all(r.n_children > 0 and r.result in (-1.0, 0.0, 1.0) for r in examples)
     # the replay text format round-trips every record (example.rs:81-133)
