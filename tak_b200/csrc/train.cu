@@ -31,7 +31,7 @@ struct TrainState {
     std::vector<TrainLayer> layers;                 // 1 + 2 * blocks
     DevBuf pol_w_fwd[2], pol_bias[2], pol_w_dgrad[2];
     DevBuf master, grad, adam_m, adam_v, zero_bias;
-    DevBuf x0, g[2], dy, dt, g2, dlogits;
+    DevBuf x0, g[2], dy, dy2, dt, g2, dlogits;
     DevBuf bn_sums, bn_mean, bn_rstd, bn_a, bn_b, bwd_sums, bwd_c1, bwd_c2;
     DevBuf logits, partials, stats, values, dpre, loss, wg_scratch;
     DevBuf in_stage, pi_stage, z_stage;
@@ -41,6 +41,9 @@ struct TrainState {
     double last_ms = 0;
     uint64_t launches = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // wgrad runs on its own stream beside the dgrad / BatchNorm chain (it only feeds the gradient accumulators)
+    cudaStream_t wstream = nullptr;
+    cudaEvent_t ev_dy[2] = {nullptr, nullptr}, ev_w[2] = {nullptr, nullptr}, ev_join = nullptr;
     std::vector<std::pair<size_t, size_t>> trainable;   // (offset, count) of every tensor Adam updates
 };
 
@@ -130,6 +133,7 @@ static int ensure_capacity(tak_engine* e, TrainState& t, int boards) {
     TB_CUDA(planes(t.g[0], 1));
     TB_CUDA(planes(t.g[1], 1));
     TB_CUDA(planes(t.dy, 1));
+    TB_CUDA(planes(t.dy2, 1));
     TB_CUDA(planes(t.dt, 1));
     TB_CUDA(planes(t.g2, 1));
     TB_CUDA(planes(t.dlogits, 2));
@@ -164,10 +168,20 @@ static int train_chunk_t(tak_engine* e, TrainState& t, const float* d_in, const 
         t.launches++;
         return TAK_OK;
     };
-    auto wgrad = [&](const bf* dy, const bf* x, int c_in, size_t w_off, int co_base, int co_valid) -> int {
+    // wgrad of a layer only feeds the gradient accumulators, so it runs on `wstream` beside the dgrad / BatchNorm chain
+    // of the main stream (the HBM-bound passes fit next to a wgrad CTA on an SM).  `slot` names the dy buffer it reads:
+    // ev_dy[slot] = dy written (main -> wstream), ev_w[slot] = wgrad done reading it (wstream -> main, before reuse).
+    auto wgrad = [&](const bf* dy, const bf* x, int c_in, size_t w_off, int co_base, int co_valid, int slot) -> int {
+        TB_CUDA(cudaEventRecord(t.ev_dy[slot], e->stream));
+        TB_CUDA(cudaStreamWaitEvent(t.wstream, t.ev_dy[slot], 0));
         TB_CUDA(wgrad_tc_launch(dy, x, S, tiles, SlotMap<N>::PITCH, c_in, t.wg_scratch.as<float>(), grad + w_off, co_base,
-                                co_valid, 1, e->num_sms, e->stream));
+                                co_valid, 1, e->num_sms, t.wstream));
+        TB_CUDA(cudaEventRecord(t.ev_w[slot], t.wstream));
         t.launches += 2;
+        return TAK_OK;
+    };
+    auto reuse_dy = [&](int slot) -> int {   // the main stream is about to overwrite dy buffer `slot`
+        TB_CUDA(cudaStreamWaitEvent(e->stream, t.ev_w[slot], 0));
         return TAK_OK;
     };
 
@@ -230,8 +244,8 @@ static int train_chunk_t(tak_engine* e, TrainState& t, const float* d_in, const 
     // policy conv: wgrad per 128-channel group, dgrad in two K passes accumulated through the residual input
     const bf* dl0 = t.dlogits.as<bf>();
     const bf* dl1 = dl0 + size_t(16) * S * 8;
-    if (int r = wgrad(dl0, trunk, 128, t.pw_off, 0, 128)) return r;
-    if (int r = wgrad(dl1, trunk, 128, t.pw_off, 128, t.policy_ch - 128)) return r;
+    if (int r = wgrad(dl0, trunk, 128, t.pw_off, 0, 128, 0)) return r;
+    if (int r = wgrad(dl1, trunk, 128, t.pw_off, 128, t.policy_ch - 128, 1)) return r;
     if (int r = conv_lin(dl0, t.pol_w_dgrad[0].as<bf>(), t.zero_bias.as<float>(), g, g_alt, nullptr, C3_MAX_SLABS)) return r;
     if (int r = conv_lin(dl1, t.pol_w_dgrad[1].as<bf>(), t.zero_bias.as<float>(), g_alt, g, nullptr, C3_MAX_SLABS)) return r;
     // ------------------------------------------------ trunk backward --------------------------------------------------
@@ -256,21 +270,27 @@ static int train_chunk_t(tak_engine* e, TrainState& t, const float* d_in, const 
         const int l1 = 1 + 2 * blk, l2 = 2 + 2 * blk;
         const bf* xin = t.layers[l1 - 1].z.as<bf>();
         // out = relu(bn2(conv2(t)) + x): g2 = g * (out > 0) goes to both branches
+        if (int r = reuse_dy(0)) return r;
         if (int r = bn_backward(l2, g, t.dy.as<bf>(), t.g2.as<bf>())) return r;
-        if (int r = wgrad(t.dy.as<bf>(), t.layers[l1].z.as<bf>(), 128, t.layers[l2].w_off, 0, 128)) return r;
+        if (int r = wgrad(t.dy.as<bf>(), t.layers[l1].z.as<bf>(), 128, t.layers[l2].w_off, 0, 128, 0)) return r;
         if (int r = conv_lin(t.dy.as<bf>(), t.layers[l2].w_dgrad.as<bf>(), t.zero_bias.as<float>(), nullptr, t.dt.as<bf>(),
                              nullptr, C3_MAX_SLABS))
             return r;
-        if (int r = bn_backward(l1, t.dt.as<bf>(), t.dy.as<bf>(), nullptr)) return r;
-        if (int r = wgrad(t.dy.as<bf>(), xin, 128, t.layers[l1].w_off, 0, 128)) return r;
+        if (int r = reuse_dy(1)) return r;
+        if (int r = bn_backward(l1, t.dt.as<bf>(), t.dy2.as<bf>(), nullptr)) return r;
+        if (int r = wgrad(t.dy2.as<bf>(), xin, 128, t.layers[l1].w_off, 0, 128, 1)) return r;
         // gradient w.r.t. the block input = dgrad(conv1) + the residual share
-        if (int r = conv_lin(t.dy.as<bf>(), t.layers[l1].w_dgrad.as<bf>(), t.zero_bias.as<float>(), t.g2.as<bf>(), g_alt,
+        if (int r = conv_lin(t.dy2.as<bf>(), t.layers[l1].w_dgrad.as<bf>(), t.zero_bias.as<float>(), t.g2.as<bf>(), g_alt,
                              nullptr, C3_MAX_SLABS))
             return r;
         std::swap(g, g_alt);
     }
+    if (int r = reuse_dy(0)) return r;
     if (int r = bn_backward(0, g, t.dy.as<bf>(), nullptr)) return r;
-    if (int r = wgrad(t.dy.as<bf>(), t.x0.as<bf>(), t.c_in, t.layers[0].w_off, 0, 128)) return r;
+    if (int r = wgrad(t.dy.as<bf>(), t.x0.as<bf>(), t.c_in, t.layers[0].w_off, 0, 128, 0)) return r;
+    // join: the chunk is complete on the main stream only when the last wgrads are
+    TB_CUDA(cudaEventRecord(t.ev_join, t.wstream));
+    TB_CUDA(cudaStreamWaitEvent(e->stream, t.ev_join, 0));
     // conv biases feed a BatchNorm on batch statistics: their gradient is identically zero (sum of dy over the batch
     // vanishes), so only the weight decay term reaches them in Adam -- nothing to accumulate here.
     TB_CUDA(cudaGetLastError());
@@ -292,12 +312,15 @@ void train_destroy(tak_engine* e) {
     for (int i = 0; i < 2; ++i)
         for (DevBuf* b : {&t->pol_w_fwd[i], &t->pol_bias[i], &t->pol_w_dgrad[i], &t->g[i]}) b->release();
     for (DevBuf* b : {&t->master, &t->grad, &t->adam_m, &t->adam_v, &t->zero_bias, &t->x0, &t->dy, &t->dt, &t->g2,
-                      &t->dlogits, &t->bn_sums, &t->bn_mean, &t->bn_rstd, &t->bn_a, &t->bn_b, &t->bwd_sums, &t->bwd_c1,
+                      &t->dy2, &t->dlogits, &t->bn_sums, &t->bn_mean, &t->bn_rstd, &t->bn_a, &t->bn_b, &t->bwd_sums, &t->bwd_c1,
                       &t->bwd_c2, &t->logits, &t->partials, &t->stats, &t->values, &t->dpre, &t->loss, &t->wg_scratch,
                       &t->in_stage, &t->pi_stage, &t->z_stage})
         b->release();
     if (t->ev0) cudaEventDestroy(t->ev0);
     if (t->ev1) cudaEventDestroy(t->ev1);
+    for (cudaEvent_t ev : {t->ev_dy[0], t->ev_dy[1], t->ev_w[0], t->ev_w[1], t->ev_join})
+        if (ev) cudaEventDestroy(ev);
+    if (t->wstream) cudaStreamDestroy(t->wstream);
     delete t;
     e->net->train = nullptr;
 }
@@ -351,6 +374,12 @@ int32_t net_train_begin(tak_engine_t* e, int32_t max_boards) {
     TB_CUDA(t->wg_scratch.ensure(wgrad_scratch_elems(e->num_sms) * 4));
     TB_CUDA(cudaEventCreate(&t->ev0));
     TB_CUDA(cudaEventCreate(&t->ev1));
+    TB_CUDA(cudaStreamCreateWithFlags(&t->wstream, cudaStreamNonBlocking));
+    for (cudaEvent_t* ev : {&t->ev_dy[0], &t->ev_dy[1], &t->ev_w[0], &t->ev_w[1], &t->ev_join})
+        TB_CUDA(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
+    // ev_w[*] must be "complete" before the first reuse_dy of a chunk
+    TB_CUDA(cudaEventRecord(t->ev_w[0], t->wstream));
+    TB_CUDA(cudaEventRecord(t->ev_w[1], t->wstream));
     if (int r = ensure_capacity(e, *t, max_boards)) return r;
     if (int r = repack(e, *t)) return r;
     TB_CUDA(cudaStreamSynchronize(e->stream));
