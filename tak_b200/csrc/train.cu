@@ -32,7 +32,7 @@ struct TrainState {
     DevBuf pol_w_fwd[2], pol_bias[2], pol_w_dgrad[2];
     DevBuf master, grad, adam_m, adam_v, zero_bias;
     DevBuf x0, g[2], dy, dy2, dt, g2, dlogits;
-    DevBuf bn_sums, bn_mean, bn_rstd, bn_a, bn_b, bwd_sums, bwd_c1, bwd_c2;
+    DevBuf bn_sums, bn_mean, bn_rstd, bwd_sums;
     DevBuf logits, partials, stats, values, dpre, loss, wg_scratch;
     DevBuf in_stage, pi_stage, z_stage;
     int cap_boards = 0, S = 0;
@@ -198,15 +198,13 @@ static int train_chunk_t(tak_engine* e, TrainState& t, const float* d_in, const 
             return r;
         float* mean = t.bn_mean.as<float>() + l * 128;
         float* rstd = t.bn_rstd.as<float>() + l * 128;
-        float* a = t.bn_a.as<float>() + l * 128;
-        float* b = t.bn_b.as<float>() + l * 128;
-        k_bn_finalize<<<1, 128, 0, e->stream>>>(sums, count, master + L.gamma_off, master + L.beta_off, master + L.rm_off,
-                                                master + L.rv_off, mean, rstd, a, b);
         // conv2 of a block adds the block input before the ReLU (res_block.rs:21-22)
         const bool is_conv2 = l >= 2 && (l % 2) == 0;
         const bf* res = is_conv2 ? t.layers[l - 2].z.as<bf>() : nullptr;
-        k_bn_apply<N><<<ew_blocks, 256, 0, e->stream>>>(L.y.as<bf>(), res, a, b, B, S, L.z.as<bf>());
-        t.launches += 2;
+        k_bn_apply<N><<<ew_blocks, 256, 0, e->stream>>>(L.y.as<bf>(), res, sums, count, master + L.gamma_off,
+                                                        master + L.beta_off, master + L.rm_off, master + L.rv_off, mean,
+                                                        rstd, B, S, L.z.as<bf>());
+        t.launches += 1;
     }
     const bf* trunk = t.layers[nl - 1].z.as<bf>();
     {   // policy conv -> fp32 logits + per-slot softmax partials (net6.rs:113-116); value head (net6.rs:117-121)
@@ -258,12 +256,10 @@ static int train_chunk_t(tak_engine* e, TrainState& t, const float* d_in, const 
         TB_CUDA(cudaMemsetAsync(t.bwd_sums.p, 0, 256 * 8, e->stream));
         k_bn_bwd_reduce<<<dim3(BNR_SPLIT, 16), 256, 0, e->stream>>>(gin, L.z.as<bf>(), L.y.as<bf>(), mean, rstd, S,
                                                                     t.bwd_sums.as<double>());
-        k_bn_bwd_finalize<<<1, 128, 0, e->stream>>>(t.bwd_sums.as<double>(), count, grad + L.gamma_off, grad + L.beta_off,
-                                                    t.bwd_c1.as<float>(), t.bwd_c2.as<float>());
         k_bn_bwd_apply<N><<<ew_blocks, 256, 0, e->stream>>>(gin, L.z.as<bf>(), L.y.as<bf>(), mean, rstd,
-                                                            master + L.gamma_off, t.bwd_c1.as<float>(),
-                                                            t.bwd_c2.as<float>(), B, S, dy_out, gmasked);
-        t.launches += 3;
+                                                            master + L.gamma_off, t.bwd_sums.as<double>(), count,
+                                                            grad + L.gamma_off, grad + L.beta_off, B, S, dy_out, gmasked);
+        t.launches += 2;
         return TAK_OK;
     };
     for (int blk = t.blocks - 1; blk >= 0; --blk) {
@@ -312,8 +308,7 @@ void train_destroy(tak_engine* e) {
     for (int i = 0; i < 2; ++i)
         for (DevBuf* b : {&t->pol_w_fwd[i], &t->pol_bias[i], &t->pol_w_dgrad[i], &t->g[i]}) b->release();
     for (DevBuf* b : {&t->master, &t->grad, &t->adam_m, &t->adam_v, &t->zero_bias, &t->x0, &t->dy, &t->dt, &t->g2,
-                      &t->dy2, &t->dlogits, &t->bn_sums, &t->bn_mean, &t->bn_rstd, &t->bn_a, &t->bn_b, &t->bwd_sums, &t->bwd_c1,
-                      &t->bwd_c2, &t->logits, &t->partials, &t->stats, &t->values, &t->dpre, &t->loss, &t->wg_scratch,
+                      &t->dy2, &t->dlogits, &t->bn_sums, &t->bn_mean, &t->bn_rstd, &t->bwd_sums, &t->logits, &t->partials, &t->stats, &t->values, &t->dpre, &t->loss, &t->wg_scratch,
                       &t->in_stage, &t->pi_stage, &t->z_stage})
         b->release();
     if (t->ev0) cudaEventDestroy(t->ev0);
@@ -366,10 +361,8 @@ int32_t net_train_begin(tak_engine_t* e, int32_t max_boards) {
     }
     const size_t nl = t->layers.size();
     TB_CUDA(t->bn_sums.ensure(nl * 256 * 8));
-    for (DevBuf* b : {&t->bn_mean, &t->bn_rstd, &t->bn_a, &t->bn_b}) TB_CUDA(b->ensure(nl * 128 * 4));
+    for (DevBuf* b : {&t->bn_mean, &t->bn_rstd}) TB_CUDA(b->ensure(nl * 128 * 4));
     TB_CUDA(t->bwd_sums.ensure(256 * 8));
-    TB_CUDA(t->bwd_c1.ensure(512));
-    TB_CUDA(t->bwd_c2.ensure(512));
     TB_CUDA(t->loss.ensure(16));
     TB_CUDA(t->wg_scratch.ensure(wgrad_scratch_elems(e->num_sms) * 4));
     TB_CUDA(cudaEventCreate(&t->ev0));

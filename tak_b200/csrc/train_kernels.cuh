@@ -93,33 +93,38 @@ __global__ void __launch_bounds__(256) k_nchw_to_planes(const float* in, int n_b
 }
 
 // ---- BatchNorm forward on batch statistics --------------------------------------------------------------------------
-// sums [2][128] (double, from the conv epilogue) -> mean / rstd (saved for backward), the affine a*y + b applied by
-// k_bn_apply, and the running statistics of the master blob (momentum 0.1, unbiased variance, as libtorch)
-static __global__ void k_bn_finalize(const double* sums, double count, const float* gamma, const float* beta,
-                                     float* running_mean, float* running_var, float* mean_out, float* rstd_out,
-                                     float* a_out, float* b_out) {
-    const int c = threadIdx.x;
-    const double mean = sums[c] / count;
-    double var = sums[128 + c] / count - mean * mean;
-    if (var < 0) var = 0;
-    const double rstd = 1.0 / sqrt(var + double(TRAIN_BN_EPS));
-    mean_out[c] = float(mean);
-    rstd_out[c] = float(rstd);
-    const double a = double(gamma[c]) * rstd;
-    a_out[c] = float(a);
-    b_out[c] = float(double(beta[c]) - mean * a);
-    const double unbiased = count > 1 ? var * count / (count - 1) : var;
-    running_mean[c] = float((1.0 - TRAIN_BN_MOMENTUM) * running_mean[c] + TRAIN_BN_MOMENTUM * mean);
-    running_var[c] = float((1.0 - TRAIN_BN_MOMENTUM) * running_var[c] + TRAIN_BN_MOMENTUM * unbiased);
-}
-
-// z = relu(a*y + b (+ res)) on the real squares, 0 elsewhere  (net6.rs:72-76, res_block.rs:14-22 with train = true)
+// z = relu(a*y + b (+ res)) on the real squares, 0 elsewhere  (net6.rs:72-76, res_block.rs:14-22 with train = true).
+// The BatchNorm statistics are finalised here too (no separate launch): S is a multiple of 256, so a block lies inside one
+// 8-channel chunk; its first 8 threads turn the conv epilogue's double sums into mean / rstd and the affine a, b, and the
+// first block of every chunk also stores mean / rstd for backward and updates the running statistics (momentum 0.1,
+// unbiased variance, as libtorch).
 template <int N>
-__global__ void __launch_bounds__(256) k_bn_apply(const __nv_bfloat16* y, const __nv_bfloat16* res, const float* a,
-                                                  const float* b, int n_boards, int S, __nv_bfloat16* z) {
+__global__ void __launch_bounds__(256) k_bn_apply(const __nv_bfloat16* y, const __nv_bfloat16* res, const double* sums,
+                                                  double count, const float* gamma, const float* beta,
+                                                  float* running_mean, float* running_var, float* mean_out,
+                                                  float* rstd_out, int n_boards, int S, __nv_bfloat16* z) {
     const size_t idx = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int chunk = int((size_t(blockIdx.x) * blockDim.x) / S);
+    __shared__ float s_a[8], s_b[8];
+    if (threadIdx.x < 8) {
+        const int c = chunk * 8 + threadIdx.x;
+        const double mean = sums[c] / count;
+        double var = sums[128 + c] / count - mean * mean;
+        if (var < 0) var = 0;
+        const double rstd = 1.0 / sqrt(var + double(TRAIN_BN_EPS));
+        const double a = double(gamma[c]) * rstd;
+        s_a[threadIdx.x] = float(a);
+        s_b[threadIdx.x] = float(double(beta[c]) - mean * a);
+        if ((size_t(blockIdx.x) * blockDim.x) % S == 0) {
+            mean_out[c] = float(mean);
+            rstd_out[c] = float(rstd);
+            const double unbiased = count > 1 ? var * count / (count - 1) : var;
+            running_mean[c] = float((1.0 - TRAIN_BN_MOMENTUM) * running_mean[c] + TRAIN_BN_MOMENTUM * mean);
+            running_var[c] = float((1.0 - TRAIN_BN_MOMENTUM) * running_var[c] + TRAIN_BN_MOMENTUM * unbiased);
+        }
+    }
+    __syncthreads();
     if (idx >= size_t(16) * S) return;
-    const int chunk = int(idx / S);
     const size_t slot = idx % S;
     float o[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (slot_valid<N>(slot, n_boards)) {
@@ -128,7 +133,7 @@ __global__ void __launch_bounds__(256) k_bn_apply(const __nv_bfloat16* y, const 
         if (res) unpack8(*reinterpret_cast<const uint4*>(res + idx * 8), r);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            float v = f[j] * a[chunk * 8 + j] + b[chunk * 8 + j];
+            float v = f[j] * s_a[j] + s_b[j];
             if (res) v += r[j];
             o[j] = fmaxf(v, 0.f);
         }
@@ -191,25 +196,30 @@ static __global__ void __launch_bounds__(256) k_bn_bwd_reduce(const __nv_bfloat1
         atomicAdd(&sums[(threadIdx.x < 8 ? 0 : 128) + chunk * 8 + j], double(t));
     }
 }
-// dgamma += sum g'*xhat, dbeta += sum g';  c1 = sum g' / n, c2 = sum g'*xhat / n for pass 2
-static __global__ void k_bn_bwd_finalize(const double* sums, double count, float* grad_gamma, float* grad_beta,
-                                         float* c1, float* c2) {
-    const int c = threadIdx.x;
-    grad_beta[c] += float(sums[c]);
-    grad_gamma[c] += float(sums[128 + c]);
-    c1[c] = float(sums[c] / count);
-    c2[c] = float(sums[128 + c] / count);
-}
 // pass 2: dy = gamma * rstd * (g' - c1 - xhat * c2) on the real squares; optionally also stores g' (the gradient that
 // flows into the residual connection, res_block.rs:21)
+// (the sums of pass 1 are finalised here: c1 = sum g' / n, c2 = sum g'*xhat / n per block, and the first block of every
+// chunk accumulates dgamma += sum g'*xhat, dbeta += sum g')
 template <int N>
 __global__ void __launch_bounds__(256) k_bn_bwd_apply(const __nv_bfloat16* g, const __nv_bfloat16* zout,
                                                       const __nv_bfloat16* y, const float* mean, const float* rstd,
-                                                      const float* gamma, const float* c1, const float* c2,
+                                                      const float* gamma, const double* sums, double count,
+                                                      float* grad_gamma, float* grad_beta,
                                                       int n_boards, int S, __nv_bfloat16* dy, __nv_bfloat16* gmasked) {
     const size_t idx = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int chunk = int((size_t(blockIdx.x) * blockDim.x) / S);
+    __shared__ float c1[8], c2[8];
+    if (threadIdx.x < 8) {
+        const int c = chunk * 8 + threadIdx.x;
+        c1[threadIdx.x] = float(sums[c] / count);
+        c2[threadIdx.x] = float(sums[128 + c] / count);
+        if ((size_t(blockIdx.x) * blockDim.x) % S == 0) {
+            grad_beta[c] += float(sums[c]);
+            grad_gamma[c] += float(sums[128 + c]);
+        }
+    }
+    __syncthreads();
     if (idx >= size_t(16) * S) return;
-    const int chunk = int(idx / S);
     const size_t slot = idx % S;
     float o[8] = {0, 0, 0, 0, 0, 0, 0, 0}, gm[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (slot_valid<N>(slot, n_boards)) {
@@ -223,7 +233,7 @@ __global__ void __launch_bounds__(256) k_bn_bwd_apply(const __nv_bfloat16* g, co
             const float gg = (!zout || zv[j] > 0.f) ? gv[j] : 0.f;
             const float xhat = (yv[j] - mean[c]) * rstd[c];
             gm[j] = gg;
-            o[j] = gamma[c] * rstd[c] * (gg - c1[c] - xhat * c2[c]);
+            o[j] = gamma[c] * rstd[c] * (gg - c1[j] - xhat * c2[j]);
         }
     }
     *reinterpret_cast<uint4*>(dy + idx * 8) = pack8(o);
