@@ -188,6 +188,9 @@ class Game:
         k = lib().orc_game_moves(self._h, buf, 4096)
         return list(buf[:k])
 
+    def flat_diff(self) -> int:
+        return lib().orc_game_flat_diff(self._h)
+
     def result(self) -> int:
         return lib().orc_game_result(self._h)
 

@@ -567,6 +567,42 @@ class Game:
     def perft(self, depth: int) -> int:
         return self.engine.perft(self.state(), depth)
 
+    def safe_play(self, move) -> "Game":
+        """`Game::safe_play` (game.rs:111-117): plays the move and returns the PRE-move backup; on a PlayError the game is
+        restored from the backup and the error raised."""
+        backup = self.clone()
+        st = self.play(move)
+        if st != 0:
+            self.engine.upload([self.slot], [backup.state()])
+            raise TakNativeError(st, "PlayError")
+        return backup
+
+    # ---- tak::Board accessors (board.rs:61-75), computed on the host from the downloaded state ----
+    def board_full(self) -> bool:
+        s = self.state()
+        return all(s.height[i] > 0 for i in range(self.n * self.n))
+
+    def flat_diff(self) -> int:
+        """White flats on top minus black flats on top (board.rs:65-75)."""
+        s, d = self.state(), 0
+        for i in range(self.n * self.n):
+            h = s.height[i]
+            if h and s.top[i] == 0:
+                hi = h - 1
+                black = ((s.stack_lo[i] >> hi) & 1) if hi < 64 else ((s.stack_hi[i] >> (hi - 64)) & 1)
+                d += -1 if black else 1
+        return d
+
+    def symmetries(self) -> List["Game"]:
+        """`Symmetry::symmetries` for a game (symm.rs:82-97): the 8 transformed games, in the reference's order."""
+        st = self.state()
+        return [Game.from_state(symmetry_state(st, k)) for k in range(8)]
+
+
+def default_starting_stones(n: int) -> Tuple[int, int]:
+    """(stones, capstones) per player (tak/src/game.rs:10-20)."""
+    return {3: (10, 0), 4: (15, 0), 5: (21, 1), 6: (30, 1), 7: (40, 2), 8: (50, 2)}[n]
+
 
 class Player:
     """Mirror of `alpha_tak::Player` (alpha-tak/src/player.rs:23-199) for ONE game slot of an engine.

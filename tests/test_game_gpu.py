@@ -164,3 +164,25 @@ def test_ptn_tps_text_matches_oracle(golden_moves_5):
     s = tb.tps_parse(6, g.tps())
     assert tb.tps_format(s) == g.tps()
     assert s.key() == oracle.Game.from_tps(6, g.tps()).state().key()
+
+
+def test_game_surface_helpers():
+    """The rest of the `tak::Game` / `Board` surface: safe_play, flat_diff, full, symmetries, default_starting_stones."""
+    import oracle
+    from util import random_positions
+    assert tb.default_starting_stones(6) == (30, 1) and tb.default_starting_stones(8) == (50, 2)
+    for og in random_positions(5, 6, seed=9, max_ply=40):
+        g = tb.Game.from_state(tb.TakState.from_buffer_copy(bytes(og.state())))
+        assert g.flat_diff() == og.flat_diff()
+        before = g.state().key()
+        mv = g.possible_moves()[0]
+        backup = g.safe_play(mv)
+        assert backup.state().key() == before and g.state().key() != before
+        with pytest.raises(tb.TakNativeError):
+            g.safe_play(tb.parse_move("a1", 5) if g.state().height[0] else tb.parse_move("1a1+", 5))
+        og.play(mv)
+        assert g.state().key() == bytes(og.state())           # a failed safe_play leaves the game untouched
+        syms = g.symmetries()
+        assert len(syms) == 8 and syms[0].state().key() == g.state().key()
+        assert sorted(s.flat_diff() for s in syms) == [g.flat_diff()] * 8
+        assert all(s.board_full() == g.board_full() for s in syms)
