@@ -186,3 +186,26 @@ def test_game_surface_helpers():
         assert len(syms) == 8 and syms[0].state().key() == g.state().key()
         assert sorted(s.flat_diff() for s in syms) == [g.flat_diff()] * 8
         assert all(s.board_full() == g.board_full() for s in syms)
+
+
+def test_symmetrical_boards(golden):
+    # reference: tak/tests/symm.rs:3-68 -- read like the reference's own test, on the device engine
+    eng = tb.Engine(5, 8, nodes_per_game=64)
+    ids = list(range(8))
+    for seed in golden["symm_seeds"]:
+        eng.reset(0, 8, 0)
+        start = eng.download([0])[0]
+        eng.upload(ids, [tb.symmetry_state(start, k) for k in range(8)])       # Game::<5>::default().symmetries()
+        plies = 0
+        while (int(eng.result([0])[0]) & 3) == tb.RESULT_ONGOING:
+            moves = eng.possible_moves([0])[0]
+            my_move = int(moves[seed % len(moves)])
+            status = eng.play(ids, [tb.symmetry_move(my_move, 5, k) for k in range(8)])
+            assert not status.any(), (seed, plies, status)
+            plies += 1
+        res = [int(r) for r in eng.result(ids)]
+        assert len(set(res)) == 1, (seed, res)
+        # stronger than the reference: the 8 games are still each other's images
+        states = eng.download(ids)
+        assert [s.key() for s in states] == [tb.symmetry_state(states[0], k).key() for k in range(8)]
+    eng.close()
