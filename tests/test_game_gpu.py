@@ -209,3 +209,21 @@ def test_symmetrical_boards(golden):
         states = eng.download(ids)
         assert [s.key() for s in states] == [tb.symmetry_state(states[0], k).key() for k in range(8)]
     eng.close()
+
+
+def test_tps_consistency(golden):
+    # reference: tak/tests/tps.rs:26-96 -- after every ply of a deterministic playout, Game -> Tps -> Game keeps the board,
+    # the side to move, the ply and the four reserve counters (komi and the reversible-ply counter are not in a TPS)
+    for seed in golden["symm_seeds"]:
+        game = tb.Game.default(5)
+        while (game.result() & 3) == tb.RESULT_ONGOING:
+            moves = game.possible_moves()
+            assert game.play(moves[seed % len(moves)]) == 0
+            st = game.state()
+            back = tb.tps_parse(5, tb.tps_format(st))
+            nsq = 25
+            assert list(back.height[:nsq]) == list(st.height[:nsq]) and list(back.top[:nsq]) == list(st.top[:nsq])
+            assert list(back.stack_lo[:nsq]) == list(st.stack_lo[:nsq])
+            assert (back.to_move, back.ply) == (st.to_move, st.ply)
+            assert (back.white_caps, back.white_stones, back.black_caps, back.black_stones) == \
+                   (st.white_caps, st.white_stones, st.black_caps, st.black_stones)
