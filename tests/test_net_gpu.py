@@ -86,3 +86,22 @@ def test_dummy_net():
     pol, val = eng.policy_eval([tb.state_init(3)])
     assert pol.shape == (1, tb.policy_size(3)) and np.all(pol == 1.0) and val[0] == 0.0
     eng.close()
+
+
+def test_board_repr_reference_plane_dump(golden):
+    """alpha-tak/src/repr/tests.rs:20-111 through the DEVICE kernel: the reference dumps board_repr(game, White) of a
+    45-ply 5x5 game; game_repr encodes from the side to move (Black at ply 45), i.e. the same planes with every
+    mine / theirs channel pair swapped."""
+    r = golden["board_repr"]
+    game = tb.Game.from_ptn_moves(r["n"], r["moves"])
+    st = game.state()
+    assert st.ply == 45 and st.to_move == 1 and r["to_move_arg"] == 0
+    planes = game.engine.game_repr([st])[0]
+    want = np.array(r["planes_12x5x5"], dtype=np.float32).reshape(12, 5, 5)
+    for ch in range(12):
+        assert np.array_equal(planes[ch ^ 1], want[ch]), ch
+    # the deeper stack planes of this position are empty in the reference dump (tests.rs:107-110)
+    assert not planes[12:2 * (5 + 8)].any()
+    # empty board: all board planes zero (tests.rs:11-17)
+    empty = tb.Game.default(5)
+    assert not empty.engine.game_repr([empty.state()])[0][:2 * (5 + 8)].any()
