@@ -116,3 +116,35 @@ def test_weight_blob_layout():
     assert parts["policy_conv.weight"].shape == (251, 128, 3, 3)
     assert parts["value_fc.weight"].shape == (1, 4608)
     assert np.array_equal(W.random_weights(6, seed=0), blob) and not np.array_equal(W.random_weights(6, seed=1), blob)
+
+
+def test_header_is_plain_c_and_a_c_program_links(tmp_path):
+    """The boundary is a C ABI: include/taknative.h compiles as C99 (-pedantic) and a C program links against the
+    library and calls its host-side entry points (what a cgo / Rust `extern "C"` consumer relies on)."""
+    src = tmp_path / "consumer.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "taknative.h"
+int main(void) {
+    tak_state_t s;
+    uint16_t mv = 0;
+    int32_t idx = -1, size = 0;
+    char buf[256];
+    if (tak_state_init(6, 4, &s) != TAK_OK || s.n != 6 || s.half_komi != 4) return 1;
+    if (tak_ptn_parse(6, "3c3>12", &mv) != TAK_OK) return 2;
+    if (tak_ptn_format(6, mv, buf, (int32_t)sizeof buf) < 0 || strcmp(buf, "3c3>12") != 0) return 3;
+    if (tak_move_index(6, mv, &idx) != TAK_OK || tak_policy_size(6, &size) != TAK_OK || idx < 0 || idx >= size) return 4;
+    if (tak_tps_format(&s, buf, (int32_t)sizeof buf) < 0) return 5;
+    if (tak_ptn_parse(6, "not a move", &mv) == TAK_OK) return 6;      /* errors are codes, never aborts */
+    printf("%d %d %s %d\n", (int)idx, (int)size, buf, (int)sizeof(tak_move_info_t));
+    return 0;
+}
+''')
+    exe = tmp_path / "consumer"
+    libdir = os.path.dirname(tb.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           str(src), "-o", str(exe), "-L", libdir, "-ltaknative", f"-Wl,-rpath,{libdir}"])
+    out = subprocess.check_output([str(exe)], text=True).split()
+    assert int(out[0]) == tb.move_index(tb.parse_move("3c3>12", 6), 6) and int(out[1]) == 9036
+    assert out[2].startswith("x6/x6/x6/x6/x6/x6") and int(out[-1]) == C.sizeof(_lib.MoveInfoRecord)
