@@ -180,3 +180,31 @@ def test_device_tensors_and_grad_view(trained):
     # not bit-identical run to run: the split-K partial sums and double atomics are order dependent
     assert rel_err(eng.train_get(1), g_host) < 1e-3
     gt.zero_()
+
+
+def test_training_api_errors():
+    """Error behaviour at the boundary: status codes, never aborts."""
+    e5 = tb.Engine(5, 4, nodes_per_game=64, max_batch=4)
+    e5.net_create(5)
+    e5.net_load_weights(W.random_weights(5, seed=1))
+    with pytest.raises(tb.TakNativeError) as ex:          # the reference trains only Net6 (train/src/main.rs:42-43)
+        e5.train_begin(64)
+    assert ex.value.code == -32
+    e5.close()
+    e6 = tb.Engine(6, 4, nodes_per_game=64, max_batch=4)
+    e6.net_create(6)
+    with pytest.raises(tb.TakNativeError):                # no weights loaded yet
+        e6.train_begin(64)
+    e6.net_load_weights(W.random_weights(6, seed=1))
+    with pytest.raises(tb.TakNativeError):                # train_chunk before train_begin
+        e6.train_chunk(*make_chunk(8, 1))
+    e6.train_begin(16)
+    with pytest.raises(tb.TakNativeError) as ex:          # chunk larger than reserved
+        e6.train_chunk(*make_chunk(17, 1))
+    assert ex.value.code == -34
+    lp, lz = e6.train_chunk(*make_chunk(1, 2))            # a single position is a valid chunk
+    assert np.isfinite([lp, lz]).all()
+    e6.train_end()
+    with pytest.raises(tb.TakNativeError):
+        e6.train_step()
+    e6.close()
