@@ -31,20 +31,25 @@ WIN_RATE_THRESHOLD = 0.55   # train/src/main.rs:27
 def train_network(eng: Engine, examples: Sequence[ReplayRecord], rng: np.random.Generator,
                   chunk_size: int = CHUNK_SIZE, chunks_in_step: int = CHUNKS_IN_STEP, lr: float = LEARNING_RATE,
                   weight_decay: float = WEIGHT_DECAY, allreduce: Optional[Callable] = None,
-                  log: Callable = print) -> np.ndarray:
+                  log: Callable = print, rank: int = 0, world: int = 1) -> np.ndarray:
     """`Network::train(&mut self, examples)` starting from the weights last loaded into `eng`; returns the new blob
-    (weights incl. BatchNorm running statistics).  `allreduce(grad_tensor)` is called before every step in data-parallel
-    runs (parallel.allreduce_gradients)."""
+    (weights incl. BatchNorm running statistics).
+
+    Data-parallel (world > 1): every rank holds the same examples and the same `rng` state, so all ranks draw the same
+    shuffle; chunk i is trained by rank i % world, and before every step `allreduce(grad_tensor)`
+    (parallel.allreduce_gradients) sums the ranks' accumulators -- the step is then the reference's single-process step
+    over the same `chunks_in_step` chunks.  (BatchNorm running statistics follow each rank's own chunks.)"""
     log(f"starting training with {len(examples)} examples")
     eng.train_begin(8 * chunk_size)                       # Adam { wd, ..Default }.build(vs, lr): fresh moments
     order = rng.permutation(len(examples))                # refs.shuffle(&mut thread_rng())
     losses = []
     for i in range(len(examples) // chunk_size):          # chunks_exact(CHUNK_SIZE)
-        recs = [examples[j] for j in order[i * chunk_size:(i + 1) * chunk_size]]
-        inputs, pi, z = eng.examples_to_tensors(recs, on_device=True)    # flat_map(|ex| ex.to_tensors())
-        lp, lz = eng.train_chunk(inputs, pi, z)
-        losses.append((lp, lz))
-        log(f"p={lp:.4f}\t z={lz:.4f}")
+        if i % world == rank:
+            recs = [examples[j] for j in order[i * chunk_size:(i + 1) * chunk_size]]
+            inputs, pi, z = eng.examples_to_tensors(recs, on_device=True)    # flat_map(|ex| ex.to_tensors())
+            lp, lz = eng.train_chunk(inputs, pi, z)
+            losses.append((lp, lz))
+            log(f"p={lp:.4f}\t z={lz:.4f}")
         if (i + 1) % chunks_in_step == 0:
             if allreduce is not None:
                 allreduce(eng.train_grad_tensor())
@@ -111,4 +116,48 @@ def training_iteration(current: Engine, candidate: Engine, blob: np.ndarray, exa
         os.makedirs(os.path.join(save_dir, "_examples"), exist_ok=True)
         save_examples(os.path.join(save_dir, "_examples", f"{int(time.time())}.data"), new_examples)
     examples = list(examples) + new_examples
+    return blob, examples, result
+
+
+def distributed_iteration(current: Engine, candidate: Engine, blob: np.ndarray, examples: List[ReplayRecord], seed: int,
+                          device, pit_games: int = 128, pit_rollouts: int = 50, pit_batch: int = 16,
+                          min_new_examples: int = 1000, train_kw: Optional[dict] = None,
+                          selfplay_kw: Optional[dict] = None, log: Callable = print):
+    """One turn of `training_loop` on N GPUs (one process per GPU, torch.distributed already initialised):
+      * training is data-parallel (chunks dealt round-robin, NCCL all-reduce of the gradient blob before each step),
+      * the pit games are split over the ranks and the win / loss / draw counts summed,
+      * self-play is sharded (every rank plays its own games with the SAME accepted network) and the replay records are
+        all-gathered, so every rank enters the next turn with the same examples and the same weights.
+    Returns (blob, examples, PitResult | None); identical on every rank."""
+    import torch
+    import torch.distributed as dist
+
+    from . import parallel as par
+    rank, world = dist.get_rank(), dist.get_world_size()
+    result: Optional[PitResult] = None
+    if examples:
+        candidate.net_load_weights(blob)
+        rng = np.random.default_rng(seed)                 # same shuffle on every rank
+        new_blob = train_network(candidate, examples, rng, log=log, allreduce=par.allreduce_gradients, rank=rank,
+                                 world=world, **(train_kw or {}))
+        t = torch.from_numpy(new_blob).to(device)         # running statistics: mean over ranks; weights already agree
+        dist.all_reduce(t)
+        new_blob = (t / world).cpu().numpy()
+        candidate.net_load_weights(new_blob)
+        mine = pit(candidate, current, games=max(1, pit_games // world), batch=pit_batch, rollouts=pit_rollouts,
+                   seed=seed * 1000 + rank)
+        counts = torch.tensor([mine.wins, mine.losses, mine.draws], dtype=torch.int64, device=device)
+        dist.all_reduce(counts)
+        result = PitResult(*[int(c) for c in counts.tolist()])
+        log(repr(result))
+        if result.win_rate() > WIN_RATE_THRESHOLD:
+            blob = new_blob
+            current.net_load_weights(blob)
+        if len(examples) > MAX_EXAMPLES:
+            examples = examples[-MAX_EXAMPLES:]
+    sp = dict(selfplay_kw or {})
+    sp["game_id_base"] = par.game_id_base(rank, current.max_games)
+    sp["seed"] = sp.get("seed", 0x7A4B) + seed
+    mine = collect_self_play(current, max(1, min_new_examples // world), **sp)
+    examples = list(examples) + par.gather_replay(mine, ReplayRecord, device)
     return blob, examples, result
