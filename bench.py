@@ -567,6 +567,21 @@ def run_b200(args):
     # ---------------- training step (next row N1): train_inner + all-reduce + Adam on those examples -----------------
     train = train_rate(engines[0], aug_tensors, world, dist, dev, pk, aug_recs) if aug_tensors is not None else None
 
+    if rank == 0 and world == 1:
+        # the CPU path beside it: the oracle's literal restatement of perft.rs:3-18 (-O3 -march=native), single-threaded as
+        # the reference's test is, and one subtree per host thread
+        import oracle
+        og = oracle.Game(6, 0)
+        t0 = time.perf_counter()
+        n4 = og.perft(4)
+        t1 = time.perf_counter()
+        threads = os.cpu_count() or 1
+        n5 = og.perft(5, threads)
+        t2 = time.perf_counter()
+        movegen["cpu_baseline"] = {"kind": "port", "single_thread_mnodes_s": n4 / (t1 - t0) / 1e6,
+                                   "all_threads_mnodes_s": n5 / (t2 - t1) / 1e6, "cores": threads,
+                                   "sample": "6x6 perft(4) on one thread, perft(5) over all host threads; counts "
+                                             f"{n4} / {n5}", "exact": n4 == 13_586_048 and n5 == PERFT6_D5}
     line = None
     if rank == 0:
         # the CPU baseline is timed beside the GPU arm at N=1 only (at N>1 the other ranks' host threads share the cores)
