@@ -6,6 +6,7 @@
 #include <cmath>
 
 #include "conv_tc3.cuh"
+#include "fc_tc.cuh"
 #include "net_kernels.cuh"
 
 namespace tb {
@@ -95,13 +96,19 @@ int net_load_blob(tak_engine* e, const float* blob, int64_t elems) {
             if (int r = upload_layer(e, ns.policy_layers[grp], packed, bias)) return r;
         }
     } else {
-        // FC policy: W[j][k] -> bf16 Wt[k][j]
+        // FC policy: W[j][c*NSQ + pos] -> the tcgen05 operand image Wp[jt][pos][slab][kchunk][128 outputs][8 channels]
         const int K = 128 * nsq, J = ns.policy_out;
         const float* w = p; p += size_t(J) * K;
         const float* b = p; p += J;
-        std::vector<__nv_bfloat16> wt(size_t(K) * J);
+        const int j_tiles = (J + 127) / 128;
+        std::vector<__nv_bfloat16> wt(size_t(j_tiles) * nsq * 8 * 2 * 128 * 8, __float2bfloat16(0.f));
         for (int j = 0; j < J; ++j)
-            for (int k = 0; k < K; ++k) wt[size_t(k) * J + j] = __float2bfloat16(w[size_t(j) * K + k]);
+            for (int c = 0; c < 128; ++c)
+                for (int pos = 0; pos < nsq; ++pos) {
+                    const int jt = j >> 7, col = j & 127, slab = c >> 4, kc = (c >> 3) & 1, i = c & 7;
+                    wt[((((size_t(jt) * nsq + pos) * 8 + slab) * 2 + kc) * 128 + col) * 8 + i] =
+                        __float2bfloat16(w[size_t(j) * K + size_t(c) * nsq + pos]);
+                }
         TB_CUDA(ns.fc_policy_w.ensure(wt.size() * 2));
         TB_CUDA(ns.fc_policy_b.ensure(size_t(J) * 4));
         TB_CUDA(cudaMemcpyAsync(ns.fc_policy_w.p, wt.data(), wt.size() * 2, cudaMemcpyHostToDevice, e->stream));
@@ -208,10 +215,19 @@ static int forward_t(tak_engine* e, const uint8_t* d_states, const int* d_index,
                                                                  ns.stats.as<float2>(), d_policy_out);
         }
     } else {
-        k_policy_fc<N><<<boards, 256, 0, e->stream>>>(x, S, ns.fc_policy_w.as<__nv_bfloat16>(),
-                                                      ns.fc_policy_b.as<float>(), ns.policy_out,
-                                                      ns.logits.as<float>());
-        e->launches++;
+        // policy FC (net5.rs:108) on the tensor cores: repack the trunk output, then one GEMM launch (fc_tc.cuh)
+        const int b_pad = (boards + FC_NT - 1) / FC_NT * FC_NT;
+        TB_CUDA(ns.fc_x.ensure(size_t(N * N) * 16 * b_pad * 16));
+        const size_t items = size_t(N * N) * 16 * b_pad;
+        k_fc_repack<N><<<unsigned((items + 255) / 256), 256, 0, e->stream>>>(x, S, boards, b_pad,
+                                                                            ns.fc_x.as<__nv_bfloat16>());
+        FcParams fp{};
+        fp.wp = ns.fc_policy_w.as<__nv_bfloat16>(); fp.x = ns.fc_x.as<__nv_bfloat16>();
+        fp.bias = ns.fc_policy_b.as<float>(); fp.logits = ns.logits.as<float>();
+        fp.n_out = ns.policy_out; fp.boards = boards; fp.b_pad = b_pad; fp.n_pos = N * N;
+        fp.j_tiles = (ns.policy_out + 127) / 128; fp.n_tiles = b_pad / FC_NT;
+        TB_CUDA(fc_tc_launch(fp, e->num_sms, e->stream));
+        e->launches += 2;
         k_policy_stats_dense<<<boards, 256, 0, e->stream>>>(ns.logits.as<float>(), ns.policy_out,
                                                             ns.stats.as<float2>(), d_policy_out);
     }
@@ -242,7 +258,7 @@ void net_destroy(tak_engine* e) {
     NetState& ns = *e->net;
     for (auto& L : ns.layers) { L.w.release(); L.bias.release(); }
     for (auto& L : ns.policy_layers) { L.w.release(); L.bias.release(); }
-    for (DevBuf* b : {&ns.fc_policy_w, &ns.fc_policy_b, &ns.value_w, &ns.act[0], &ns.act[1], &ns.act[2], &ns.logits,
+    for (DevBuf* b : {&ns.fc_policy_w, &ns.fc_policy_b, &ns.fc_x, &ns.value_w, &ns.act[0], &ns.act[1], &ns.act[2], &ns.logits,
                       &ns.partials, &ns.stats, &ns.values, &ns.stage_states, &ns.stage_policy, &ns.stage_repr})
         b->release();
     delete e->net;

@@ -28,7 +28,8 @@ struct NetState {
     bool loaded = false;
     std::vector<ConvLayer> layers;         // initial conv + 2 per block (BN folded)
     std::vector<ConvLayer> policy_layers;  // Net6 policy conv, one per group
-    DevBuf fc_policy_w, fc_policy_b;       // Net5 policy FC: bf16 Wt[k][j], fp32 bias
+    DevBuf fc_policy_w, fc_policy_b;       // Net5 policy FC: bf16 operand image Wp[jt][pos][slab][2][128][8] (fc_tc.cuh), fp32 bias
+    DevBuf fc_x;                           // Net5: trunk output repacked as X[pos][chunk][board][8] for the FC GEMM
     DevBuf value_w;                        // fp32 [128*NSQ] (NCHW flatten order)
     float value_bias = 0.f;
     // activations

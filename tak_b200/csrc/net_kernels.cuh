@@ -2,7 +2,7 @@
 //   k_encode      alpha_tak::repr::game_repr (repr/game.rs:19-51, board.rs:12-54, reserves.rs:4-28) written straight
 //                 into the first conv's bf16 slot-plane layout (no host tensor ops, no H2D of planes)
 //   k_repr_f32    the same planes as fp32 [C][N][N] (the reference's exact tensor; parity/debug surface)
-//   k_policy_stats6 / k_policy_fc5 / k_value / k_policy_full   heads of net6.rs:98-109 / net5.rs:106-111
+//   k_policy_stats_* / k_value / k_policy_full   heads of net6.rs:98-109 / net5.rs:106-111 (Net5's policy FC: fc_tc.cuh)
 #pragma once
 #include <cuda_bf16.h>
 
@@ -186,27 +186,6 @@ __global__ void __launch_bounds__(256)
     }
 }
 
-// Net5-style head (net5.rs:56-62,108): logits[b][j] = bias[j] + sum_{c,pos} W[j][c*NSQ + pos] * s[c][pos]; the
-// weights are stored transposed as bf16 Wt[k = c*NSQ+pos][j] so a warp reads 32 consecutive outputs.
-// One block per board; the board's trunk output is staged in shared memory as fp32.
-template <int N>
-__global__ void __launch_bounds__(256)
-    k_policy_fc(const __nv_bfloat16* act, int S, const __nv_bfloat16* wt, const float* bias, int n_out,
-                float* logits_out /*[b][n_out]*/) {
-    constexpr int NSQ = N * N, K = 128 * NSQ;
-    __shared__ float s_act[K];
-    const int b = blockIdx.x;
-    for (int i = threadIdx.x; i < K; i += blockDim.x) {
-        const int c = i / NSQ, pos = i % NSQ, y = pos / N, x = pos % N;
-        s_act[i] = __bfloat162float(act[(size_t(c >> 3) * S + SlotMap<N>::slot(b, y, x)) * 8 + (c & 7)]);
-    }
-    __syncthreads();
-    for (int j = threadIdx.x; j < n_out; j += blockDim.x) {
-        float acc = 0.f;
-        for (int k = 0; k < K; ++k) acc += s_act[k] * __bfloat162float(wt[size_t(k) * n_out + j]);
-        logits_out[size_t(b) * n_out + j] = acc + bias[j];
-    }
-}
 // softmax statistics / full policy over a dense logits row [b][n_out]
 static __global__ void __launch_bounds__(256)
     k_policy_stats_dense(const float* logits, int n_out, float2* stats, float* policy_out) {
