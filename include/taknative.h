@@ -161,7 +161,7 @@ int32_t net_forward_timed(tak_engine_t* e, int32_t first, int32_t count, int32_t
  * (CUDA events around each conv launch), out[2] = conv launches per forward, out[3] = algorithmic FLOP per forward */
 int32_t net_forward_profile(tak_engine_t* e, int32_t first, int32_t count, int32_t reps, double* out4);
 
-/* ---- Network::train (alpha-tak/src/model/network.rs:37-97), Net6 ------------------------------------------------
+/* ---- Network::train (alpha-tak/src/model/network.rs:37-97), Net6 and Net5 ---------------------------------------
  * net_train_begin   allocate the training state for chunks of up to max_boards positions; fp32 master weights start from
  *                   the blob last loaded with net_load_weights (VarStore of a fresh or loaded network); Adam moments 0
  * net_train_chunk   train_inner for one chunk (network.rs:59-97): inputs [b][C][n][n], pi [b][policy_size], z [b] fp32
@@ -173,7 +173,8 @@ int32_t net_forward_profile(tak_engine_t* e, int32_t first, int32_t count, int32
  * net_train_get     copy out the blob-shaped fp32 state: 0 weights (incl. BN running statistics), 1 gradients,
  *                   2 / 3 Adam first / second moments.  Feed `0` to net_load_weights to search with the new network.
  * net_train_grad_ptr device pointer of the gradient blob (data-parallel training: all-reduce it in place before the step)
- * The reference trains only Net6 (train/src/main.rs:42-43); other architectures return TAK_ERR_BAD_ARG.            */
+ * (The reference's `train` binary instantiates only Net6, train/src/main.rs:42-43; `Network::train` itself is generic.)
+ * The DummyNet returns TAK_ERR_BAD_ARG.                                                                              */
 int32_t net_train_begin(tak_engine_t* e, int32_t max_boards);
 int32_t net_train_chunk(tak_engine_t* e, const float* inputs, const float* pi, const float* z, int32_t boards,
                         int32_t on_device, float* out_loss2);

@@ -71,8 +71,8 @@ class _RoundFwd(torch.autograd.Function):
 
 
 class RefTrainer:
-    """fp32 PyTorch restatement of `Network::train_inner` + `Adam` for Net6 (alpha-tak/src/model/network.rs:37-97,
-    net6.rs:111-122): forward_training (BatchNorm on batch statistics, momentum 0.1, eps 1e-5 -- tch's BatchNormConfig
+    """fp32 PyTorch restatement of `Network::train_inner` + `Adam` for Net6 / Net5 (alpha-tak/src/model/network.rs:37-97,
+    net6.rs:111-122, net5.rs:113-124): forward_training (BatchNorm on batch statistics, momentum 0.1, eps 1e-5 -- tch's BatchNormConfig
     defaults), loss = -sum(pi * log_softmax)/B + sum((z - v)^2)/B, gradients accumulated over chunks, then
     torch.optim.Adam(lr, weight_decay) -- the optimiser tch's nn::Adam {wd} builds.  TEST INFRASTRUCTURE (parity unpinned
     against the reference binary: libtorch 1.11 is not available here)."""
@@ -83,11 +83,11 @@ class RefTrainer:
         accumulation, fp32 BatchNorm arithmetic and fp32 weight gradients.  It separates "the kernels compute what
         autograd computes" (tight tolerance against this mode) from "bf16 storage costs precision" (loose tolerance
         against plain fp32)."""
-        assert arch == 6
+        assert arch in (5, 6)
         torch.backends.cudnn.allow_tf32 = False
         torch.backends.cuda.matmul.allow_tf32 = False
         self.emulate = emulate_bf16
-        self.arch, self.blocks, self.device = arch, 16, device
+        self.arch, self.blocks, self.device = arch, (16 if arch == 6 else 8), device
         self.names = [name for name, _ in W.spec(arch)]
         self.t = {}
         for k, v in W.split(np.array(blob, dtype=np.float32, copy=True), arch).items():
@@ -118,7 +118,10 @@ class RefTrainer:
             y = ra(F.relu(self._bn(conv(s, p + "conv1"), p + "bn1")))
             y = self._bn(conv(y, p + "conv2"), p + "bn2")
             s = ra(F.relu(y + s))
-        logits = F.conv2d(s, rw(t["policy_conv.weight"]), t["policy_conv.bias"], padding=1).reshape(s.shape[0], -1)
+        if self.arch == 6:
+            logits = F.conv2d(s, rw(t["policy_conv.weight"]), t["policy_conv.bias"], padding=1).reshape(s.shape[0], -1)
+        else:   # net5.rs:106-108
+            logits = F.linear(s.reshape(s.shape[0], -1), rw(t["policy_fc.weight"]), t["policy_fc.bias"])
         logp = torch.log_softmax(logits, dim=1)
         value = torch.tanh(F.linear(s.reshape(s.shape[0], -1), t["value_fc.weight"], t["value_fc.bias"]))
         return logp, value

@@ -1,4 +1,4 @@
-// Network::train for Net6 on the device: alpha-tak/src/model/network.rs:37-97 (train / train_inner:
+// Network::train for Net6 / Net5 on the device: alpha-tak/src/model/network.rs:37-97 (train / train_inner:
 // loss = -sum(pi*logp)/B + sum((z-v)^2)/B accumulated over chunks, Adam lr 1e-4 wd 1e-4 every CHUNKS_IN_STEP chunks) over
 // forward_training (net6.rs:111-122; BatchNorm on batch statistics) and its backward pass, which the reference gets from
 // libtorch autograd.  fp32 master weights / gradients / Adam moments in the weight-blob layout (net6.rs:39-57), bf16
@@ -10,6 +10,7 @@
 #include <cmath>
 
 #include "conv_tc3.cuh"
+#include "fc_tc.cuh"
 #include "net.hpp"
 #include "net_kernels.cuh"
 #include "train_kernels.cuh"
@@ -25,7 +26,8 @@ struct TrainLayer {
 };
 
 struct TrainState {
-    int n = 6, c_in = 0, blocks = 16, policy_ch = 251, nsq = 36;
+    int arch = 6, n = 6, c_in = 0, blocks = 16, policy_ch = 251, nsq = 36;
+    int policy_out = 0;       // policy vector length (Net5: the FC head's 1575 outputs)
     int64_t elems = 0;
     size_t pw_off = 0, pb_off = 0, vw_off = 0, vb_off = 0;
     std::vector<TrainLayer> layers;                 // 1 + 2 * blocks
@@ -34,6 +36,9 @@ struct TrainState {
     DevBuf x0, g[2], dy, dy2, dt, g2, dlogits;
     DevBuf bn_sums, bn_mean, bn_rstd, bwd_sums;
     DevBuf logits, partials, stats, values, dpre, loss, wg_scratch;
+    // Net5 (FC policy head, fc_tc.cuh): operand images of W, repacked activations / gradients, GEMM outputs
+    DevBuf fc_wp, fc_wpt, fc_x, fc_dlx, fc_dla, fc_s2, fc_ds, fc_dwt, fc_zero_bias;
+    int fc_bpad = 0, fc_kpad = 0;
     DevBuf in_stage, pi_stage, z_stage;
     int cap_boards = 0, S = 0;
     int steps = 0;          // Adam steps taken
@@ -49,7 +54,7 @@ struct TrainState {
 
 static TrainState* train_of(tak_engine* e);
 
-static int tiles_for6(int boards) { return SlotMap<6>::tiles(boards); }
+static int tiles_for(int n, int boards) { return n == 5 ? SlotMap<5>::tiles(boards) : SlotMap<6>::tiles(boards); }
 
 static void build_layout(TrainState& t) {
     size_t off = 0;
@@ -83,8 +88,13 @@ static void build_layout(TrainState& t) {
         bn(L1);
         bn(L2);
     }
-    t.pw_off = tensor(size_t(t.policy_ch) * 128 * 9, true);
-    t.pb_off = tensor(size_t(t.policy_ch), true);
+    if (t.arch == 6) {   // policy conv (net6.rs:56)
+        t.pw_off = tensor(size_t(t.policy_ch) * 128 * 9, true);
+        t.pb_off = tensor(size_t(t.policy_ch), true);
+    } else {             // policy FC (net5.rs:56-61)
+        t.pw_off = tensor(size_t(t.policy_out) * 128 * t.nsq, true);
+        t.pb_off = tensor(size_t(t.policy_out), true);
+    }
     t.vw_off = tensor(size_t(128) * t.nsq, true);
     t.vb_off = tensor(1, true);
     t.elems = int64_t(off);
@@ -102,7 +112,16 @@ static int repack(tak_engine* e, TrainState& t) {
             k_pack_conv_train<<<blocks, 256, 0, e->stream>>>(m + L.w_off, 128, 128, 0, 0, 1, L.w_dgrad.as<__nv_bfloat16>());
         t.launches += 3;
     }
-    for (int grp = 0; grp < 2; ++grp) {
+    if (t.arch == 5) {
+        const int J = t.policy_out, K = 128 * t.nsq, P = (J + 127) / 128;
+        const size_t n_fwd = size_t(P) * 128 * t.nsq * 128, n_dg = size_t(K) * P * 128;
+        k_fc_pack_fwd<<<unsigned((n_fwd + 255) / 256), 256, 0, e->stream>>>(m + t.pw_off, J, t.nsq, P,
+                                                                            t.fc_wp.as<__nv_bfloat16>());
+        k_fc_pack_dgrad<<<unsigned((n_dg + 255) / 256), 256, 0, e->stream>>>(m + t.pw_off, J, K, P,
+                                                                             t.fc_wpt.as<__nv_bfloat16>());
+        t.launches += 2;
+    }
+    for (int grp = 0; grp < (t.arch == 6 ? 2 : 0); ++grp) {
         k_pack_conv_train<<<blocks, 256, 0, e->stream>>>(m + t.pw_off, t.policy_ch, 128, grp * 128, 0, 0,
                                                          t.pol_w_fwd[grp].as<__nv_bfloat16>());
         k_pack_bias_train<<<1, 128, 0, e->stream>>>(m + t.pb_off, t.policy_ch, grp * 128, t.pol_bias[grp].as<float>());
@@ -117,7 +136,7 @@ static int repack(tak_engine* e, TrainState& t) {
 
 static int ensure_capacity(tak_engine* e, TrainState& t, int boards) {
     if (boards <= t.cap_boards) return TAK_OK;
-    const int tiles = tiles_for6(boards);
+    const int tiles = tiles_for(t.n, boards);
     const int S = tiles * C3_TILE_M;
     const size_t plane = size_t(S) * 256;   // 16 chunks x S slots x 16 B
     auto planes = [&](DevBuf& b, int stacks) -> cudaError_t {
@@ -136,9 +155,22 @@ static int ensure_capacity(tak_engine* e, TrainState& t, int boards) {
     TB_CUDA(planes(t.dy2, 1));
     TB_CUDA(planes(t.dt, 1));
     TB_CUDA(planes(t.g2, 1));
-    TB_CUDA(planes(t.dlogits, 2));
-    TB_CUDA(t.logits.ensure(size_t(256) * S * 4));
-    TB_CUDA(t.partials.ensure(size_t(8) * S * 8));
+    if (t.arch == 6) {
+        TB_CUDA(planes(t.dlogits, 2));
+        TB_CUDA(t.logits.ensure(size_t(256) * S * 4));
+        TB_CUDA(t.partials.ensure(size_t(8) * S * 8));
+    } else {
+        const int J = t.policy_out, K = 128 * t.nsq, P = (J + 127) / 128;
+        t.fc_bpad = (boards + FC_NT - 1) / FC_NT * FC_NT;
+        t.fc_kpad = (K + FC_NT - 1) / FC_NT * FC_NT;
+        TB_CUDA(t.logits.ensure(size_t(boards) * J * 4));
+        TB_CUDA(t.fc_x.ensure(size_t(t.nsq) * 16 * t.fc_bpad * 16));
+        TB_CUDA(t.fc_dlx.ensure(size_t(P) * 16 * t.fc_bpad * 16));
+        TB_CUDA(t.fc_dla.ensure(size_t(P) * (t.fc_bpad / 128) * FC_W_POS_BYTES));
+        TB_CUDA(t.fc_s2.ensure(size_t(t.fc_bpad / 128) * 16 * t.fc_kpad * 16));
+        TB_CUDA(t.fc_ds.ensure(size_t(boards) * K * 4));
+        TB_CUDA(t.fc_dwt.ensure(size_t(K) * J * 4));
+    }
     TB_CUDA(t.stats.ensure(size_t(boards) * 8));
     TB_CUDA(t.values.ensure(size_t(boards) * 4));
     TB_CUDA(t.dpre.ensure(size_t(boards) * 4));
@@ -149,7 +181,7 @@ static int ensure_capacity(tak_engine* e, TrainState& t, int boards) {
 
 template <int N>
 static int train_chunk_t(tak_engine* e, TrainState& t, const float* d_in, const float* d_pi, const float* d_z, int B) {
-    const int tiles = tiles_for6(B);
+    const int tiles = tiles_for(N, B);
     const int S = t.S;
     float* master = t.master.as<float>();
     float* grad = t.grad.as<float>();
@@ -207,6 +239,64 @@ static int train_chunk_t(tak_engine* e, TrainState& t, const float* d_in, const 
         t.launches += 1;
     }
     const bf* trunk = t.layers[nl - 1].z.as<bf>();
+    bf* g = t.g[0].as<bf>();
+    bf* g_alt = t.g[1].as<bf>();
+    const int wblocks = (B + 7) / 8;
+    if constexpr (N == 5) {
+        // ---- Net5 heads: FC policy (net5.rs:106-108) + value; loss; head gradients -- three GEMMs on fc_tc_kernel ----
+        const int J = t.policy_out, K = 128 * N * N, P = (J + 127) / 128, b_pad = t.fc_bpad, k_pad = t.fc_kpad;
+        auto gemm = [&](const bf* a, const bf* x, float* out, int n_out, int n, int n_pad, int n_pos, cudaStream_t st) -> int {
+            FcParams fp{};
+            fp.wp = a; fp.x = x; fp.bias = t.fc_zero_bias.as<float>(); fp.logits = out;
+            fp.n_out = n_out; fp.boards = n; fp.b_pad = n_pad; fp.n_pos = n_pos;
+            fp.j_tiles = (n_out + 127) / 128; fp.n_tiles = n_pad / FC_NT;
+            TB_CUDA(fc_tc_launch(fp, e->num_sms, st));
+            t.launches++;
+            return TAK_OK;
+        };
+        {   // forward: logits[b][j] = bias[j] + W s
+            const size_t items = size_t(N * N) * 16 * b_pad;
+            k_fc_repack<N><<<unsigned((items + 255) / 256), 256, 0, e->stream>>>(trunk, S, B, b_pad, t.fc_x.as<bf>());
+            FcParams fp{};
+            fp.wp = t.fc_wp.as<bf>(); fp.x = t.fc_x.as<bf>(); fp.bias = master + t.pb_off; fp.logits = t.logits.as<float>();
+            fp.n_out = J; fp.boards = B; fp.b_pad = b_pad; fp.n_pos = N * N; fp.j_tiles = P; fp.n_tiles = b_pad / FC_NT;
+            TB_CUDA(fc_tc_launch(fp, e->num_sms, e->stream));
+            k_policy_stats_dense<<<B, 256, 0, e->stream>>>(t.logits.as<float>(), J, t.stats.as<float2>(), nullptr);
+            k_value_train<N><<<wblocks, 256, 0, e->stream>>>(trunk, S, master + t.vw_off, master + t.vb_off, B,
+                                                             t.values.as<float>());
+            t.launches += 4;
+        }
+        TB_CUDA(cudaMemsetAsync(t.loss.p, 0, 16, e->stream));
+        TB_CUDA(cudaMemsetAsync(t.fc_dlx.p, 0, t.fc_dlx.bytes, e->stream));
+        TB_CUDA(cudaMemsetAsync(t.fc_dla.p, 0, t.fc_dla.bytes, e->stream));
+        k_fc_loss_grad<<<B, 256, 0, e->stream>>>(t.logits.as<float>(), J, t.stats.as<float2>(), d_pi, B, b_pad,
+                                                 t.fc_dlx.as<bf>(), t.fc_dla.as<bf>(), t.loss.as<double>());
+        k_planes_colsum<<<dim3(BNR_SPLIT, P * 16), 256, 0, e->stream>>>(t.fc_dlx.as<bf>(), b_pad, J, grad + t.pb_off);
+        k_value_loss_grad<<<(B + 255) / 256, 256, 0, e->stream>>>(t.values.as<float>(), d_z, B, t.dpre.as<float>(),
+                                                                  t.loss.as<double>(), grad + t.vb_off);
+        k_value_wgrad<N><<<dim3(16 * N * N, 16), 128, 0, e->stream>>>(t.dpre.as<float>(), trunk, B, S, grad + t.vw_off);
+        t.launches += 4;
+        // wgrad: dW^T[k][j] = sum_b s[b][k] dl[b][j]  (on the wgrad stream), then grad W += (dW^T)^T
+        {
+            TB_CUDA(cudaEventRecord(t.ev_dy[0], e->stream));
+            TB_CUDA(cudaStreamWaitEvent(t.wstream, t.ev_dy[0], 0));
+            const size_t items = size_t(b_pad / 8) * k_pad;
+            k_fc_repack_wgrad<N><<<unsigned((items + 255) / 256), 256, 0, t.wstream>>>(trunk, S, B, b_pad, k_pad,
+                                                                                     t.fc_s2.as<bf>());
+            if (int r = gemm(t.fc_dla.as<bf>(), t.fc_s2.as<bf>(), t.fc_dwt.as<float>(), J, K, k_pad, b_pad / 128, t.wstream))
+                return r;
+            k_fc_wgrad_add<<<unsigned((size_t(J) * K + 255) / 256), 256, 0, t.wstream>>>(t.fc_dwt.as<float>(), J, K,
+                                                                                        grad + t.pw_off);
+            TB_CUDA(cudaEventRecord(t.ev_w[0], t.wstream));
+            t.launches += 2;
+        }
+        // dgrad: ds[b][k] = sum_j dl[b][j] W[j][k]; trunk gradient = ds + the value head's share
+        if (int r = gemm(t.fc_wpt.as<bf>(), t.fc_dlx.as<bf>(), t.fc_ds.as<float>(), K, B, b_pad, P, e->stream)) return r;
+        k_fc_ds_to_planes<N><<<ew_blocks, 256, 0, e->stream>>>(t.fc_ds.as<float>(), t.dpre.as<float>(), master + t.vw_off,
+                                                               B, S, g);
+        t.launches++;
+        TB_CUDA(cudaGetLastError());
+    } else {
     {   // policy conv -> fp32 logits + per-slot softmax partials (net6.rs:113-116); value head (net6.rs:117-121)
         ConvParams p{};
         conv_params_set_layout(p, N);
@@ -219,7 +309,6 @@ static int train_chunk_t(tak_engine* e, TrainState& t, const float* d_in, const 
             d.out_ch_valid = std::min(128, t.policy_ch - grp * 128); d.group = grp;
         }
         TB_CUDA(conv3x3_tc3_launch<false>(p, e->num_sms, e->stream));
-        const int wblocks = (B + 7) / 8;
         k_policy_stats_conv<N><<<wblocks, 256, 0, e->stream>>>(t.partials.as<float2>(), S, 8, B, t.stats.as<float2>());
         k_value_train<N><<<wblocks, 256, 0, e->stream>>>(trunk, S, master + t.vw_off, master + t.vb_off, B,
                                                          t.values.as<float>());
@@ -234,8 +323,6 @@ static int train_chunk_t(tak_engine* e, TrainState& t, const float* d_in, const 
     k_value_loss_grad<<<(B + 255) / 256, 256, 0, e->stream>>>(t.values.as<float>(), d_z, B, t.dpre.as<float>(),
                                                               t.loss.as<double>(), grad + t.vb_off);
     k_value_wgrad<N><<<dim3(16 * N * N, 16), 128, 0, e->stream>>>(t.dpre.as<float>(), trunk, B, S, grad + t.vw_off);
-    bf* g = t.g[0].as<bf>();
-    bf* g_alt = t.g[1].as<bf>();
     k_value_bwd_trunk<N><<<ew_blocks, 256, 0, e->stream>>>(t.dpre.as<float>(), master + t.vw_off, B, S, g);
     t.launches += 5;
     TB_CUDA(cudaGetLastError());
@@ -246,6 +333,7 @@ static int train_chunk_t(tak_engine* e, TrainState& t, const float* d_in, const 
     if (int r = wgrad(dl1, trunk, 128, t.pw_off, 128, t.policy_ch - 128, 1)) return r;
     if (int r = conv_lin(dl0, t.pol_w_dgrad[0].as<bf>(), t.zero_bias.as<float>(), g, g_alt, nullptr, C3_MAX_SLABS)) return r;
     if (int r = conv_lin(dl1, t.pol_w_dgrad[1].as<bf>(), t.zero_bias.as<float>(), g_alt, g, nullptr, C3_MAX_SLABS)) return r;
+    }   // N == 6 heads
     // ------------------------------------------------ trunk backward --------------------------------------------------
     // bn_backward(l, upstream gradient w.r.t. the layer's post-ReLU output) -> dy (gradient w.r.t. the raw conv output);
     // optionally the ReLU-masked upstream gradient (the residual connection's share)
@@ -309,7 +397,8 @@ void train_destroy(tak_engine* e) {
         for (DevBuf* b : {&t->pol_w_fwd[i], &t->pol_bias[i], &t->pol_w_dgrad[i], &t->g[i]}) b->release();
     for (DevBuf* b : {&t->master, &t->grad, &t->adam_m, &t->adam_v, &t->zero_bias, &t->x0, &t->dy, &t->dt, &t->g2,
                       &t->dy2, &t->dlogits, &t->bn_sums, &t->bn_mean, &t->bn_rstd, &t->bwd_sums, &t->logits, &t->partials, &t->stats, &t->values, &t->dpre, &t->loss, &t->wg_scratch,
-                      &t->in_stage, &t->pi_stage, &t->z_stage})
+                      &t->in_stage, &t->pi_stage, &t->z_stage, &t->fc_wp, &t->fc_wpt, &t->fc_x, &t->fc_dlx, &t->fc_dla,
+                      &t->fc_s2, &t->fc_ds, &t->fc_dwt, &t->fc_zero_bias})
         b->release();
     if (t->ev0) cudaEventDestroy(t->ev0);
     if (t->ev1) cudaEventDestroy(t->ev1);
@@ -326,8 +415,8 @@ extern "C" {
 int32_t net_train_begin(tak_engine_t* e, int32_t max_boards) {
     TB_CHECK(e && e->net, TAK_ERR_NO_NETWORK, "no network: call net_create first");
     NetState& ns = *e->net;
-    TB_CHECK(ns.arch == 6 && e->n == 6, TAK_ERR_BAD_ARG,
-             "training is implemented for Net6 (the reference trains only 6x6: train/src/main.rs:42-43)");
+    TB_CHECK((ns.arch == 6 && e->n == 6) || (ns.arch == 5 && e->n == 5), TAK_ERR_BAD_ARG,
+             "training needs a Net5 or Net6 engine (the DummyNet has no weights)");
     TB_CHECK(ns.loaded && int64_t(ns.blob_host.size()) == net_blob_elems(ns), TAK_ERR_NO_NETWORK,
              "load weights (net_load_weights) before net_train_begin");
     TB_CHECK(max_boards > 0, TAK_ERR_BAD_ARG, "max_boards must be positive");
@@ -335,9 +424,12 @@ int32_t net_train_begin(tak_engine_t* e, int32_t max_boards) {
     train_destroy(e);
     TrainState* t = new TrainState();
     ns.train = t;
+    t->arch = ns.arch;
+    t->n = e->n;
     t->c_in = ns.c_in;
     t->blocks = ns.blocks;
     t->policy_ch = ns.policy_ch;
+    t->policy_out = ns.policy_out;
     t->nsq = e->nsq;
     build_layout(*t);
     TB_CHECK(t->elems == net_blob_elems(ns), TAK_ERR_BAD_ARG, "internal: training layout does not match the blob");
@@ -354,7 +446,14 @@ int32_t net_train_begin(tak_engine_t* e, int32_t max_boards) {
         TB_CUDA(L.w_dgrad.ensure(C3_W_LAYER_ELEMS * 2));
         TB_CUDA(L.bias_fwd.ensure(512));
     }
-    for (int i = 0; i < 2; ++i) {
+    if (t->arch == 5) {
+        const int J = t->policy_out, K = 128 * t->nsq, P = (J + 127) / 128;
+        TB_CUDA(t->fc_wp.ensure(size_t(P) * t->nsq * FC_W_POS_BYTES));
+        TB_CUDA(t->fc_wpt.ensure(size_t(K / 128) * P * FC_W_POS_BYTES));
+        TB_CUDA(t->fc_zero_bias.ensure(size_t(K) * 4));
+        TB_CUDA(cudaMemsetAsync(t->fc_zero_bias.p, 0, size_t(K) * 4, e->stream));
+    }
+    for (int i = 0; i < (t->arch == 6 ? 2 : 0); ++i) {
         TB_CUDA(t->pol_w_fwd[i].ensure(C3_W_LAYER_ELEMS * 2));
         TB_CUDA(t->pol_w_dgrad[i].ensure(C3_W_LAYER_ELEMS * 2));
         TB_CUDA(t->pol_bias[i].ensure(512));
@@ -387,7 +486,7 @@ int32_t net_train_chunk(tak_engine_t* e, const float* inputs, const float* pi, c
     TB_CHECK(boards <= t->cap_boards, TAK_ERR_CAPACITY, "chunk of %d boards, net_train_begin reserved %d", boards,
              t->cap_boards);
     TB_CUDA(cudaSetDevice(e->device));
-    const size_t in_elems = size_t(boards) * t->c_in * t->nsq, pi_elems = size_t(boards) * t->policy_ch * t->nsq;
+    const size_t in_elems = size_t(boards) * t->c_in * t->nsq, pi_elems = size_t(boards) * t->policy_out;
     const float *d_in = inputs, *d_pi = pi, *d_z = z;
     TB_CUDA(cudaEventRecord(t->ev0, e->stream));
     if (!on_device) {
@@ -400,7 +499,8 @@ int32_t net_train_chunk(tak_engine_t* e, const float* inputs, const float* pi, c
         d_in = t->in_stage.as<float>(); d_pi = t->pi_stage.as<float>(); d_z = t->z_stage.as<float>();
     }
     const uint64_t before = t->launches;
-    if (int r = train_chunk_t<6>(e, *t, d_in, d_pi, d_z, boards)) return r;
+    if (int r = t->n == 5 ? train_chunk_t<5>(e, *t, d_in, d_pi, d_z, boards) : train_chunk_t<6>(e, *t, d_in, d_pi, d_z, boards))
+        return r;
     e->launches += t->launches - before;
     TB_CUDA(cudaEventRecord(t->ev1, e->stream));
     double loss[2] = {0, 0};

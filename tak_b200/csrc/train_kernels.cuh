@@ -449,3 +449,146 @@ static __global__ void k_adam(float* w, const float* grad, float* m, float* v, i
 }
 
 }  // namespace tb
+
+// ---- Net5: fully connected policy head (net5.rs:56-62,106-108) in training ----------------------------------------------
+// All three GEMMs of the head (forward, dgrad, wgrad) run on fc_tc_kernel (fc_tc.cuh), which computes
+//   out[n][m] = bias[m] + sum over (p, c < 128) of  A[m][p*128 + c] * X[p][c][n]
+// from the packed images  A -> Wp[m / 128][p][c / 16][(c / 8) % 2][m % 128][c % 8]   and   X -> [p][c / 8][n_pad][c % 8]:
+//   forward : m = output j,          n = board,            (p, c) = (board position, trunk channel)
+//   dgrad   : m = k = c*NSQ + pos,   n = board,            p*128 + c = j          (A = W^T, X = dlogits)
+//   wgrad   : m = output j,          n = k = c*NSQ + pos,  p*128 + c = board      (A = dlogits^T, X = trunk output^T)
+namespace tb {
+
+__device__ __forceinline__ size_t fc_a_index(int m, int kk, int P) {      // element (m, kk = p*128 + c) of an A image
+    const int mt = m >> 7, col = m & 127, p = kk >> 7, c = kk & 127;
+    return ((((size_t(mt) * P + p) * 8 + (c >> 4)) * 2 + ((c >> 3) & 1)) * 128 + col) * 8 + (c & 7);
+}
+__device__ __forceinline__ size_t fc_x_index(int n, int kk, int n_pad) {  // element (kk, n) of an X image
+    const int p = kk >> 7, c = kk & 127;
+    return ((size_t(p) * 16 + (c >> 3)) * n_pad + n) * 8 + (c & 7);
+}
+
+// forward / dgrad operand images of the fp32 master W[J][K] (K = 128*NSQ, column k = c*NSQ + pos)
+static __global__ void k_fc_pack_fwd(const float* w, int J, int NSQ, int m_tiles, __nv_bfloat16* wp) {
+    const size_t idx = size_t(blockIdx.x) * blockDim.x + threadIdx.x;     // (m = j, pos, c)
+    const size_t total = size_t(m_tiles) * 128 * NSQ * 128;
+    if (idx >= total) return;
+    const int c = int(idx % 128), pos = int((idx / 128) % NSQ), j = int(idx / (size_t(128) * NSQ));
+    const float v = j < J ? w[size_t(j) * 128 * NSQ + size_t(c) * NSQ + pos] : 0.f;
+    wp[fc_a_index(j, pos * 128 + c, NSQ)] = __float2bfloat16(v);
+}
+static __global__ void k_fc_pack_dgrad(const float* w, int J, int K, int P /*ceil(J/128)*/, __nv_bfloat16* wpt) {
+    const size_t idx = size_t(blockIdx.x) * blockDim.x + threadIdx.x;     // (m = k, kk = j)
+    const size_t total = size_t(K) * P * 128;
+    if (idx >= total) return;
+    const int j = int(idx % (size_t(P) * 128)), k = int(idx / (size_t(P) * 128));
+    const float v = j < J ? w[size_t(j) * K + k] : 0.f;
+    wpt[fc_a_index(k, j, P)] = __float2bfloat16(v);
+}
+
+// policy loss and gradient over dense logits [B][J] (log_softmax, network.rs:79): loss_p += -sum pi*logp / B;
+// dlogit = (softmax * sum(pi) - pi) / B written as bf16 in BOTH operand layouts: dl_x (X image, contraction over j: dgrad)
+// and dl_a (A image, contraction over boards: wgrad).  One block per board; both images are zeroed by the caller.
+static __global__ void __launch_bounds__(256) k_fc_loss_grad(const float* logits, int J, const float2* stats,
+                                                             const float* pi, int n_boards, int b_pad,
+                                                             __nv_bfloat16* dl_x, __nv_bfloat16* dl_a, double* loss) {
+    const int b = blockIdx.x;
+    const float2 st = stats[b];
+    const float log_sum = logf(st.y);
+    const float* row = logits + size_t(b) * J;
+    const float* p = pi + size_t(b) * J;
+    __shared__ float sh[8];
+    __shared__ float s_sum_pi;
+    float sum_pi = 0.f;
+    for (int j = threadIdx.x; j < J; j += blockDim.x) sum_pi += p[j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum_pi += __shfl_xor_sync(0xffffffffu, sum_pi, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = sum_pi;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w) t += sh[w];
+        s_sum_pi = t;
+    }
+    __syncthreads();
+    sum_pi = s_sum_pi;
+    const float inv_b = 1.0f / float(n_boards);
+    const int P = (J + 127) / 128, PB = b_pad / 128;
+    float nll = 0.f;
+    for (int j = threadIdx.x; j < J; j += blockDim.x) {
+        const float logp = row[j] - st.x - log_sum;
+        nll -= p[j] * logp;
+        const __nv_bfloat16 d = __float2bfloat16((expf(logp) * sum_pi - p[j]) * inv_b);
+        dl_x[fc_x_index(b, j, b_pad)] = d;
+        dl_a[fc_a_index(j, b, PB)] = d;
+    }
+    (void)P;
+    __syncthreads();
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nll += __shfl_xor_sync(0xffffffffu, nll, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = nll;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w) t += sh[w];
+        atomicAdd(&loss[0], double(t) * double(inv_b));
+    }
+}
+
+// trunk gradient = policy-head dgrad (ds[b][c*NSQ + pos], fp32 from the GEMM) + value-head gradient, as strip planes
+template <int N>
+__global__ void __launch_bounds__(256) k_fc_ds_to_planes(const float* ds, const float* dpre, const float* wv,
+                                                         int n_boards, int S, __nv_bfloat16* g) {
+    const size_t idx = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx >= size_t(16) * S) return;
+    using SM = SlotMap<N>;
+    constexpr int NSQ = N * N;
+    const int chunk = int(idx / S);
+    const size_t slot = idx % S;
+    float o[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (slot_valid<N>(slot, n_boards)) {
+        const int tile = int(slot >> 8), w = int(slot & 255);
+        const int ry = w / SM::PITCH, rem = w - ry * SM::PITCH;
+        const int bj = rem / SM::BW, rx = rem - bj * SM::BW;
+        const int b = tile * SM::BPT + bj, pos = ry * N + rx;
+        const float d = dpre[b];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int k = (chunk * 8 + j) * NSQ + pos;
+            o[j] = ds[size_t(b) * (128 * NSQ) + k] + d * wv[k];
+        }
+    }
+    *reinterpret_cast<uint4*>(g + idx * 8) = pack8(o);
+}
+
+// X image of the transposed trunk output for the FC wgrad: element (kk = board, n = k = c*NSQ + pos)
+template <int N>
+__global__ void __launch_bounds__(256) k_fc_repack_wgrad(const __nv_bfloat16* act, int S, int n_boards, int b_pad,
+                                                         int k_pad, __nv_bfloat16* x) {
+    const size_t idx = size_t(blockIdx.x) * blockDim.x + threadIdx.x;     // (board group of 8, k)
+    constexpr int NSQ = N * N, K = 128 * NSQ;
+    if (idx >= size_t(b_pad / 8) * k_pad) return;
+    const int k = int(idx % k_pad), bg = int(idx / k_pad);
+    float f[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (k < K) {
+        const int c = k / NSQ, pos = k % NSQ;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int b = bg * 8 + i;
+            if (b < n_boards)
+                f[i] = __bfloat162float(act[(size_t(c >> 3) * S + SlotMap<N>::slot(b, pos / N, pos % N)) * 8 + (c & 7)]);
+        }
+    }
+    // boards bg*8 .. bg*8+7 = contraction index kk: p = kk / 128, chunk = (kk % 128) / 8
+    *reinterpret_cast<uint4*>(x + fc_x_index(k, bg * 8, k_pad)) = pack8(f);
+}
+
+// grad W[j][k] += dWt[k][j]  (dWt = GEMM output [K][J] fp32)
+static __global__ void k_fc_wgrad_add(const float* dwt, int J, int K, float* grad_w) {
+    const size_t idx = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx >= size_t(J) * K) return;
+    const int j = int(idx % J), k = int(idx / J);
+    grad_w[size_t(j) * K + k] += dwt[idx];
+}
+
+}  // namespace tb
