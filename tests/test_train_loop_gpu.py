@@ -11,13 +11,14 @@ from tak_b200 import weights as W
 pytestmark = pytest.mark.gpu
 
 
-def test_training_loop_iteration(tmp_path):
+@pytest.mark.parametrize("n", [6, 5])
+def test_training_loop_iteration(tmp_path, n):
     G = 64
-    blob = W.random_weights(6, seed=5)
-    cur = tb.Engine(6, G, nodes_per_game=1 << 12, max_batch=G)
-    cand = tb.Engine(6, G, nodes_per_game=1 << 12, max_batch=G)
+    blob = W.random_weights(n, seed=5)
+    cur = tb.Engine(n, G, nodes_per_game=1 << 12, max_batch=G)
+    cand = tb.Engine(n, G, nodes_per_game=1 << 12, max_batch=G)
     for e in (cur, cand):
-        e.net_create(6)
+        e.net_create(n)
         e.net_load_weights(blob)
     sp = dict(rollouts=12, half_komi=4, instant_win=1, exploit_ply=6, noise_ply=8, max_plies=24, seed=3)
     lines = []
@@ -30,12 +31,12 @@ def test_training_loop_iteration(tmp_path):
     assert len(data) == 1
     with open(tmp_path / "_examples" / data[0]) as f:
         text = f.read().split("\n")
-    assert len(text) - 1 == len(examples) and tb.example_parse(text[0], 6).n_children == examples[0].n_children
+    assert len(text) - 1 == len(examples) and tb.example_parse(text[0], n).n_children == examples[0].n_children
     assert res is None and np.array_equal(blob1, blob) and len(examples) >= 200
     assert all(r.n_children > 0 and r.result in (-1.0, 0.0, 1.0) for r in examples)
     # the replay text format round-trips every record (example.rs:81-133)
     for r in examples[:20]:
-        back = tb.example_parse(tb.example_format(r), 6)
+        back = tb.example_parse(tb.example_format(r), n)
         # the text carries the position as TPS: komi and the reversible-ply counter are not part of it (tps.rs:37-96)
         assert tb.tps_format(back.state) == tb.tps_format(r.state)
         assert back.n_children == r.n_children and back.result == r.result
