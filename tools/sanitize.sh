@@ -14,8 +14,9 @@ run wgrad_memcheck memcheck ./build/wgrad_selftest 7 96 42
 run conv_memcheck memcheck ./build/conv_selftest 60 6
 run game_memcheck memcheck python -m pytest tests/test_game_gpu.py -x -q -k "wins or tps or error or known"
 run mcts_memcheck memcheck python -m pytest tests/test_mcts_gpu.py -x -q -k "reference_mcts or stepwise"
-run train_memcheck memcheck python -m pytest tests/test_train_gpu.py -x -q -k "losses"
 run player_memcheck memcheck python -m pytest tests/test_player_gpu.py tests/test_pit_gpu.py -x -q -k "batch4 or 5-5-4 or equals or counts"
 run perft_multi_memcheck memcheck python -m pytest tests/test_game_gpu.py -x -q -k "multi or surface or symmetrical or consistency"
+run train5_memcheck memcheck python -m pytest tests/test_train_gpu.py -x -q -k "losses"
+run net5_memcheck memcheck python -m pytest tests/test_net_gpu.py -x -q -k "5"
 run game_racecheck racecheck python -m pytest tests/test_game_gpu.py -x -q -k "wins or tps or error"
 cat gpurun_out/sanitizer.txt
