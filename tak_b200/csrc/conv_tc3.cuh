@@ -29,11 +29,12 @@
 // this arrangement (8 + 1 commits) 41.8 us; cta_group::2 with resident weights is bound by a ~100-cycle floor per N=128
 // instruction (58.8 us); the bytes of the weight stream itself are not the limit (a quarter of the bytes: same time).
 //
-// Warp roles (320 threads, 1 persistent CTA per SM):
+// Warp roles (352 threads, 1 persistent CTA per SM):
 //   warp 0     producer: cp.async.bulk of the stage's activation slab (2 x 4 KiB) and weight slab (36 KiB) -> full
 //   warp 1     TMEM allocator + single-thread tcgen05.mma issuer; tcgen05.commit -> empty / acc_full
 //   warps 2-9  epilogue: residual prefetch, tcgen05.ld (software pipelined) -> 8x8 shfl transpose -> +bias (+residual)
 //              -> ReLU -> pad mask -> bf16 strip planes, or fp32 logits + per-slot softmax partials (policy head)
+//   warp 10    janitor: L2-discards the dead input / residual tiles of finished work items (inference tower only)
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -66,7 +67,7 @@ constexpr int C3_W_SLAB_BYTES = 9 * 2 * 128 * 16;          // 36864: 9 taps x 16
 constexpr int C3_STAGE_BYTES = C3_SLAB_BYTES + C3_W_SLAB_BYTES;  // 48640
 constexpr int C3_STAGES = 4;                               // ring depth (one stage = one K-slab: activations + weights)
 constexpr int C3_MAX_SLABS = 8;                            // 128 input channels
-constexpr int C3_THREADS = 320;
+constexpr int C3_THREADS = 352;                            // producer, MMA issuer, 8 epilogue warps, janitor
 constexpr int C3_SMEM_BYTES = C3_STAGES * C3_STAGE_BYTES + 3072;
 constexpr size_t C3_W_LAYER_ELEMS = size_t(C3_MAX_SLABS) * 9 * 2 * 128 * 8;  // bf16 elements per packed layer
 constexpr int C3_TILE_ALIGN = 1;
@@ -96,7 +97,8 @@ struct ConvLayerDesc {
     int out_ch_offset;          // mode 2: first output channel of this 128-wide group
     int out_ch_valid;           // mode 2: number of real channels in this group (<=128)
     int group;                  // mode 2: group index for `partials`
-    int pad_;
+    int discard;                // bit 0: `in`, bit 1: `res` are dead after this layer -> their L2 lines are discarded
+                                // (never written back to HBM); only the fused inference tower sets it
     double* stats;              // mode 3: [2][128] {sum, sum of squares} per output channel, accumulated (or nullptr)
 };
 
@@ -343,7 +345,7 @@ static __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc3_kernel(const
                     if (etid < 128) bias_s[etid] = ld.bias[etid];
                     asm volatile("bar.sync 1, 256;" ::: "memory");
                     // the residual does not depend on the MMAs: the first chunk's 4 x 16 B are fetched before waiting for
-                    // the accumulator, the next chunk's while the current one is processed (registers: a 320-thread CTA
+                    // the accumulator, the next chunk's while the current one is processed (registers: a 352-thread CTA
                     // is allocated as 12 warps, i.e. 168 registers per thread at most).
                     // Plain (coherent) loads: these slots were stored by this very thread two layers ago.
                     auto load_res = [&](int cc, uint4 (&dst)[4]) {
@@ -508,6 +510,36 @@ static __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc3_kernel(const
                     if (L + 1 < p.n_layers) asm volatile("fence.proxy.async;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) mbar_arrive(BAR(C3B_READY + jj));
+                }
+            }
+        }
+    }
+
+    else if (warp == 10) {
+        // ===================== janitor =====================
+        // Dead activations: once the epilogue of a work item is done (READY), the tile's input (fully consumed by the
+        // MMAs) and / or residual are never read again before they are rewritten, so their L2 lines are dropped instead
+        // of being written back -- without this 70 % of the tower's intermediate activations reached HBM (1.6 GB per
+        // launch at 5328 boards, 0.68 GB with it).  Issued from this otherwise idle warp: the same discards issued by
+        // the epilogue warps made the (epilogue-bound) tower 5 % slower.  The warp follows every READY phase, flagged
+        // layer or not, so that it is never more than one phase behind.
+        uint32_t items_of[C3_GROUP] = {0, 0, 0};
+        for (int g = 0, j0 = 0; g < walk.n_groups; j0 += walk.group_size(g), ++g) {
+            const int gs = walk.group_size(g);
+            for (int L = 0; L < p.n_layers; ++L) {
+                const ConvLayerDesc& ld = p.layers[L];
+                for (int jj = 0; jj < gs; ++jj) {
+                    const int tile = tile0 + (j0 + jj) * int(gridDim.x);
+                    mbar_wait(BAR(C3B_READY + jj), items_of[jj] & 1);
+                    items_of[jj]++;
+                    if (ld.discard) {
+                        for (int idx = lane; idx < 16 * (C3_TILE_M / 8); idx += 32) {    // (chunk, 128-byte line of 8 slots)
+                            const size_t off = (static_cast<size_t>(idx >> 5) * p.S + static_cast<size_t>(tile) * C3_TILE_M +
+                                                (idx & 31) * 8) * 8;
+                            if (ld.discard & 1) l2_discard_128(ld.in + off);
+                            if ((ld.discard & 2) && ld.res) l2_discard_128(ld.res + off);
+                        }
+                    }
                 }
             }
         }

@@ -4,6 +4,7 @@
 #include "net.hpp"
 
 #include <cmath>
+#include <cstdlib>
 
 #include "conv_tc3.cuh"
 #include "fc_tc.cuh"
@@ -140,9 +141,9 @@ int net_ensure_capacity(tak_engine* e, int boards) {
     if (boards <= ns.cap_boards) return TAK_OK;
     const int tiles = tiles_for(ns.n, boards);
     const int S = tiles * C3_TILE_M;
-    for (int i = 0; i < 3; ++i) {
-        TB_CUDA(ns.act[i].ensure(size_t(S) * 256));
-        TB_CUDA(cudaMemsetAsync(ns.act[i].p, 0, size_t(S) * 256, e->stream));
+    for (DevBuf* b : {&ns.act[0], &ns.act[1], &ns.act[2], &ns.act_in}) {
+        TB_CUDA(b->ensure(size_t(S) * 256));
+        TB_CUDA(cudaMemsetAsync(b->p, 0, size_t(S) * 256, e->stream));
     }
     if (ns.arch == 6) {
         TB_CUDA(ns.logits.ensure(size_t(ns.policy_groups) * 128 * S * 4));
@@ -163,11 +164,12 @@ static int forward_t(tak_engine* e, const uint8_t* d_states, const int* d_index,
     if (int r = net_ensure_capacity(e, boards)) return r;
     const int tiles = tiles_for(N, boards);
     const int S = ns.cap_S;  // plane stride is fixed by the allocation
+    __nv_bfloat16* x_in = ns.act_in.as<__nv_bfloat16>();
     __nv_bfloat16* x = ns.act[0].as<__nv_bfloat16>();
     __nv_bfloat16* t = ns.act[1].as<__nv_bfloat16>();
     __nv_bfloat16* y = ns.act[2].as<__nv_bfloat16>();
     const int wblocks = (boards + 7) / 8;
-    k_encode<N><<<wblocks, 256, 0, e->stream>>>(d_states, d_index, boards, x, S);
+    k_encode<N><<<wblocks, 256, 0, e->stream>>>(d_states, d_index, boards, x_in, S);
     e->launches++;
     TB_CUDA(cudaGetLastError());
     // the whole conv tower (initial conv, residual blocks, Net6 policy conv groups) is ONE launch: conv_tc3.cuh
@@ -175,19 +177,20 @@ static int forward_t(tak_engine* e, const uint8_t* d_states, const int* d_index,
     conv_params_set_layout(p, N);
     p.S = S; p.tile_begin = 0; p.tile_end = tiles; p.n_boards = boards;
     auto conv = [&](const ConvLayer& L, const __nv_bfloat16* in, const __nv_bfloat16* res, __nv_bfloat16* out,
-                    int mode, int slabs, int grp, int ch_valid) {
+                    int mode, int slabs, int grp, int ch_valid, int discard = 0) {
         ConvLayerDesc& d = p.layers[p.n_layers++];
+        static const bool no_discard = std::getenv("TAK_NO_L2_DISCARD") != nullptr;   // A/B switch for measurements
+        d.discard = no_discard ? 0 : discard;
         d.in = in; d.res = res; d.out = out; d.out_f32 = ns.logits.as<float>(); d.partials = ns.partials.as<float2>();
         d.w = L.w.as<__nv_bfloat16>(); d.bias = L.bias.as<float>();
         d.slabs = slabs; d.mode = mode; d.out_ch_offset = grp * 128; d.out_ch_valid = ch_valid; d.group = grp;
     };
     // initial conv + BN + ReLU (net6.rs:72-76); only ceil(c_in/16) K-slabs carry input planes
-    conv(ns.layers[0], x, nullptr, y, CONV_RELU, (ns.c_in + 15) / 16, 0, 128);
-    std::swap(x, y);
+    conv(ns.layers[0], x_in, nullptr, x, CONV_RELU, (ns.c_in + 15) / 16, 0, 128);
     // residual tower (res_block.rs:14-22)
     for (int blk = 0; blk < ns.blocks; ++blk) {
         conv(ns.layers[1 + 2 * blk], x, nullptr, t, CONV_RELU, C3_MAX_SLABS, 0, 128);
-        conv(ns.layers[2 + 2 * blk], t, x, y, CONV_RES_RELU, C3_MAX_SLABS, 0, 128);
+        conv(ns.layers[2 + 2 * blk], t, x, y, CONV_RES_RELU, C3_MAX_SLABS, 0, 128, /*t and the block input are dead*/ 3);
         std::swap(x, y);
     }
     ns.trunk_out = x;
@@ -258,7 +261,7 @@ void net_destroy(tak_engine* e) {
     NetState& ns = *e->net;
     for (auto& L : ns.layers) { L.w.release(); L.bias.release(); }
     for (auto& L : ns.policy_layers) { L.w.release(); L.bias.release(); }
-    for (DevBuf* b : {&ns.fc_policy_w, &ns.fc_policy_b, &ns.fc_x, &ns.value_w, &ns.act[0], &ns.act[1], &ns.act[2], &ns.logits,
+    for (DevBuf* b : {&ns.fc_policy_w, &ns.fc_policy_b, &ns.fc_x, &ns.value_w, &ns.act[0], &ns.act[1], &ns.act[2], &ns.act_in, &ns.logits,
                       &ns.partials, &ns.stats, &ns.values, &ns.stage_states, &ns.stage_policy, &ns.stage_repr})
         b->release();
     delete e->net;

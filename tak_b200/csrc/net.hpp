@@ -34,7 +34,9 @@ struct NetState {
     float value_bias = 0.f;
     // activations
     int cap_boards = 0, cap_S = 0;
-    DevBuf act[3];                         // bf16 strip planes [16][S][8]
+    DevBuf act[3];                         // bf16 strip planes [16][S][8], rotating through the tower (each is fully
+                                           // rewritten by a conv epilogue before it is read: dead tiles are L2-discarded)
+    DevBuf act_in;                         // the encoded input planes (k_encode writes only real squares: never discarded)
     DevBuf logits;                         // Net6: fp32 [256][S]; Net5: fp32 [B][1575]
     DevBuf partials;                       // Net6: float2 [groups][S] per-slot softmax partials (conv epilogue)
     DevBuf stats;                          // float2 {max, sum exp} per board

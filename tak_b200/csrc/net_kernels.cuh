@@ -56,7 +56,8 @@ __device__ __forceinline__ float repr_plane(const ReprCtx<N>& cx, int ch, Col co
 }
 
 // one warp per board; `states` = packed records of the boards to encode (index list optional).  Pad columns and the
-// tile remainder are zero already: the planes are zero-filled at allocation and every conv epilogue rewrites them as 0.
+// tile remainder are zero already: the input planes (NetState::act_in) are zero-filled at allocation and only real
+// squares are ever written to them.
 // (launch bounds: at most 40 registers per thread, so that a block fits in the 11 776 registers a resident conv-tower
 // CTA of the OTHER engine replica leaves free on an SM -- at 42 the encode of one replica waited for the other's tower)
 template <int N>

@@ -63,6 +63,12 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
                  : "memory");
 }
 
+// The 128-byte line at `p` will not be read again before it is overwritten: L2 may drop the dirty data instead of
+// writing it back to HBM (a hint; reads after it return indeterminate data).
+__device__ __forceinline__ void l2_discard_128(const void* p) {
+    asm volatile("discard.global.L2 [%0], 128;" ::"l"(p) : "memory");
+}
+
 // ----------------------------------------------------------------------------------------------
 // tcgen05
 // ----------------------------------------------------------------------------------------------
