@@ -97,7 +97,8 @@ struct ConvLayerDesc {
     int out_ch_offset;          // mode 2: first output channel of this 128-wide group
     int out_ch_valid;           // mode 2: number of real channels in this group (<=128)
     int group;                  // mode 2: group index for `partials`
-    int discard;                // bit 0: `in`, bit 1: `res` are dead after this layer -> their L2 lines are discarded
+    int discard;                // bit 2: fp32 logits are stored with the streaming hint (st.global.cs)
+                                // bit 0: `in`, bit 1: `res` are dead after this layer -> their L2 lines are discarded
                                 // (never written back to HBM); only the fused inference tower sets it
     double* stats;              // mode 3: [2][128] {sum, sum of squares} per output channel, accumulated (or nullptr)
 };
@@ -413,9 +414,13 @@ static __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc3_kernel(const
                                 x[s4 + 1] = __float_as_uint(ch_ok ? o.y : -INFINITY);
                                 x[s4 + 2] = __float_as_uint(ch_ok ? o.z : -INFINITY);
                                 x[s4 + 3] = __float_as_uint(ch_ok ? o.w : -INFINITY);
-                                if (ch_ok)
-                                    *reinterpret_cast<float4*>(ld.out_f32 + static_cast<size_t>(ld.out_ch_offset + ch) * p.S +
-                                                               (slot0 - j) + 32 * cc + s4) = o;
+                                if (ch_ok) {
+                                    // the logits stream out (read later by other kernels, never by the tower): with the
+                                    // streaming hint they do not push the tower's live activation tiles out of L2
+                                    float4* dst = reinterpret_cast<float4*>(ld.out_f32 + static_cast<size_t>(ld.out_ch_offset + ch) * p.S +
+                                                                            (slot0 - j) + 32 * cc + s4);
+                                    if (ld.discard & 4) __stcs(dst, o); else *dst = o;
+                                }
                             }
                         }
                         // 8x8 block transpose across the 8 lanes of a channel chunk: x[8i+b] (channel j, slot 8i+b) ->

@@ -197,7 +197,7 @@ static int forward_t(tak_engine* e, const uint8_t* d_states, const int* d_index,
     if (ns.arch == 6)  // policy conv (net6.rs:99-100), 128 output channels per group
         for (int grp = 0; grp < ns.policy_groups; ++grp)
             conv(ns.policy_layers[grp], x, nullptr, nullptr, CONV_LOGITS_F32, C3_MAX_SLABS, grp,
-                 std::min(128, ns.policy_ch - grp * 128));
+                 std::min(128, ns.policy_ch - grp * 128), std::getenv("TAK_NO_STCS") ? 0 : 4);
     {
         NetProfile* prof = ns.profile;
         if (prof) TB_CUDA(cudaEventRecord(prof->ev[2 * prof->n], e->stream));
