@@ -534,7 +534,7 @@ def run_b200(args):
         "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"],
         # dram__bytes_read.sum + dram__bytes_write.sum of one tower launch over 5328 boards (ncu --set full,
         # profiles/r01_conv_tc3_ncu_full.txt), scaled to this launch's boards: logits + write-backs of the activations
-        "traffic": 1_804_369_024 * Gr / 5328,
+        "traffic": 829_248_512 * Gr / 5328,
         "peak_kind": "sustained bf16 (kernel timed in a back-to-back loop under the step's power cap, CUDA events around "
                      "each launch), " + pk["source"],
         "avg_launch_us": 1e3 * prof["ms_conv"] / prof["conv_launches"],
