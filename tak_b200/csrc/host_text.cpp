@@ -283,8 +283,15 @@ int32_t tak_tps_parse(int32_t n, const char* text, tak_state_t* out) {
     out->to_move = *p == '2';
     ++p;
     TB_CHECK(*p == ' ', TAK_ERR_PARSE, "bad TPS move number");
-    int mv = atoi(p + 1);
-    TB_CHECK(mv >= 1, TAK_ERR_PARSE, "bad TPS move number");
+    // exactly three space-separated segments (takparse's Tps::from_str refuses a wrong segment count); the move number
+    // is all digits; trailing blanks are tolerated
+    ++p;
+    TB_CHECK(*p >= '0' && *p <= '9', TAK_ERR_PARSE, "bad TPS move number");
+    long mv = 0;
+    while (*p >= '0' && *p <= '9' && mv < 100000) mv = mv * 10 + (*p++ - '0');
+    while (*p == ' ') ++p;
+    TB_CHECK(*p == 0, TAK_ERR_PARSE, "unexpected text after the TPS move number");
+    TB_CHECK(mv >= 1 && mv <= 30000, TAK_ERR_PARSE, "bad TPS move number");
     out->ply = uint16_t((mv - 1) * 2 + out->to_move);
     // reserves are inferred from the board (tps.rs:63-84)
     int ws = stones_for(n), wc = caps_for(n), bs = ws, bc = wc;
