@@ -124,6 +124,19 @@ int32_t tak_perft_multi(tak_engine_t* e, const tak_state_t* roots, int32_t n_roo
 /* timing hook for bench.py: device milliseconds (CUDA events on the engine stream) of the last tak_perft, and
  * the number of child states it materialised / kernels it launched */
 int32_t tak_perft_stats(tak_engine_t* e, double* out_ms, uint64_t* out_materialised, uint64_t* out_launches);
+/* finer timing of the last tak_perft, CUDA events on the engine stream: out6 = { ms of the whole call, ms spent in the
+ * expansion kernel pairs (move lists + apply/classify), child states materialised, kernels launched, children of the
+ * largest single expansion, ms of that expansion } -- the roofline of movegen + play is computed from [4] and [5] */
+int32_t tak_perft_profile(tak_engine_t* e, double* out6);
+/* Random playouts on the device (workload A; the uniform-random playout loop of tak/tests/tps.rs:26-96
+ * and symm.rs:3-68, `moves[seed % len]`, with a counter-based seed): every game in [first, first+count) is played from
+ * its current position until Game::result() != Ongoing or it has added max_plies + (hash(game) % ply_spread) plies;
+ * move = possible_moves()[splitmix64(seed ^ splitmix64(global_id << 32 | ply)) % len], global_id = game_id_base + slot.
+ * out_plies[count] / out_results[count] may be NULL; out_totals2 = { plies played, legal moves generated } summed over
+ * the games; out_ms = device milliseconds of the playout kernel. */
+int32_t tak_playouts(tak_engine_t* e, int32_t first, int32_t count, uint64_t seed, int32_t game_id_base, int32_t max_plies,
+                     int32_t ply_spread, int32_t* out_plies, uint8_t* out_results, uint64_t* out_totals2,
+                     double* out_ms);
 
 /* ---- host-side (cold) helpers: takparse surface ---------------------------------------------------
  * tak_move_index         alpha_tak::search::move_index (move_map.rs:19-48)
@@ -154,6 +167,9 @@ int32_t net_load_weights_device(tak_engine_t* e, const void* device_blob, int64_
 int32_t net_input_channels(int32_t n, int32_t* out_channels);
 int32_t net_game_repr(tak_engine_t* e, const tak_state_t* states, int32_t b, float* out);
 int32_t net_policy_eval(tak_engine_t* e, const tak_state_t* states, int32_t b, float* out_policy, float* out_value);
+/* the same forward pass, but out_logits[B][policy_size] holds the PRE-softmax policy logits (net6.rs:99-100 / net5.rs:108
+ * before `softmax`): the surface the network tolerance is stated on (max abs 1e-2 against an fp32 forward) */
+int32_t net_policy_logits(tak_engine_t* e, const tak_state_t* states, int32_t b, float* out_logits, float* out_value);
 /* device-resident variant used by bench.py `value`: evaluates the states of games [first, first+count) in place;
  * returns device milliseconds for `reps` forward passes */
 int32_t net_forward_timed(tak_engine_t* e, int32_t first, int32_t count, int32_t reps, double* out_ms);
@@ -238,6 +254,10 @@ typedef struct tak_move_info_t {
 int32_t mcts_debug(tak_engine_t* e, int32_t id, int32_t depth, tak_move_info_t* out, int32_t cap, int32_t* out_count);
 
 int32_t mcts_pick_move(tak_engine_t* e, const int32_t* ids, int32_t n, uint16_t* out_moves);
+/* Node::pick_move(exploitation=false) (play.rs:60-65): a child drawn with probability visits / sum(visits) -- the
+ * reference draws from thread_rng; here r = splitmix64(seed ^ splitmix64(game id)) % sum(visits) selects the first
+ * child whose cumulative visit count exceeds r (same draw the device self-play loop makes below EXPLOIT_PLIES) */
+int32_t mcts_pick_move_sampled(tak_engine_t* e, const int32_t* ids, int32_t n, uint64_t seed, uint16_t* out_moves);
 int32_t mcts_play(tak_engine_t* e, const int32_t* ids, const uint16_t* moves, int32_t n);
 int32_t mcts_apply_dirichlet(tak_engine_t* e, const int32_t* ids, int32_t n, float alpha, float ratio,
                              uint64_t seed);
@@ -269,10 +289,14 @@ typedef struct tak_selfplay_stats {
     uint64_t records;            /* replay records produced */
     double device_ms;            /* CUDA-event time of the whole call */
     double net_ms;               /* CUDA-event time spent in network kernels */
+    uint64_t records_truncated;  /* roots with more than TAK_REPLAY_MAX_CHILDREN children (the call fails if > 0) */
+    uint64_t reserved[3];
 } tak_selfplay_stats_t;
 
-/* fixed-size replay record == alpha_tak::Example (example.rs:28-33) */
-#define TAK_REPLAY_MAX_CHILDREN 256
+/* fixed-size replay record == alpha_tak::Example (example.rs:28-33).  512 (move, visits) pairs: random play peaks at
+ * 135 / 194 / 220 legal moves on 5x5 / 6x6 / 8x8.  A root with more children than that is never
+ * truncated silently: selfplay_step fails with TAK_ERR_CAPACITY and tak_selfplay_stats_t::records_truncated counts it. */
+#define TAK_REPLAY_MAX_CHILDREN 512
 typedef struct tak_replay_record {
     int32_t game_id;            /* global game id */
     int32_t game_serial;        /* how many games this slot had completed before */

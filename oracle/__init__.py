@@ -69,6 +69,7 @@ def lib():
             "orc_game_from_state": (vp, [C.POINTER(TakState)]),
             "orc_game_set_half_komi": (None, [vp, i32]),
             "orc_game_flat_diff": (i32, [vp]),
+            "orc_selfplay_instant_win": (i32, [vp, C.POINTER(u16), C.POINTER(C.c_uint32), i32, C.POINTER(i32)]),
             "orc_perft": (u64, [vp, i32]),
             "orc_perft_mt": (u64, [vp, i32, i32]),
             "orc_parse_move": (i32, [C.c_char_p, i32]),
@@ -201,6 +202,13 @@ class Game:
 
     def set_half_komi(self, hk: int):
         lib().orc_game_set_half_komi(self._h, hk)
+
+    def instant_win_policy(self):
+        """self_play.rs:121-140: ([(move, 1000 if it wins on the spot else 1)], any win)."""
+        mv, vis = (C.c_uint16 * 4096)(), (C.c_uint32 * 4096)()
+        win = C.c_int(0)
+        k = lib().orc_selfplay_instant_win(self._h, mv, vis, 4096, C.byref(win))
+        return [(mv[i], vis[i]) for i in range(k)], bool(win.value)
 
     def perft(self, depth: int, threads: int = 1) -> int:
         if threads > 1:

@@ -16,6 +16,9 @@ from tak_b200 import weights as W
 
 class RefNet:
     def __init__(self, arch: int, blob: np.ndarray, device="cpu"):
+        # an fp32 reference: no TF32 in cuDNN convolutions / cuBLAS matmuls when it runs on a GPU
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
         self.arch = arch
         self.n = arch
         self.blocks = 16 if arch == 6 else 8

@@ -87,6 +87,31 @@ void orc_game_set_half_komi(void* g, int hk) { static_cast<Game*>(g)->half_komi 
 int orc_game_flat_diff(void* g) { return static_cast<Game*>(g)->flat_diff(); }
 uint64_t orc_perft(void* g, int depth) { return perft(*static_cast<Game*>(g), depth); }
 
+// "Play winning moves if there are any" -- the scan of train/src/self_play.rs:121-140 for ONE worker slot:
+// policy = possible_moves().map(|m| (m, if clone.play(m).result() == Winner{color == inner_game.to_move} {1000} else {1}))
+// Returns the number of moves; *win = whether any move wins on the spot.
+int orc_selfplay_instant_win(void* g, uint16_t* out_moves, uint32_t* out_visits, int cap, int* win) {
+    const Game& inner_game = *static_cast<Game*>(g);
+    bool w = false;
+    auto moves = inner_game.possible_moves();
+    for (size_t i = 0; i < moves.size(); ++i) {
+        Game clone = inner_game;
+        clone.play(moves[i]);
+        const GameResult r = clone.result();
+        uint32_t visits = 1;  // at least one visit for all possible moves
+        if (r.is_winner() && r.winner() == inner_game.to_move) {
+            w = true;
+            visits = 1000;    // high fake visits for winning moves
+        }
+        if (int(i) < cap) {
+            out_moves[i] = moves[i].encode(inner_game.n);
+            out_visits[i] = visits;
+        }
+    }
+    *win = w ? 1 : 0;
+    return int(moves.size());
+}
+
 // perft split over root moves on `threads` host threads (CPU-baseline leg; same counting rule)
 uint64_t orc_perft_mt(void* g, int depth, int threads) {
     Game& game = *static_cast<Game*>(g);

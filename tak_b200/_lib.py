@@ -7,7 +7,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libtaknative.so")
 
-TAK_REPLAY_MAX_CHILDREN = 256
+TAK_REPLAY_MAX_CHILDREN = 512
 
 
 class TakState(C.Structure):
@@ -71,6 +71,8 @@ class SelfplayStats(C.Structure):
         ("records", C.c_uint64),
         ("device_ms", C.c_double),
         ("net_ms", C.c_double),
+        ("records_truncated", C.c_uint64),
+        ("reserved", C.c_uint64 * 3),
     ]
 
 
@@ -120,6 +122,9 @@ SYMBOLS = {
     "tak_perft": (_i32, [_vp, _P(TakState), _i32, _P(_u64)]),
     "tak_perft_multi": (_i32, [_vp, _P(TakState), _i32, _i32, _P(_u64)]),
     "tak_perft_stats": (_i32, [_vp, _P(C.c_double), _P(_u64), _P(_u64)]),
+    "tak_perft_profile": (_i32, [_vp, _P(C.c_double)]),
+    "tak_playouts": (_i32, [_vp, _i32, _i32, _u64, _i32, _i32, _i32, _P(_i32), _P(C.c_uint8), _P(_u64),
+                            _P(C.c_double)]),
     "tak_move_index": (_i32, [_i32, _u16, _P(_i32)]),
     "tak_policy_size": (_i32, [_i32, _P(_i32)]),
     "tak_ptn_parse": (_i32, [_i32, C.c_char_p, _P(_u16)]),
@@ -134,6 +139,7 @@ SYMBOLS = {
     "net_input_channels": (_i32, [_i32, _P(_i32)]),
     "net_game_repr": (_i32, [_vp, _P(TakState), _i32, _P(_f32)]),
     "net_policy_eval": (_i32, [_vp, _P(TakState), _i32, _P(_f32), _P(_f32)]),
+    "net_policy_logits": (_i32, [_vp, _P(TakState), _i32, _P(_f32), _P(_f32)]),
     "net_forward_timed": (_i32, [_vp, _i32, _i32, _i32, _P(C.c_double)]),
     "net_forward_profile": (_i32, [_vp, _i32, _i32, _i32, _P(C.c_double)]),
     "net_train_begin": (_i32, [_vp, _i32]),
@@ -155,6 +161,7 @@ SYMBOLS = {
     "mcts_root": (_i32, [_vp, _i32, _P(C.c_uint32), _P(C.c_uint32), _P(_f32)]),
     "mcts_debug": (_i32, [_vp, _i32, _i32, _P(MoveInfoRecord), _i32, _P(_i32)]),
     "mcts_pick_move": (_i32, [_vp, _P(_i32), _i32, _P(_u16)]),
+    "mcts_pick_move_sampled": (_i32, [_vp, _P(_i32), _i32, _u64, _P(_u16)]),
     "mcts_play": (_i32, [_vp, _P(_i32), _P(_u16), _i32]),
     "mcts_apply_dirichlet": (_i32, [_vp, _P(_i32), _i32, _f32, _f32, _u64]),
     "selfplay_begin": (_i32, [_vp, _P(SelfplayConfig)]),

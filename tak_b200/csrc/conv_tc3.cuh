@@ -119,6 +119,9 @@ struct ConvParams {
     int S;                      // plane stride in slots (= allocated tiles * 256)
     int tile_begin, tile_end;   // tiles to process
     int n_boards;
+    const int* n_boards_dev;    // if set: the number of boards is read from device memory when the kernel starts (the
+                                // search loop counts its leaves on the device; tile_end = tile_begin + tiles(boards) and
+                                // the launch is sized for the largest batch) -- no host round trip per evaluation
     int n;                      // board size N
     int bw;                     // N + 1
     int bpt;                    // boards per tile
@@ -154,9 +157,9 @@ __device__ __forceinline__ void transpose8_stage(uint32_t (&x)[32], int j) {
 // work-item walk shared by the three roles: groups of tiles, all layers per group
 struct TowerWalk {
     int n_my, n_groups, base, rem;
-    __device__ TowerWalk(const ConvParams& p) {
+    __device__ TowerWalk(const ConvParams& p, int tile_end) {
         const int first = p.tile_begin + blockIdx.x;
-        n_my = first < p.tile_end ? (p.tile_end - 1 - first) / int(gridDim.x) + 1 : 0;
+        n_my = first < tile_end ? (tile_end - 1 - first) / int(gridDim.x) + 1 : 0;
         n_groups = (n_my + C3_GROUP - 1) / C3_GROUP;
         base = n_groups ? n_my / n_groups : 0;
         rem = n_groups ? n_my % n_groups : 0;
@@ -212,7 +215,14 @@ static __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc3_kernel(const
     const uint32_t tmem_base = *tmem_slot;
 
     const size_t plane_bytes = static_cast<size_t>(p.S) * 16;
-    const TowerWalk walk(p);
+    int n_boards = p.n_boards, tile_end = p.tile_end;
+    if (p.n_boards_dev != nullptr) {
+        griddep_wait();   // the count is written by the kernel before this one
+        n_boards = *reinterpret_cast<const volatile int*>(p.n_boards_dev);
+        const int t = (n_boards + p.bpt - 1) / p.bpt;
+        tile_end = p.tile_begin + (t < p.tile_end - p.tile_begin ? t : p.tile_end - p.tile_begin);
+    }
+    const TowerWalk walk(p, tile_end);
     const int tile0 = p.tile_begin + blockIdx.x;
 
     if (warp == 0) {
@@ -338,7 +348,7 @@ static __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc3_kernel(const
                     uint32_t valid_mask = 0;
 #pragma unroll
                     for (int idx = 0; idx < 16; ++idx)
-                        if (((frame_mask >> idx) & 1) && tile * p.bpt + int((board_of >> (4 * idx)) & 15) < p.n_boards)
+                        if (((frame_mask >> idx) & 1) && tile * p.bpt + int((board_of >> (4 * idx)) & 15) < n_boards)
                             valid_mask |= 1u << idx;
                     // bias of this layer -> shared (double buffered by accumulator stage; the named barrier keeps the
                     // 256 epilogue threads within one work item of each other)

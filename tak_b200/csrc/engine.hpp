@@ -101,12 +101,21 @@ struct tak_engine {
     // perft
     static constexpr int PF_LEVELS = 13;
     struct PerftLevel {
-        tb::DevBuf children, counts, offsets, moves;
+        tb::DevBuf children, counts, offsets, moves, block_parent;
     };
     PerftLevel pf_level[PF_LEVELS];
-    tb::DevBuf pf_root, pf_scan_tmp, pf_leaves;
+    tb::DevBuf pf_root, pf_root_counts, pf_scan_tmp, pf_leaves;
     double pf_ms = 0;
     uint64_t pf_materialised = 0, pf_launches = 0;
+    // CUDA-event spans around each (k_perft_moves, k_perft_apply) pair of the last tak_perft (tak_perft_profile)
+    static constexpr int PF_SPANS = 64;
+    cudaEvent_t pf_span_ev[2 * PF_SPANS] = {};
+    uint64_t pf_span_children[PF_SPANS] = {};
+    int pf_n_spans = 0;
+    double pf_expand_ms = 0, pf_top_span_ms = 0;
+    uint64_t pf_top_span_children = 0;
+    // random playouts (tak_playouts)
+    tb::DevBuf po_plies, po_result, po_totals;
 
     tb::NetState* net = nullptr;
     tb::MctsState* mcts = nullptr;

@@ -90,54 +90,48 @@ static int check_ids(tak_engine_t* e, const int32_t* ids, int32_t n) {
 }
 
 // ---- perft: breadth-first over packed frontiers ---------------------------------------------------------------
-// Level k frontier -> count kernel (result + move count per parent, run ONCE per frontier) -> exclusive scan ->
-// expand kernel writing the children in move-generation order.  The last level only counts (perft.rs:6-7), finished
+// Roots -> count kernel (result + move count per root).  Then per level: exclusive scan of the parents' child counts ->
+// k_perft_moves (move lists + block map) -> k_perft_apply (children written in move-generation order AND classified /
+// counted in the same pass, game_kernels.cuh).  The last level's counts are perf_count's answer (perft.rs:6-7), finished
 // games count 1 (perft.rs:4).  When a frontier's children exceed PF_CAP states, the parents are cut into slices by
 // binary search on the scanned offsets and each slice is expanded and recursed into separately, so memory is bounded
 // by PF_CAP states per level.
 static constexpr size_t PF_CAP = size_t(1) << 24;
 
+// `frontier` holds n parents at `depth_left` >= 2 plies above the counted level; counts[i] = children of parent i
 template <int N>
-static int perft_level(tak_engine* e, const uint8_t* frontier, size_t n, int depth_left, int level,
-                       unsigned long long* d_leaves) {
+static int perft_level(tak_engine* e, const uint8_t* frontier, size_t n, const uint32_t* d_counts, int depth_left,
+                       int level, unsigned long long* d_leaves) {
+    using P = PerftCfg<N>;
     constexpr int S = StateLayout<N>::S;
     TB_CHECK(level < tak_engine::PF_LEVELS, TAK_ERR_BAD_ARG, "perft too deep");
     TB_CHECK(n < (size_t(1) << 31), TAK_ERR_CAPACITY, "perft frontier too large");
-    const bool last = depth_left == 1;
     tak_engine::PerftLevel& lv = e->pf_level[level];
-    uint32_t* d_counts = nullptr;
-    if (!last) {
-        TB_CUDA(lv.counts.ensure(n * 4));
-        TB_CUDA(lv.offsets.ensure(n * 8));
-        d_counts = lv.counts.as<uint32_t>();
-    }
-    k_perft_count<N><<<(unsigned(n) + 255) / 256, 256, 0, e->stream>>>(frontier, int(n), last ? 1 : 0, d_counts, d_leaves);
-    e->pf_launches++;
-    TB_CUDA(cudaGetLastError());
-    if (last) return TAK_OK;
+    TB_CUDA(lv.offsets.ensure(n * 8));
     uint64_t* d_off = lv.offsets.as<uint64_t>();
     size_t tmp_bytes = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_counts, d_off, int(n), e->stream);
     TB_CUDA(e->pf_scan_tmp.ensure(tmp_bytes + 16));
     TB_CUDA(cub::DeviceScan::ExclusiveSum(e->pf_scan_tmp.p, tmp_bytes, d_counts, d_off, int(n), e->stream));
     e->pf_launches += 2;
+    TB_CUDA(e->ensure_pinned(64));
     auto offset_at = [&](size_t i, uint64_t* out) -> int {  // offsets[i], with offsets[n] = total
-        if (i < n) {
-            TB_CUDA(cudaMemcpyAsync(out, d_off + i, 8, cudaMemcpyDeviceToHost, e->stream));
-            TB_CUDA(cudaStreamSynchronize(e->stream));
-            return TAK_OK;
-        }
-        uint64_t o = 0;
-        uint32_t c = 0;
-        TB_CUDA(cudaMemcpyAsync(&o, d_off + (n - 1), 8, cudaMemcpyDeviceToHost, e->stream));
-        TB_CUDA(cudaMemcpyAsync(&c, d_counts + (n - 1), 4, cudaMemcpyDeviceToHost, e->stream));
+        uint64_t* h = static_cast<uint64_t*>(e->h_stage);
+        uint32_t* hc = reinterpret_cast<uint32_t*>(h + 1);
+        const size_t at = i < n ? i : n - 1;
+        TB_CUDA(cudaMemcpyAsync(h, d_off + at, 8, cudaMemcpyDeviceToHost, e->stream));
+        *hc = 0;
+        if (i >= n) TB_CUDA(cudaMemcpyAsync(hc, d_counts + at, 4, cudaMemcpyDeviceToHost, e->stream));
         TB_CUDA(cudaStreamSynchronize(e->stream));
-        *out = o + c;
+        *out = *h + *hc;
         return TAK_OK;
     };
     uint64_t total = 0;
     if (int r = offset_at(n, &total)) return r;
     if (total == 0) return TAK_OK;
+    const bool last = depth_left == 2;   // the children of this frontier are the counted level
+    TB_CUDA(cudaFuncSetAttribute(k_perft_apply<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, P::SMEM));
+    TB_CUDA(cudaFuncSetAttribute(k_perft_apply<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, P::SMEM));
     size_t begin = 0;
     uint64_t begin_off = 0;
     while (begin < n) {
@@ -158,21 +152,58 @@ static int perft_level(tak_engine* e, const uint8_t* frontier, size_t n, int dep
         const size_t children = size_t(end_off - begin_off);
         if (children > 0) {
             TB_CHECK(children <= PF_CAP, TAK_ERR_CAPACITY, "one position has more children than the perft arena");
+            const int n_blocks = int((children + P::CH - 1) / P::CH);
             TB_CUDA(lv.children.ensure(children * S));
             TB_CUDA(lv.moves.ensure(children * 2));
-            k_perft_expand<N><<<warp_blocks(int(end - begin)), GAME_THREADS, 0, e->stream>>>(
+            TB_CUDA(lv.block_parent.ensure(size_t(n_blocks) * 4));
+            if (!last) TB_CUDA(lv.counts.ensure(children * 4));
+            cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+            if (e->pf_n_spans < tak_engine::PF_SPANS) {
+                ev0 = e->pf_span_ev[2 * e->pf_n_spans];
+                ev1 = e->pf_span_ev[2 * e->pf_n_spans + 1];
+                e->pf_span_children[e->pf_n_spans++] = children;
+                TB_CUDA(cudaEventRecord(ev0, e->stream));
+            }
+            k_perft_moves<N><<<warp_blocks(int(end - begin)), GAME_THREADS, 0, e->stream>>>(
                 frontier + begin * S, int(end - begin), d_counts + begin, d_off + begin, begin_off,
-                lv.children.as<uint8_t>(), lv.moves.as<uint16_t>());
-            e->pf_launches++;
+                lv.moves.as<uint16_t>(), lv.block_parent.as<int>());
+            if (last)
+                k_perft_apply<N, true><<<n_blocks, P::THREADS, P::SMEM, e->stream>>>(
+                    frontier + begin * S, int(end - begin), d_off + begin, begin_off, lv.block_parent.as<int>(), n_blocks,
+                    int(children), lv.moves.as<uint16_t>(), lv.children.as<uint8_t>(), nullptr, d_leaves);
+            else
+                k_perft_apply<N, false><<<n_blocks, P::THREADS, P::SMEM, e->stream>>>(
+                    frontier + begin * S, int(end - begin), d_off + begin, begin_off, lv.block_parent.as<int>(), n_blocks,
+                    int(children), lv.moves.as<uint16_t>(), lv.children.as<uint8_t>(), lv.counts.as<uint32_t>(), d_leaves);
+            if (ev1) TB_CUDA(cudaEventRecord(ev1, e->stream));
+            e->pf_launches += 2;
             e->pf_materialised += children;
             TB_CUDA(cudaGetLastError());
-            if (int r = perft_level<N>(e, lv.children.as<uint8_t>(), children, depth_left - 1, level + 1, d_leaves))
-                return r;
+            if (!last)
+                if (int r = perft_level<N>(e, lv.children.as<uint8_t>(), children, lv.counts.as<uint32_t>(),
+                                           depth_left - 1, level + 1, d_leaves))
+                    return r;
         }
         begin = end;
         begin_off = end_off;
     }
     return TAK_OK;
+}
+
+// roots: one count pass (the only frontier that is not produced by k_perft_apply), then the levels
+template <int N>
+static int perft_roots(tak_engine* e, const uint8_t* roots, size_t n, int depth, unsigned long long* d_leaves) {
+    const bool last = depth == 1;
+    uint32_t* d_counts = nullptr;
+    if (!last) {
+        TB_CUDA(e->pf_root_counts.ensure(n * 4));
+        d_counts = e->pf_root_counts.as<uint32_t>();
+    }
+    k_perft_count<N><<<(unsigned(n) + 255) / 256, 256, 0, e->stream>>>(roots, int(n), last ? 1 : 0, d_counts, d_leaves);
+    e->pf_launches++;
+    TB_CUDA(cudaGetLastError());
+    if (last) return TAK_OK;
+    return perft_level<N>(e, roots, n, d_counts, depth, 0, d_leaves);
 }
 
 extern "C" {
@@ -222,10 +253,13 @@ int32_t tak_engine_destroy(tak_engine_t* e) {
     mcts_destroy(e);
     net_destroy(e);
     for (DevBuf* b : {&e->states, &e->d_ids, &e->d_moves, &e->d_counts, &e->d_status, &e->d_results, &e->d_stage,
-                      &e->pf_root, &e->pf_scan_tmp, &e->pf_leaves})
+                      &e->pf_root, &e->pf_root_counts, &e->pf_scan_tmp, &e->pf_leaves, &e->po_plies, &e->po_result,
+                      &e->po_totals})
         b->release();
     for (auto& lv : e->pf_level)
-        for (DevBuf* b : {&lv.children, &lv.counts, &lv.offsets, &lv.moves}) b->release();
+        for (DevBuf* b : {&lv.children, &lv.counts, &lv.offsets, &lv.moves, &lv.block_parent}) b->release();
+    for (cudaEvent_t ev : e->pf_span_ev)
+        if (ev) cudaEventDestroy(ev);
     if (e->h_stage) cudaFreeHost(e->h_stage);
     cudaStreamDestroy(e->stream);
     delete e;
@@ -392,12 +426,15 @@ int32_t tak_perft_multi(tak_engine_t* e, const tak_state_t* roots, int32_t n_roo
     TB_CUDA(cudaMemsetAsync(e->pf_leaves.p, 0, 8, e->stream));
     e->pf_materialised = 0;
     e->pf_launches = 0;
+    for (cudaEvent_t& ev : e->pf_span_ev)
+        if (!ev) TB_CUDA(cudaEventCreate(&ev));
     cudaEvent_t e0, e1;
     TB_CUDA(cudaEventCreate(&e0));
     TB_CUDA(cudaEventCreate(&e1));
     TB_CUDA(cudaEventRecord(e0, e->stream));
     int r = TAK_OK;
-    TB_DISPATCH_N(e->n, r = perft_level<N_>(e, e->pf_root.as<uint8_t>(), n_roots, depth, 0,
+    e->pf_n_spans = 0;
+    TB_DISPATCH_N(e->n, r = perft_roots<N_>(e, e->pf_root.as<uint8_t>(), n_roots, depth,
                                             e->pf_leaves.as<unsigned long long>()));
     if (r == TAK_OK) {
         cudaEventRecord(e1, e->stream);
@@ -412,6 +449,18 @@ int32_t tak_perft_multi(tak_engine_t* e, const tak_state_t* roots, int32_t n_roo
             cudaEventElapsedTime(&ms, e0, e1);
             e->pf_ms = ms;
             *out_nodes = total;
+            e->pf_expand_ms = 0;
+            e->pf_top_span_ms = 0;
+            e->pf_top_span_children = 0;
+            for (int i = 0; i < e->pf_n_spans; ++i) {
+                float sp = 0;
+                cudaEventElapsedTime(&sp, e->pf_span_ev[2 * i], e->pf_span_ev[2 * i + 1]);
+                e->pf_expand_ms += sp;
+                if (e->pf_span_children[i] > e->pf_top_span_children) {
+                    e->pf_top_span_children = e->pf_span_children[i];
+                    e->pf_top_span_ms = sp;
+                }
+            }
         }
     }
     cudaEventDestroy(e0);
@@ -425,6 +474,61 @@ int32_t tak_perft_stats(tak_engine_t* e, double* out_ms, uint64_t* out_materiali
     if (out_ms) *out_ms = e->pf_ms;
     if (out_materialised) *out_materialised = e->pf_materialised;
     if (out_launches) *out_launches = e->pf_launches;
+    return TAK_OK;
+}
+
+int32_t tak_perft_profile(tak_engine_t* e, double* out6) {
+    TB_CHECK(e && out6, TAK_ERR_BAD_ARG, "tak_perft_profile: bad argument");
+    out6[0] = e->pf_ms;
+    out6[1] = e->pf_expand_ms;
+    out6[2] = double(e->pf_materialised);
+    out6[3] = double(e->pf_launches);
+    out6[4] = double(e->pf_top_span_children);
+    out6[5] = e->pf_top_span_ms;
+    return TAK_OK;
+}
+
+int32_t tak_playouts(tak_engine_t* e, int32_t first, int32_t count, uint64_t seed, int32_t game_id_base, int32_t max_plies,
+                     int32_t ply_spread, int32_t* out_plies, uint8_t* out_results, uint64_t* out_totals2,
+                     double* out_ms) {
+    TB_CHECK(e && first >= 0 && count >= 0 && first + count <= e->max_games && max_plies >= 0 && ply_spread >= 0,
+             TAK_ERR_BAD_ARG, "tak_playouts: bad argument");
+    if (out_totals2) out_totals2[0] = out_totals2[1] = 0;
+    if (out_ms) *out_ms = 0;
+    if (count == 0) return TAK_OK;
+    TB_CUDA(cudaSetDevice(e->device));
+    TB_CUDA(e->po_plies.ensure(size_t(count) * 4));
+    TB_CUDA(e->po_result.ensure(size_t(count)));
+    TB_CUDA(e->po_totals.ensure(16));
+    TB_CUDA(cudaMemsetAsync(e->po_totals.p, 0, 16, e->stream));
+    cudaEvent_t e0, e1;
+    TB_CUDA(cudaEventCreate(&e0));
+    TB_CUDA(cudaEventCreate(&e1));
+    TB_CUDA(cudaEventRecord(e0, e->stream));
+    TB_DISPATCH_N(e->n, (k_playout<N_><<<warp_blocks(count), GAME_THREADS, 0, e->stream>>>(
+                            e->states.as<uint8_t>(), first, count, seed, game_id_base, max_plies, ply_spread,
+                            e->po_plies.as<int>(), e->po_result.as<uint8_t>(),
+                            e->po_totals.as<unsigned long long>())));
+    e->launches++;
+    cudaError_t ce = cudaGetLastError();
+    if (ce == cudaSuccess) ce = cudaEventRecord(e1, e->stream);
+    unsigned long long totals[2] = {0, 0};
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(totals, e->po_totals.p, 16, cudaMemcpyDeviceToHost, e->stream);
+    if (ce == cudaSuccess && out_plies)
+        ce = cudaMemcpyAsync(out_plies, e->po_plies.p, size_t(count) * 4, cudaMemcpyDeviceToHost, e->stream);
+    if (ce == cudaSuccess && out_results)
+        ce = cudaMemcpyAsync(out_results, e->po_result.p, size_t(count), cudaMemcpyDeviceToHost, e->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+    float ms = 0;
+    if (ce == cudaSuccess) cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (ce != cudaSuccess) {
+        set_error("tak_playouts: %s", cudaGetErrorString(ce));
+        return TAK_ERR_CUDA;
+    }
+    if (out_totals2) { out_totals2[0] = totals[0]; out_totals2[1] = totals[1]; }
+    if (out_ms) *out_ms = ms;
     return TAK_OK;
 }
 

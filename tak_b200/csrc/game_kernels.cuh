@@ -1,6 +1,7 @@
 // Batched Tak kernels over packed states: one warp per game.
 //   k_reset / k_moves / k_play / k_result         -> tak_games_reset / tak_possible_moves / tak_play / tak_result
-//   k_perft_count / k_perft_expand                -> tak_perft (breadth-first, perf_count rule of perft.rs:3-18)
+//   k_perft_count / k_perft_moves / k_perft_apply -> tak_perft (breadth-first, perf_count rule of perft.rs:3-18)
+//   k_playout                                     -> tak_playouts (random playouts to termination, device-resident)
 #pragma once
 #include "tak_device.cuh"
 
@@ -105,27 +106,152 @@ __global__ void __launch_bounds__(256)
     }
 }
 
-// children of parent w are written to out[offsets[w] ...] in move-generation order; the generated moves go
-// through `moves_out` (also kept: it is the per-node move record of the expansion).
+// ---- perft expansion, output-centric ----------------------------------------------------------------------------
+// Children of a frontier are contiguous in the output (parent order, then move-generation order), so the expansion is
+// organised by OUTPUT range: a block owns PerftCfg::CH consecutive children, whatever parents they come from.
+//   k_perft_moves  one warp per parent: possible_moves -> moves_out[offsets[w] ...]; it also records, for every block
+//                  boundary that falls inside its children, which parent the block starts in (block_parent).
+//   k_perft_apply  per block: (1) every child finds its parent (binary search between the block's first and last
+//                  parent), (2) the parents' records are copied into per-child images in shared memory, 16 B per thread,
+//                  (3) ONE THREAD per child patches its image in place (RecordPlay: at most N+1 squares and the tail)
+//                  and classifies / counts the new position from the tail it just built (ThreadPos: Game::result +
+//                  possible_moves().len()), (4) the block streams its images out as one contiguous run of 16-byte
+//                  stores.  The child counts feed the next level's scan; at the last level they ARE perf_count's
+//                  answer (perft.rs:6-7), so no position is ever re-read by a separate count kernel.
+// HBM traffic per child: S written + S/b read (the parent, once per block that touches it) + 2 B move written + read
+// + 4 B count -- SURVEY.md 8(d)'s S + S/b + 2 within 2 %.
+template <int N>
+struct PerftCfg {
+    static constexpr int S = StateLayout<N>::S;
+    static constexpr int W = S / 16;                  // 16-byte words per record
+    static constexpr int CH = N <= 6 ? 128 : 64;      // children per block
+    static constexpr int STRIDE = S + 16;             // image pitch in shared memory (16 B of skew against bank conflicts)
+    static constexpr int THREADS = 256;
+    static constexpr int SMEM = CH * STRIDE + CH * 4;
+};
+
 template <int N>
 __global__ void __launch_bounds__(GAME_THREADS)
-    k_perft_expand(const uint8_t* frontier, int n, const uint32_t* counts, const uint64_t* offsets,
-                   uint64_t base_off, uint8_t* out, uint16_t* moves_out) {
+    k_perft_moves(const uint8_t* frontier, int n, const uint32_t* counts, const uint64_t* offsets, uint64_t base_off,
+                  uint16_t* moves_out, int* block_parent) {
     const int w = warp_global_id();
     if (w >= n) return;
     const uint32_t cnt = counts[w];
     if (cnt == 0) return;
-    constexpr int S = StateLayout<N>::S;
+    constexpr int CH = PerftCfg<N>::CH;
     WarpGame<N> g;
-    g.load(frontier + size_t(w) * S);
+    g.load(frontier + size_t(w) * StateLayout<N>::S);
     const uint64_t base = offsets[w] - base_off;
     uint16_t* mv = moves_out + base;
     g.generate([&](int k, uint16_t m) { mv[k] = m; });
-    __syncwarp();
-    for (uint32_t k = 0; k < cnt; ++k) {
-        WarpGame<N> child = g;
-        child.template play<false>(mv[k]);
-        child.store(out + (base + k) * S);
+    for (uint64_t b = (base + CH - 1) / CH + (threadIdx.x & 31); b * CH < base + cnt; b += 32) block_parent[b] = w;
+}
+
+template <int N, bool LAST>
+__global__ void __launch_bounds__(PerftCfg<N>::THREADS)
+    k_perft_apply(const uint8_t* frontier, int n_parents, const uint64_t* offsets, uint64_t base_off,
+                  const int* block_parent, int n_blocks, int total_children, const uint16_t* moves, uint8_t* out,
+                  uint32_t* child_counts, unsigned long long* leaves) {
+    using P = PerftCfg<N>;
+    extern __shared__ __align__(16) uint8_t s_img[];
+    int* s_parent = reinterpret_cast<int*>(s_img + P::CH * P::STRIDE);
+    const int t = threadIdx.x;
+    const int c0 = blockIdx.x * P::CH;
+    const int nc = min(P::CH, total_children - c0);
+    if (t < nc) {
+        // owner of child c = the LAST parent whose first child is <= c (parents without children share their offset
+        // with the next parent), searched between the owners of this block's and the next block's first child
+        const uint64_t c = uint64_t(c0 + t);
+        int lo = block_parent[blockIdx.x];
+        int hi = int(blockIdx.x) + 1 < n_blocks ? block_parent[blockIdx.x + 1] : n_parents - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (offsets[mid] - base_off <= c) lo = mid; else hi = mid - 1;
+        }
+        s_parent[t] = lo;
+    }
+    __syncthreads();
+    const uint4* src = reinterpret_cast<const uint4*>(frontier);
+    for (int idx = t; idx < nc * P::W; idx += P::THREADS) {
+        const int ch = idx / P::W, wd = idx - ch * P::W;
+        *reinterpret_cast<uint4*>(s_img + ch * P::STRIDE + wd * 16) = __ldg(src + size_t(s_parent[ch]) * P::W + wd);
+    }
+    __syncthreads();
+    unsigned long long add = 0;
+    if (t < nc) {
+        ThreadPos<N> tp;
+        RecordPlay<N>::apply(s_img + t * P::STRIDE, moves[c0 + t], tp);
+        uint32_t cnt = 0;
+        if (tp.result() != RES_ONGOING) {
+            add = 1;                                   // a finished game counts 1 wherever it ends (perft.rs:4)
+        } else {
+            const uint32_t total = tp.count_moves();
+            if (LAST) add = total; else cnt = total;   // depth 1: the number of legal moves (perft.rs:6-7)
+        }
+        if (!LAST) child_counts[c0 + t] = cnt;
+    }
+    __syncthreads();
+    uint4* dst = reinterpret_cast<uint4*>(out) + size_t(c0) * P::W;
+    for (int idx = t; idx < nc * P::W; idx += P::THREADS) {
+        const int ch = idx / P::W, wd = idx - ch * P::W;
+        dst[idx] = *reinterpret_cast<const uint4*>(s_img + ch * P::STRIDE + wd * 16);
+    }
+    // block reduction of `add` (only the first CH threads carry a value)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) add += __shfl_xor_sync(FULL, add, o);
+    __shared__ unsigned long long s_add[P::THREADS / 32];
+    if ((t & 31) == 0) s_add[t >> 5] = add;
+    __syncthreads();
+    if (t == 0) {
+        unsigned long long sum = 0;
+        for (int i = 0; i < P::THREADS / 32; ++i) sum += s_add[i];
+        if (sum) atomicAdd(leaves, sum);
+    }
+}
+
+// ---- random playouts (workload A) -----------------------------------------------------------
+// One warp plays game w from its current position: while the game is ongoing and fewer than max_plies[w] (or max_ply)
+// plies were added, move = possible_moves()[splitmix64(seed ^ splitmix64(game_id << 32 | ply)) % len] -- the state stays
+// in registers for the whole playout; HBM sees one load and one store per game.
+__device__ __forceinline__ uint64_t playout_mix(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+template <int N>
+__global__ void __launch_bounds__(GAME_THREADS)
+    k_playout(uint8_t* states, int first, int n, uint64_t seed, int id_base, int max_plies, int ply_spread,
+              int* out_plies, uint8_t* out_result, unsigned long long* totals) {
+    const int w = warp_global_id();
+    if (w >= n) return;
+    constexpr int S = StateLayout<N>::S;
+    const int l = threadIdx.x & 31;
+    const uint64_t gid = uint64_t(uint32_t(id_base + first + w));
+    WarpGame<N> g;
+    uint8_t* rec = states + size_t(first + w) * S;
+    g.load(rec);
+    // per-game ply budget: max_plies + (hash % ply_spread) so that a batch can be cut at staggered depths
+    int budget = max_plies;
+    if (ply_spread > 0) budget += int(playout_mix(seed ^ playout_mix(gid ^ 0xC0FFEEull)) % uint64_t(ply_spread));
+    int plies = 0;
+    unsigned long long generated = 0;
+    uint8_t r = g.result();
+    while (r == RES_ONGOING && plies < budget) {
+        int total = 0;
+        const uint64_t key = playout_mix(seed ^ playout_mix((gid << 32) | uint64_t(uint32_t(g.ply))));
+        const uint16_t mv = g.select_move([&](int len) { return int(key % uint64_t(len)); }, total);
+        generated += uint64_t(total);
+        g.template play<false>(mv);
+        ++plies;
+        r = g.result();
+    }
+    g.store(rec);
+    if (l == 0) {
+        if (out_plies) out_plies[w] = plies;
+        if (out_result) out_result[w] = r;
+        atomicAdd(totals + 0, (unsigned long long)plies);
+        atomicAdd(totals + 1, generated);
     }
 }
 

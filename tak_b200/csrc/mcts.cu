@@ -4,6 +4,7 @@
 #include "mcts.hpp"
 
 #include <cmath>
+#include <cstdlib>
 
 #include "game_kernels.cuh"
 #include "net.hpp"
@@ -161,6 +162,71 @@ int mcts_eval_and_backup(tak_engine* e) {
         ps.S = ns.cap_S;
     }
     return mcts_launch_backup(e, ps);
+}
+
+// ---- the fused search loop -------------------------------------------------------------------------------------
+// `reps` x Node::rollout (mcts.rs:16-23) for the listed games in lock step, one leaf per game per iteration, with NO host
+// round trip: leaves take their evaluation slot with a device atomic and write their input planes from the rollout warp,
+// the tower reads the leaf count from device memory, the heads are computed by the backup warp, and backup(i) + rollout
+// (i+1) share a launch:   step(rollout) ; { tower ; step(backup + rollout) } x (reps - 1) ; tower ; step(backup).
+// Two launches per rollout (Net6), against seven and a stream synchronisation in the stepwise path.
+static int launch_step(tak_engine* e, const int* d_ids, int n, const uint8_t* d_enable, const FastEval& fe,
+                       const PriorSource& ps, int do_backup, int do_rollout, int reps) {
+    MctsState& m = *e->mcts;
+    // 2 warps per block: at 128 registers per thread a block takes 8 192 registers, which fits beside a resident
+    // conv-tower CTA of the other engine replica on the same SM (it leaves 11 776 free), so one replica's search hides
+    // under the other's tower.  TAK_STEP_WARPS overrides it for measurements.
+    static const int warps = [] {
+        const char* s = std::getenv("TAK_STEP_WARPS");
+        const int v = s ? std::atoi(s) : 2;
+        return v >= 1 && v <= 4 ? v : 2;
+    }();
+    TB_DISPATCH_N(e->n, (k_mcts_step<N_><<<(n + warps - 1) / warps, 32 * warps, 0, e->stream>>>(
+                            m.view(), e->states.as<uint8_t>(), d_ids, n, d_enable, fe, ps, do_backup, do_rollout, reps)));
+    e->launches++;
+    TB_CUDA(cudaGetLastError());
+    return TAK_OK;
+}
+
+int mcts_fast_rollouts(tak_engine* e, const int* d_ids, int n, int reps, const uint8_t* d_enable) {
+    TB_CHECK(e->net, TAK_ERR_NO_NETWORK, "no network: call net_create first");
+    MctsState& m = *e->mcts;
+    NetState& ns = *e->net;
+    if (reps <= 0 || n <= 0) return TAK_OK;
+    if (m.queued) {   // leaves queued by an earlier stepwise call: evaluate and back them up first (queue order)
+        if (int r = mcts_eval_and_backup(e)) return r;
+    }
+    FastEval fe{};
+    PriorSource ps{};
+    ps.arch = ns.arch;
+    ps.psz = ns.policy_out;
+    if (ns.arch == 0) {
+        // DummyNet: nothing to evaluate -- every rollout's backup can follow it at once, the whole loop is one launch
+        if (int r = launch_step(e, d_ids, n, d_enable, fe, ps, 1, 1, reps)) return r;
+        return launch_step(e, d_ids, n, nullptr, fe, ps, 1, 0, 1);
+    }
+    TB_CHECK(n <= e->max_batch, TAK_ERR_CAPACITY, "%d games searched together exceed max_batch %d", n, e->max_batch);
+    if (int r = net_fast_views(e, n, fe, ps)) return r;
+    int* cnt = m.eval_count.as<int>() + 2;   // [2], [3]: the two phases of the loop ([0] belongs to the compaction path)
+    TB_CUDA(cudaMemsetAsync(cnt, 0, 8, e->stream));
+    fe.eval_slot = m.eval_slot.as<int>();
+    int phase = 0;
+    fe.eval_count = cnt + phase;
+    fe.eval_count_reset = cnt + (phase ^ 1);
+    if (int r = launch_step(e, d_ids, n, d_enable, fe, ps, 0, 1, 1)) return r;
+    for (int i = 1; i < reps; ++i) {
+        if (int r = net_tower_fast(e, n, cnt + phase)) return r;
+        phase ^= 1;
+        fe.eval_count = cnt + phase;
+        fe.eval_count_reset = cnt + (phase ^ 1);
+        if (int r = launch_step(e, d_ids, n, d_enable, fe, ps, 1, 1, 1)) return r;
+    }
+    if (int r = net_tower_fast(e, n, cnt + phase)) return r;
+    fe.eval_count = nullptr;
+    fe.eval_count_reset = nullptr;
+    if (int r = launch_step(e, d_ids, n, nullptr, fe, ps, 1, 0, 1)) return r;
+    m.queued = false;
+    return TAK_OK;
 }
 
 int mcts_check_errors(tak_engine* e) {
@@ -393,9 +459,13 @@ int32_t mcts_rollouts(tak_engine_t* e, const int32_t* ids, int32_t n, int32_t n_
     if (n == 0) return TAK_OK;
     const int* d_ids = nullptr;
     if (int r = upload_ids(e, ids, n, &d_ids)) return r;
-    for (int i = 0; i < n_rollouts; ++i) {
-        if (int r = mcts_launch_rollout(e, d_ids, n, 1)) return r;
-        if (int r = mcts_eval_and_backup(e)) return r;
+    if (e->net->arch == 0 || n <= e->max_batch) {
+        if (int r = mcts_fast_rollouts(e, d_ids, n, n_rollouts, nullptr)) return r;
+    } else {
+        for (int i = 0; i < n_rollouts; ++i) {   // more games than one network batch holds: stepwise
+            if (int r = mcts_launch_rollout(e, d_ids, n, 1)) return r;
+            if (int r = mcts_eval_and_backup(e)) return r;
+        }
     }
     return mcts_check_errors(e);
 }
@@ -527,6 +597,23 @@ int32_t mcts_pick_move(tak_engine_t* e, const int32_t* ids, int32_t n, uint16_t*
     if (int r = upload_ids(e, ids, n, &d_ids)) return r;
     TB_CUDA(m.d_moves.ensure(size_t(n) * 2 + 2));
     if (int r = mcts_launch_pick(e, d_ids, n, nullptr, 0, nullptr, m.d_moves.as<uint16_t>())) return r;
+    TB_CUDA(cudaMemcpyAsync(out_moves, m.d_moves.p, size_t(n) * 2, cudaMemcpyDeviceToHost, e->stream));
+    return mcts_check_errors(e);
+}
+
+int32_t mcts_pick_move_sampled(tak_engine_t* e, const int32_t* ids, int32_t n, uint64_t seed, uint16_t* out_moves) {
+    TB_CHECK(e && ids && out_moves && n >= 0, TAK_ERR_BAD_ARG, "mcts_pick_move_sampled: bad argument");
+    TB_CUDA(cudaSetDevice(e->device));
+    if (int r = mcts_ensure(e, 1)) return r;
+    if (n == 0) return TAK_OK;
+    MctsState& m = *e->mcts;
+    const int* d_ids = nullptr;
+    if (int r = upload_ids(e, ids, n, &d_ids)) return r;
+    TB_CUDA(m.d_moves.ensure(size_t(n) * 2 + 2));
+    TB_CUDA(m.stage_count.ensure(size_t(n) + 16));
+    TB_CUDA(cudaMemsetAsync(m.stage_count.p, 1, size_t(n), e->stream));   // sample flag of every listed game
+    if (int r = mcts_launch_pick(e, d_ids, n, m.stage_count.as<uint8_t>(), seed, nullptr, m.d_moves.as<uint16_t>()))
+        return r;
     TB_CUDA(cudaMemcpyAsync(out_moves, m.d_moves.p, size_t(n) * 2, cudaMemcpyDeviceToHost, e->stream));
     return mcts_check_errors(e);
 }

@@ -25,6 +25,8 @@ int mcts_launch_compact(tak_engine* e);                 // fills eval_index / ev
 int mcts_read_eval_count(tak_engine* e, int* out);      // syncs the stream
 int mcts_launch_backup(tak_engine* e, const PriorSource& ps);
 int mcts_eval_and_backup(tak_engine* e);                // compact -> network -> backup (syncs once for the count)
+// `reps` x Node::rollout for the listed games, fused on the device (two launches per rollout, no host round trip)
+int mcts_fast_rollouts(tak_engine* e, const int* d_ids, int n, int reps, const uint8_t* d_enable);
 int mcts_check_errors(tak_engine* e);                   // syncs; maps device error flags to a status
 int mcts_launch_tree_reset(tak_engine* e, const int* d_ids, int n);
 int mcts_launch_pick(tak_engine* e, const int* d_ids, int n, const uint8_t* d_sample, uint64_t seed,

@@ -12,6 +12,7 @@
 // indexed by the integer visit count.
 #pragma once
 #include "game_kernels.cuh"
+#include "eval_views.hpp"
 #include "net_kernels.cuh"
 #include "tak_device.cuh"
 
@@ -61,14 +62,10 @@ __device__ __forceinline__ void update_concrete(uint4& s, float reward) {
     s.y = __float_as_uint(__fdiv_rn(__fadd_rn(cumulative, reward), float(s.z)));
 }
 
-// Node::virtual_rollout x k (mcts.rs:26-65) incl. select (mcts.rs:94-118); one warp per listed game
+// Node::virtual_rollout x k (mcts.rs:26-65) incl. select (mcts.rs:94-118) for ONE game, executed by one warp
 template <int N>
-__global__ void __launch_bounds__(GAME_THREADS)
-    k_mcts_rollout(MctsView v, const uint8_t* states, const int* ids, int n, int k, const uint8_t* enable) {
-    const int w = warp_global_id();
-    if (w >= n) return;
-    if (enable && !enable[w]) return;
-    const int gid = ids ? ids[w] : w;
+__device__ __forceinline__ void rollout_game(const MctsView& v, const uint8_t* states, int gid, int k,
+                                             const FastEval& fe) {
     const int l = threadIdx.x & 31;
     constexpr int S = StateLayout<N>::S;
     const int half = v.half[gid];
@@ -186,10 +183,19 @@ __global__ void __launch_bounds__(GAME_THREADS)
         }
         if (res == RES_ONGOING) {
             g.store(v.leaf_states + (size_t(gid) * v.kcap + pend) * S);
+            int slot = 0;
             if (l == 0) {
                 v.pend_leaf[size_t(gid) * v.kcap + pend] = node;
                 v.pend_plen[size_t(gid) * v.kcap + pend] = depth;
                 atomicAdd(v.counters + 1, 1ull);
+                if (fe.eval_count) {
+                    slot = atomicAdd(fe.eval_count, 1);
+                    fe.eval_slot[size_t(gid) * v.kcap + pend] = slot;
+                }
+            }
+            if (fe.eval_count && fe.planes) {
+                slot = __shfl_sync(FULL, slot, 0);
+                encode_board<N>(g, slot, fe.planes, fe.S);
             }
             ++pend;
         }
@@ -199,6 +205,16 @@ __global__ void __launch_bounds__(GAME_THREADS)
         v.top[gid] = top;
         v.pend_cnt[gid] = pend;
     }
+}
+
+template <int N>
+__global__ void __launch_bounds__(GAME_THREADS)
+    k_mcts_rollout(MctsView v, const uint8_t* states, const int* ids, int n, int k, const uint8_t* enable) {
+    const int w = warp_global_id();
+    if (w >= n) return;
+    if (enable && !enable[w]) return;
+    FastEval none{};
+    rollout_game<N>(v, states, ids ? ids[w] : w, k, none);
 }
 
 // flat pending slot (gid*kcap + j) <-> compact evaluation index; single block
@@ -244,16 +260,54 @@ static __global__ void __launch_bounds__(1024)
     if (threadIdx.x == 0) *eval_count = s_carry;
 }
 
-struct PriorSource {
-    int arch;               // 0 dummy (prior 1, eval 0), 5 dense logits, 6 conv logits, -1 host-supplied policy
-    const float* logits;    // arch 5: [B][psz]; arch 6: [ch][S]; arch -1: policy [B][psz]
-    const float2* stats;    // {max, sum} per compact index (arch 5/6)
-    const float* values;    // per compact index
-    int S;
-    int psz;
-};
 
-// Node::devirtualize_path (mcts.rs:67-91) for every queued leaf of every game, in queue order
+// Node::devirtualize_path (mcts.rs:67-91) for ONE queued leaf (flat queue slot `slot`, evaluation slot `ei`)
+template <int N>
+__device__ __forceinline__ void backup_leaf(const MctsView& v, uint4* stat, const uint2* link, size_t slot, int ei,
+                                            const PriorSource& ps, float mx, float sum, float eval) {
+    constexpr int NSQ = N * N;
+    const int l = threadIdx.x & 31;
+    const uint32_t leaf = v.pend_leaf[slot];
+    const int plen = v.pend_plen[slot];
+    const uint32_t* path = v.pend_path + slot * MCTS_MAX_DEPTH;
+    // replace the temporary priors (mcts.rs:78-83): policy[move_index(mov)] -- no mask, no renormalisation
+    const uint2 lk = link[leaf];
+    const uint32_t base = lk.x & 0xFFFFFFu;
+    const int nchild = int(lk.y >> 16);
+    for (int i = l; i < nchild; i += 32) {
+        const uint16_t mv = uint16_t(link[base + i].y & 0xFFFFu);
+        const int idx = v.move_table[mv];
+        float prior = 1.0f;
+        if (idx == 0xFFFF) {
+            atomicOr(v.err, MERR_BAD_MOVE);
+        } else if (ps.arch == 6) {
+            const int ch = idx / NSQ, sq = idx % NSQ, row = sq / N, col = sq % N;
+            const float lg = ps.logits[size_t(ch) * ps.S + SlotMap<N>::slot(ei, row, col)];
+            prior = __fdiv_rn(expf(__fsub_rn(lg, mx)), sum);
+        } else if (ps.arch == 5) {
+            prior = __fdiv_rn(expf(__fsub_rn(ps.logits[size_t(ei) * ps.psz + idx], mx)), sum);
+        } else if (ps.arch == -1) {
+            prior = ps.logits[size_t(ei) * ps.psz + idx];
+        }
+        uint4 cs = stat[base + i];
+        cs.x = __float_as_uint(prior);
+        stat[base + i] = cs;
+    }
+    __syncwarp();
+    if (l == 0) {
+        for (int d = plen; d >= 0; --d) {
+            const uint32_t nd = path[d];
+            uint4 s = stat[nd];
+            s.w -= 1;
+            eval = -eval;
+            update_concrete(s, eval);
+            stat[nd] = s;
+        }
+    }
+    __syncwarp();
+}
+
+// Node::devirtualize_path for every queued leaf of every game, in queue order
 template <int N>
 __global__ void __launch_bounds__(GAME_THREADS)
     k_mcts_backup(MctsView v, const int* eval_slot, int n_games, PriorSource ps, const int* limits,
@@ -265,58 +319,19 @@ __global__ void __launch_bounds__(GAME_THREADS)
     const int cnt = limits ? min(queued, limits[gid]) : queued;
     if (cnt == 0) return;
     const int l = threadIdx.x & 31;
-    constexpr int NSQ = N * N;
     const int half = v.half[gid];
     uint4* stat = v.stat + arena_base(v, gid, half);
     uint2* link = v.link + arena_base(v, gid, half);
     for (int j = 0; j < cnt; ++j) {
         const size_t slot = size_t(gid) * v.kcap + j;
         const int ei = eval_slot[slot];
-        const uint32_t leaf = v.pend_leaf[slot];
-        const int plen = v.pend_plen[slot];
-        const uint32_t* path = v.pend_path + slot * MCTS_MAX_DEPTH;
-        // replace the temporary priors (mcts.rs:78-83): policy[move_index(mov)] -- no mask, no renormalisation
-        const uint2 lk = link[leaf];
-        const uint32_t base = lk.x & 0xFFFFFFu;
-        const int nchild = int(lk.y >> 16);
         float mx = 0.f, sum = 1.f;
         if (ps.arch == 5 || ps.arch == 6) {
             const float2 st = ps.stats[ei];
             mx = st.x;
             sum = st.y;
         }
-        for (int i = l; i < nchild; i += 32) {
-            const uint16_t mv = uint16_t(link[base + i].y & 0xFFFFu);
-            const int idx = v.move_table[mv];
-            float prior = 1.0f;
-            if (idx == 0xFFFF) {
-                atomicOr(v.err, MERR_BAD_MOVE);
-            } else if (ps.arch == 6) {
-                const int ch = idx / NSQ, sq = idx % NSQ, row = sq / N, col = sq % N;
-                const float lg = ps.logits[size_t(ch) * ps.S + SlotMap<N>::slot(ei, row, col)];
-                prior = __fdiv_rn(expf(__fsub_rn(lg, mx)), sum);
-            } else if (ps.arch == 5) {
-                prior = __fdiv_rn(expf(__fsub_rn(ps.logits[size_t(ei) * ps.psz + idx], mx)), sum);
-            } else if (ps.arch == -1) {
-                prior = ps.logits[size_t(ei) * ps.psz + idx];
-            }
-            uint4 cs = stat[base + i];
-            cs.x = __float_as_uint(prior);
-            stat[base + i] = cs;
-        }
-        __syncwarp();
-        if (l == 0) {
-            float eval = ps.arch == 0 ? 0.0f : ps.values[ei];
-            for (int d = plen; d >= 0; --d) {
-                const uint32_t nd = path[d];
-                uint4 s = stat[nd];
-                s.w -= 1;
-                eval = -eval;
-                update_concrete(s, eval);
-                stat[nd] = s;
-            }
-        }
-        __syncwarp();
+        backup_leaf<N>(v, stat, link, slot, ei, ps, mx, sum, ps.arch == 0 ? 0.0f : ps.values[ei]);
     }
     // leaves queued after the first `limit` stay queued: move them to the front of the game's queue
     const int rest = queued - cnt;
@@ -337,6 +352,45 @@ __global__ void __launch_bounds__(GAME_THREADS)
         }
     }
     if (l == 0) v.pend_cnt[gid] = rest;
+}
+
+// One iteration of the fused search loop for every listed game: devirtualise the leaf the previous iteration queued
+// (its network outputs are in place), then run the next virtual rollout and queue / encode its leaf.  Both halves touch
+// only this game's tree, so they need no grid-wide ordering and live in one launch: the loop is {k_mcts_step; tower} x R.
+// With the DummyNet (arch 0: prior 1, eval 0 -- nothing to evaluate) the whole loop of `reps` rollouts is ONE launch.
+template <int N>
+__global__ void __launch_bounds__(128)
+    k_mcts_step(MctsView v, const uint8_t* states, const int* ids, int n, const uint8_t* enable, FastEval fe,
+                PriorSource ps, int do_backup, int do_rollout, int reps) {
+    if (blockIdx.x == 0 && threadIdx.x == 0 && fe.eval_count_reset) *fe.eval_count_reset = 0;
+    const int w = warp_global_id();
+    if (w >= n) return;
+    const int gid = ids ? ids[w] : w;
+    const bool roll = do_rollout && (!enable || enable[w]);
+    for (int rep = 0; rep < reps; ++rep) {
+        if (do_backup && v.pend_cnt[gid] > 0) {
+            const int half = v.half[gid];
+            uint4* stat = v.stat + arena_base(v, gid, half);
+            const uint2* link = v.link + arena_base(v, gid, half);
+            const size_t slot = size_t(gid) * v.kcap;
+            const int ei = ps.arch != 0 ? fe.eval_slot[slot] : 0;
+            float mx = 0.f, sum = 1.f, eval = 0.f;
+            if (ps.arch == 6) {
+                const float2 st = warp_policy_stats<N>(ps.partials, ps.S, ps.groups, ei);
+                mx = st.x;
+                sum = st.y;
+            } else if (ps.arch == 5) {
+                const float2 st = ps.stats[ei];
+                mx = st.x;
+                sum = st.y;
+            }
+            if (ps.arch != 0) eval = warp_value<N>(ps.trunk, ps.S, ps.value_w, ps.value_b, ei);
+            backup_leaf<N>(v, stat, link, slot, ei, ps, mx, sum, eval);
+            if ((threadIdx.x & 31) == 0) v.pend_cnt[gid] = 0;
+            __syncwarp();
+        }
+        if (roll) rollout_game<N>(v, states, gid, 1, fe);
+    }
 }
 
 // Node::pick_move(true) (play.rs:52-58): LAST child with the maximal visit count.  With `sample` != 0 the move is

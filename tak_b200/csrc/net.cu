@@ -158,8 +158,11 @@ int net_ensure_capacity(tak_engine* e, int boards) {
     return TAK_OK;
 }
 
+// The whole conv tower (initial conv, residual blocks, Net6 policy conv groups) as ONE launch of conv_tc3.cuh over the
+// input planes in NetState::act_in.  `boards` sizes the launch; with d_count the kernel reads the actual number of
+// boards from device memory (the fused search loop counts its leaves on the device).
 template <int N>
-static int forward_t(tak_engine* e, const uint8_t* d_states, const int* d_index, int boards, float* d_policy_out) {
+static int launch_tower(tak_engine* e, int boards, const int* d_count) {
     NetState& ns = *e->net;
     if (int r = net_ensure_capacity(e, boards)) return r;
     const int tiles = tiles_for(N, boards);
@@ -168,14 +171,9 @@ static int forward_t(tak_engine* e, const uint8_t* d_states, const int* d_index,
     __nv_bfloat16* x = ns.act[0].as<__nv_bfloat16>();
     __nv_bfloat16* t = ns.act[1].as<__nv_bfloat16>();
     __nv_bfloat16* y = ns.act[2].as<__nv_bfloat16>();
-    const int wblocks = (boards + 7) / 8;
-    k_encode<N><<<wblocks, 256, 0, e->stream>>>(d_states, d_index, boards, x_in, S);
-    e->launches++;
-    TB_CUDA(cudaGetLastError());
-    // the whole conv tower (initial conv, residual blocks, Net6 policy conv groups) is ONE launch: conv_tc3.cuh
     ConvParams p{};
     conv_params_set_layout(p, N);
-    p.S = S; p.tile_begin = 0; p.tile_end = tiles; p.n_boards = boards;
+    p.S = S; p.tile_begin = 0; p.tile_end = tiles; p.n_boards = boards; p.n_boards_dev = d_count;
     auto conv = [&](const ConvLayer& L, const __nv_bfloat16* in, const __nv_bfloat16* res, __nv_bfloat16* out,
                     int mode, int slabs, int grp, int ch_valid, int discard = 0) {
         ConvLayerDesc& d = p.layers[p.n_layers++];
@@ -198,26 +196,15 @@ static int forward_t(tak_engine* e, const uint8_t* d_states, const int* d_index,
         for (int grp = 0; grp < ns.policy_groups; ++grp)
             conv(ns.policy_layers[grp], x, nullptr, nullptr, CONV_LOGITS_F32, C3_MAX_SLABS, grp,
                  std::min(128, ns.policy_ch - grp * 128), std::getenv("TAK_NO_STCS") ? 0 : 4);
-    {
-        NetProfile* prof = ns.profile;
-        if (prof) TB_CUDA(cudaEventRecord(prof->ev[2 * prof->n], e->stream));
-        TB_CUDA(conv3x3_tc3_launch(p, e->num_sms, e->stream));
-        e->launches++;
-        if (prof) {
-            TB_CUDA(cudaEventRecord(prof->ev[2 * prof->n + 1], e->stream));
-            prof->n++;
-        }
+    NetProfile* prof = ns.profile;
+    if (prof) TB_CUDA(cudaEventRecord(prof->ev[2 * prof->n], e->stream));
+    TB_CUDA(conv3x3_tc3_launch(p, e->num_sms, e->stream));
+    e->launches++;
+    if (prof) {
+        TB_CUDA(cudaEventRecord(prof->ev[2 * prof->n + 1], e->stream));
+        prof->n++;
     }
-    // heads
-    if (ns.arch == 6) {
-        k_policy_stats_conv<N><<<wblocks, 256, 0, e->stream>>>(ns.partials.as<float2>(), S, ns.policy_groups * 4, boards,
-                                                               ns.stats.as<float2>());
-        if (d_policy_out) {
-            e->launches++;
-            k_policy_full_conv<N><<<boards, 256, 0, e->stream>>>(ns.logits.as<float>(), S, ns.policy_ch,
-                                                                 ns.stats.as<float2>(), d_policy_out);
-        }
-    } else {
+    if (ns.arch == 5) {
         // policy FC (net5.rs:108) on the tensor cores: repack the trunk output, then one GEMM launch (fc_tc.cuh)
         const int b_pad = (boards + FC_NT - 1) / FC_NT * FC_NT;
         TB_CUDA(ns.fc_x.ensure(size_t(N * N) * 16 * b_pad * 16));
@@ -231,27 +218,95 @@ static int forward_t(tak_engine* e, const uint8_t* d_states, const int* d_index,
         fp.j_tiles = (ns.policy_out + 127) / 128; fp.n_tiles = b_pad / FC_NT;
         TB_CUDA(fc_tc_launch(fp, e->num_sms, e->stream));
         e->launches += 2;
+    }
+    TB_CUDA(cudaGetLastError());
+    return TAK_OK;
+}
+
+template <int N>
+static int forward_t(tak_engine* e, const uint8_t* d_states, const int* d_index, int boards, float* d_policy_out,
+                     int raw_logits) {
+    NetState& ns = *e->net;
+    if (int r = net_ensure_capacity(e, boards)) return r;
+    const int S = ns.cap_S;
+    const int wblocks = (boards + 7) / 8;
+    k_encode<N><<<wblocks, 256, 0, e->stream>>>(d_states, d_index, boards, ns.act_in.as<__nv_bfloat16>(), S);
+    e->launches++;
+    TB_CUDA(cudaGetLastError());
+    if (int r = launch_tower<N>(e, boards, nullptr)) return r;
+    // heads
+    if (ns.arch == 6) {
+        k_policy_stats_conv<N><<<wblocks, 256, 0, e->stream>>>(ns.partials.as<float2>(), S, ns.policy_groups * 4, boards,
+                                                               ns.stats.as<float2>());
+        if (d_policy_out) {
+            e->launches++;
+            k_policy_full_conv<N><<<boards, 256, 0, e->stream>>>(ns.logits.as<float>(), S, ns.policy_ch,
+                                                                 ns.stats.as<float2>(), d_policy_out, raw_logits);
+        }
+    } else {
         k_policy_stats_dense<<<boards, 256, 0, e->stream>>>(ns.logits.as<float>(), ns.policy_out,
-                                                            ns.stats.as<float2>(), d_policy_out);
+                                                            ns.stats.as<float2>(), d_policy_out, raw_logits);
     }
     e->launches++;
     TB_CUDA(cudaGetLastError());
-    k_value<N><<<wblocks, 256, 0, e->stream>>>(x, S, ns.value_w.as<float>(), ns.value_bias, boards,
+    k_value<N><<<wblocks, 256, 0, e->stream>>>(ns.trunk_out, S, ns.value_w.as<float>(), ns.value_bias, boards,
                                                ns.values.as<float>());
     e->launches++;
     TB_CUDA(cudaGetLastError());
     return TAK_OK;
 }
 
-int net_forward(tak_engine* e, const uint8_t* d_states, const int* d_index, int boards, float* d_policy_out) {
+// The fused search loop's evaluation (mcts.cu): input planes were written by the rollout warps, the number of leaves is
+// on the device, the heads are computed by the backup warps.  Net5 additionally needs its FC policy GEMM and the
+// softmax statistics of the dense logits (both sized for `max_boards`; rows beyond the live count are never read).
+int net_tower_fast(tak_engine* e, int max_boards, const int* d_count) {
+    NetState& ns = *e->net;
+    int r = TAK_ERR_BAD_ARG;
+    if (e->n == 5) r = launch_tower<5>(e, max_boards, d_count);
+    if (e->n == 6) r = launch_tower<6>(e, max_boards, d_count);
+    if (r) return r;
+    if (ns.arch == 5) {
+        k_policy_stats_dense<<<max_boards, 256, 0, e->stream>>>(ns.logits.as<float>(), ns.policy_out,
+                                                                ns.stats.as<float2>(), nullptr, 0);
+        e->launches++;
+        TB_CUDA(cudaGetLastError());
+    }
+    return TAK_OK;
+}
+
+// where the fused loop's rollout warps write the input planes and its backup warps find the network outputs
+int net_fast_views(tak_engine* e, int max_boards, FastEval& fe, PriorSource& ps) {
+    TB_CHECK(e->net && e->net->arch != 0 && e->net->loaded, TAK_ERR_NO_NETWORK, "network weights not loaded");
+    NetState& ns = *e->net;
+    if (int r = net_ensure_capacity(e, max_boards)) return r;
+    // the trunk output buffer is where the block rotation of launch_tower ends: act[0] after an even number of swaps
+    ns.trunk_out = ns.act[(ns.blocks & 1) ? 2 : 0].as<__nv_bfloat16>();
+    fe.planes = ns.act_in.as<__nv_bfloat16>();
+    fe.S = ns.cap_S;
+    ps.arch = ns.arch;
+    ps.psz = ns.policy_out;
+    ps.logits = ns.logits.as<float>();
+    ps.stats = ns.stats.as<float2>();
+    ps.values = ns.values.as<float>();
+    ps.S = ns.cap_S;
+    ps.partials = ns.partials.as<float2>();
+    ps.groups = ns.policy_groups * 4;
+    ps.trunk = ns.trunk_out;
+    ps.value_w = ns.value_w.as<float>();
+    ps.value_b = ns.value_bias;
+    return TAK_OK;
+}
+
+int net_forward(tak_engine* e, const uint8_t* d_states, const int* d_index, int boards, float* d_policy_out,
+                int raw_logits) {
     TB_CHECK(e->net, TAK_ERR_NO_NETWORK, "no network: call net_create first");
     NetState& ns = *e->net;
     TB_CHECK(ns.arch != 0, TAK_ERR_BAD_ARG, "internal: forward on the DummyNet");
     TB_CHECK(ns.loaded, TAK_ERR_NO_NETWORK, "network weights not loaded");
     if (boards == 0) return TAK_OK;
     int r = TAK_ERR_BAD_ARG;
-    if (e->n == 5) r = forward_t<5>(e, d_states, d_index, boards, d_policy_out);
-    if (e->n == 6) r = forward_t<6>(e, d_states, d_index, boards, d_policy_out);
+    if (e->n == 5) r = forward_t<5>(e, d_states, d_index, boards, d_policy_out, raw_logits);
+    if (e->n == 6) r = forward_t<6>(e, d_states, d_index, boards, d_policy_out, raw_logits);
     return r;
 }
 
@@ -362,7 +417,16 @@ int32_t net_game_repr(tak_engine_t* e, const tak_state_t* states, int32_t b, flo
     return TAK_OK;
 }
 
+static int32_t policy_eval_impl(tak_engine_t* e, const tak_state_t* states, int32_t b, float* out_policy,
+                                float* out_value, int raw_logits);
 int32_t net_policy_eval(tak_engine_t* e, const tak_state_t* states, int32_t b, float* out_policy, float* out_value) {
+    return policy_eval_impl(e, states, b, out_policy, out_value, 0);
+}
+int32_t net_policy_logits(tak_engine_t* e, const tak_state_t* states, int32_t b, float* out_logits, float* out_value) {
+    return policy_eval_impl(e, states, b, out_logits, out_value, 1);
+}
+static int32_t policy_eval_impl(tak_engine_t* e, const tak_state_t* states, int32_t b, float* out_policy,
+                                float* out_value, int raw_logits) {
     TB_CHECK(e && states && out_policy && out_value && b >= 0, TAK_ERR_BAD_ARG, "net_policy_eval: bad argument");
     TB_CHECK(e->net, TAK_ERR_NO_NETWORK, "no network: call net_create first");
     if (b == 0) return TAK_OK;
@@ -370,7 +434,7 @@ int32_t net_policy_eval(tak_engine_t* e, const tak_state_t* states, int32_t b, f
     NetState& ns = *e->net;
     const int psz = ns.policy_out;
     if (ns.arch == 0) {  // DummyNet: policy all ones, eval 0 (search/tests.rs:29-34)
-        for (size_t i = 0; i < size_t(b) * psz; ++i) out_policy[i] = 1.0f;
+        for (size_t i = 0; i < size_t(b) * psz; ++i) out_policy[i] = raw_logits ? 0.0f : 1.0f;
         for (int i = 0; i < b; ++i) out_value[i] = 0.0f;
         return TAK_OK;
     }
@@ -379,7 +443,8 @@ int32_t net_policy_eval(tak_engine_t* e, const tak_state_t* states, int32_t b, f
         const int cur = std::min(chunk, b - done);
         if (int r = stage_states(e, states + done, cur)) return r;
         TB_CUDA(ns.stage_policy.ensure(size_t(cur) * psz * 4));
-        if (int r = net_forward(e, ns.stage_states.as<uint8_t>(), nullptr, cur, ns.stage_policy.as<float>())) return r;
+        if (int r = net_forward(e, ns.stage_states.as<uint8_t>(), nullptr, cur, ns.stage_policy.as<float>(), raw_logits))
+            return r;
         TB_CUDA(cudaMemcpyAsync(out_policy + size_t(done) * psz, ns.stage_policy.p, size_t(cur) * psz * 4,
                                 cudaMemcpyDeviceToHost, e->stream));
         TB_CUDA(cudaMemcpyAsync(out_value + done, ns.values.p, size_t(cur) * 4, cudaMemcpyDeviceToHost, e->stream));

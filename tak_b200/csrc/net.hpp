@@ -3,6 +3,7 @@
 #include <cuda_bf16.h>
 
 #include "engine.hpp"
+#include "eval_views.hpp"
 
 namespace tb {
 
@@ -50,8 +51,12 @@ struct NetState {
 
 // Evaluate `boards` packed states (d_states[index[i]] or d_states[i] if index == nullptr) on the engine stream.
 // Leaves logits / stats / values on device; optionally writes the full softmax policy [boards][policy_out].
-int net_forward(tak_engine* e, const uint8_t* d_states, const int* d_index, int boards, float* d_policy_out);
+int net_forward(tak_engine* e, const uint8_t* d_states, const int* d_index, int boards, float* d_policy_out,
+                int raw_logits = 0);
 int net_ensure_capacity(tak_engine* e, int boards);
+// fused search loop (mcts.cu): tower over the planes the rollout warps wrote, board count read on the device
+int net_tower_fast(tak_engine* e, int max_boards, const int* d_count);
+int net_fast_views(tak_engine* e, int max_boards, FastEval& fe, PriorSource& ps);
 int net_load_blob(tak_engine* e, const float* blob, int64_t elems);
 int64_t net_blob_elems(const NetState& ns);
 void train_destroy(tak_engine* e);   // train.cu

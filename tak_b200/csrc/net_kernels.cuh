@@ -55,18 +55,11 @@ __device__ __forceinline__ float repr_plane(const ReprCtx<N>& cx, int ch, Col co
     return 0.f;  // channel padding up to 128
 }
 
-// one warp per board; `states` = packed records of the boards to encode (index list optional).  Pad columns and the
-// tile remainder are zero already: the input planes (NetState::act_in) are zero-filled at allocation and only real
-// squares are ever written to them.
-// (launch bounds: at most 40 registers per thread, so that a block fits in the 11 776 registers a resident conv-tower
-// CTA of the OTHER engine replica leaves free on an SM -- at 42 the encode of one replica waited for the other's tower)
+// game_repr of the game a warp holds in registers -> strip planes of evaluation slot w.  Pad columns and the tile
+// remainder are zero already: the input planes (NetState::act_in) are zero-filled at allocation and only real squares
+// are ever written to them.
 template <int N>
-__global__ void __launch_bounds__(256, 6)
-    k_encode(const uint8_t* states, const int* index, int n_boards, __nv_bfloat16* planes, int S) {
-    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (w >= n_boards) return;
-    WarpGame<N> g;
-    g.load(states + size_t(index ? index[w] : w) * StateLayout<N>::S);
+__device__ __forceinline__ void encode_board(const WarpGame<N>& g, int w, __nv_bfloat16* planes, int S) {
     ReprCtx<N> cx;
     cx.to_move = g.to_move; cx.ws = g.ws; cx.wc = g.wc; cx.bs = g.bs; cx.bc = g.bc;
     const int fcd = int(int8_t(g.flat_diff() - g.half_komi / 2));
@@ -93,6 +86,19 @@ __global__ void __launch_bounds__(256, 6)
             *reinterpret_cast<uint4*>(planes + (size_t(chunk) * S + slot) * 8) = v;
         }
     }
+}
+
+// one warp per board; `states` = packed records of the boards to encode (index list optional).
+// (launch bounds: at most 40 registers per thread, so that a block fits in the 11 776 registers a resident conv-tower
+// CTA of the OTHER engine replica leaves free on an SM -- at 42 the encode of one replica waited for the other's tower)
+template <int N>
+__global__ void __launch_bounds__(256, 6)
+    k_encode(const uint8_t* states, const int* index, int n_boards, __nv_bfloat16* planes, int S) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= n_boards) return;
+    WarpGame<N> g;
+    g.load(states + size_t(index ? index[w] : w) * StateLayout<N>::S);
+    encode_board<N>(g, w, planes, S);
 }
 
 template <int N>
@@ -148,10 +154,7 @@ __device__ __forceinline__ float block_reduce_sum(float v, float* s_tmp) {
 // The conv epilogue already reduced every slot's channels to {max, sum exp(l - max)} per 32-channel lane quarter
 // (partials[group*4 + quarter][S]); one warp per board merges the N*N x parts partials: stats[b] = {max, sum of exp(l - max)}.
 template <int N>
-__global__ void __launch_bounds__(256)
-    k_policy_stats_conv(const float2* partials, int S, int groups, int n_boards, float2* stats) {
-    const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (b >= n_boards) return;
+__device__ __forceinline__ float2 warp_policy_stats(const float2* partials, int S, int groups, int b) {
     constexpr int NSQ = N * N;
     const int l = threadIdx.x & 31;
     float mx = -INFINITY;
@@ -169,13 +172,21 @@ __global__ void __launch_bounds__(256)
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(FULL, sum, o);
-    if (l == 0) stats[b] = make_float2(mx, sum);
+    return make_float2(mx, sum);
+}
+template <int N>
+__global__ void __launch_bounds__(256)
+    k_policy_stats_conv(const float2* partials, int S, int groups, int n_boards, float2* stats) {
+    const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (b >= n_boards) return;
+    const float2 st = warp_policy_stats<N>(partials, S, groups, b);
+    if ((threadIdx.x & 31) == 0) stats[b] = st;
 }
 // full softmax vector [b][n_ch * N*N] (index = ch*N*N + row*N + col) from the logits and the board statistics: the
 // host-facing Network::policy_eval surface (network.rs:34); the search gathers only the legal moves' priors instead.
 template <int N>
 __global__ void __launch_bounds__(256)
-    k_policy_full_conv(const float* logits, int S, int n_ch, const float2* stats, float* policy_out) {
+    k_policy_full_conv(const float* logits, int S, int n_ch, const float2* stats, float* policy_out, int raw) {
     const int b = blockIdx.x;
     constexpr int NSQ = N * N;
     const float2 st = stats[b];
@@ -183,13 +194,13 @@ __global__ void __launch_bounds__(256)
     for (int i = threadIdx.x; i < n_ch * NSQ; i += blockDim.x) {
         const int ch = i / NSQ, sq = i % NSQ;
         const float lg = logits[size_t(ch) * S + SlotMap<N>::slot(b, sq / N, sq % N)];
-        dst[i] = __fdiv_rn(expf(__fsub_rn(lg, st.x)), st.y);
+        dst[i] = raw ? lg : __fdiv_rn(expf(__fsub_rn(lg, st.x)), st.y);   // raw: the pre-softmax logits (parity surface)
     }
 }
 
 // softmax statistics / full policy over a dense logits row [b][n_out]
 static __global__ void __launch_bounds__(256)
-    k_policy_stats_dense(const float* logits, int n_out, float2* stats, float* policy_out) {
+    k_policy_stats_dense(const float* logits, int n_out, float2* stats, float* policy_out, int raw) {
     __shared__ float s_tmp[8];
     const int b = blockIdx.x;
     const float* row = logits + size_t(b) * n_out;
@@ -202,15 +213,12 @@ static __global__ void __launch_bounds__(256)
     if (threadIdx.x == 0) stats[b] = make_float2(mx, sum);
     if (policy_out)
         for (int j = threadIdx.x; j < n_out; j += blockDim.x)
-            policy_out[size_t(b) * n_out + j] = __fdiv_rn(expf(__fsub_rn(row[j], mx)), sum);
+            policy_out[size_t(b) * n_out + j] = raw ? row[j] : __fdiv_rn(expf(__fsub_rn(row[j], mx)), sum);
 }
 
 // value head (net6.rs:104-107 / net5.rs:109): tanh(fc(flatten_NCHW(s)))  -- one warp per board
 template <int N>
-__global__ void __launch_bounds__(256)
-    k_value(const __nv_bfloat16* act, int S, const float* wv /*[128*NSQ]*/, float bv, int n_boards, float* out) {
-    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (w >= n_boards) return;
+__device__ __forceinline__ float warp_value(const __nv_bfloat16* act, int S, const float* wv /*[128*NSQ]*/, float bv, int w) {
     constexpr int NSQ = N * N;
     const int l = threadIdx.x & 31;
     float acc = 0.f;
@@ -230,7 +238,15 @@ __global__ void __launch_bounds__(256)
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
-    if (l == 0) out[w] = tanhf(acc + bv);
+    return tanhf(acc + bv);
+}
+template <int N>
+__global__ void __launch_bounds__(256)
+    k_value(const __nv_bfloat16* act, int S, const float* wv /*[128*NSQ]*/, float bv, int n_boards, float* out) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= n_boards) return;
+    const float val = warp_value<N>(act, S, wv, bv, w);
+    if ((threadIdx.x & 31) == 0) out[w] = val;
 }
 
 }  // namespace tb

@@ -113,7 +113,10 @@ struct SpView {
     uint64_t seed;
 };
 
-// "play winning moves if there are any" (self_play.rs:119-171)
+// "play winning moves if there are any" (self_play.rs:119-171).  The scan walks EVERY legal move (in chunks of
+// TAK_REPLAY_MAX_CHILDREN through shared memory); the record keeps the first TAK_REPLAY_MAX_CHILDREN (move, visits) pairs
+// and a position with more legal moves than that is counted in counts[2] (selfplay_step then fails with
+// TAK_ERR_CAPACITY rather than hand out a truncated policy target).
 template <int N>
 __global__ void __launch_bounds__(GAME_THREADS) k_sp_instant_win(SpView sp, MctsView mv) {
     __shared__ uint64_t s_lo[GAME_WARPS_PER_BLOCK][64], s_hi[GAME_WARPS_PER_BLOCK][64];
@@ -125,26 +128,34 @@ __global__ void __launch_bounds__(GAME_THREADS) k_sp_instant_win(SpView sp, Mcts
     const int wi = (threadIdx.x >> 5);
     const int l = threadIdx.x & 31;
     constexpr int S = StateLayout<N>::S;
+    constexpr int CHUNK = TAK_REPLAY_MAX_CHILDREN;
     WarpGame<N> g;
     g.load(sp.states + size_t(w) * S);
-    if (g.ply < 2) return;  // fresh slot waiting for its opening (reference quirk)
-    const int total = g.generate([&](int k, uint16_t m) {
-        if (k < TAK_REPLAY_MAX_CHILDREN) s_moves[wi][k] = m;
-    });
-    __syncwarp();
-    const int n = total < TAK_REPLAY_MAX_CHILDREN ? total : TAK_REPLAY_MAX_CHILDREN;
-    bool win = false;
+    if (g.ply < 2) return;  // fresh slot waiting for its opening (reference quirk); no move can win yet
     const int mover = g.to_move;
-    for (int k = 0; k < n; ++k) {
-        WarpGame<N> c = g;
-        c.template play<false>(s_moves[wi][k]);
-        const uint8_t r = c.result();
-        const bool wk = ((r & 0xF) == RES_WHITE && mover == 0) || ((r & 0xF) == RES_BLACK && mover == 1);
-        if (l == 0) s_win[wi][k] = wk;
-        win |= wk;
+    bool win = false;
+    int total = 0;
+    // later chunks first, the record's chunk (moves 0..CHUNK-1) last so that s_moves / s_win hold it afterwards
+    const int n_chunks = (g.count_total() + CHUNK - 1) / CHUNK;
+    for (int c = n_chunks - 1; c >= 0; --c) {
+        const int lo = c * CHUNK;
+        total = g.generate([&](int k, uint16_t m) {
+            if (k >= lo && k < lo + CHUNK) s_moves[wi][k - lo] = m;
+        });
+        __syncwarp();
+        const int cnt = min(CHUNK, total - lo);
+        for (int k = 0; k < cnt; ++k) {
+            WarpGame<N> ch = g;
+            ch.template play<false>(s_moves[wi][k]);
+            const uint8_t r = ch.result();
+            const bool wk = ((r & 0xF) == RES_WHITE && mover == 0) || ((r & 0xF) == RES_BLACK && mover == 1);
+            if (l == 0) s_win[wi][k] = wk;
+            win |= wk;
+        }
+        __syncwarp();
     }
-    __syncwarp();
     if (!win) return;
+    const int n = total < CHUNK ? total : CHUNK;
     // example with 1000 fake visits on winning moves, 1 elsewhere (self_play.rs:131-140)
     int slot = 0;
     if (l == 0) slot = atomicAdd(sp.counts + 0, 1);
@@ -313,16 +324,12 @@ static int step_t(tak_engine* e, int moves) {
         TB_CUDA(cudaGetLastError());
         if (s.cfg.noise_ply > 0) {
             // node.rollout(game) then apply_dirichlet for plies below NOISE_PLIES (self_play.rs:174-180)
-            if (int r = mcts_launch_rollout(e, nullptr, G, 1, sp.noise_on)) return r;
-            if (int r = mcts_eval_and_backup(e)) return r;
+            if (int r = mcts_fast_rollouts(e, nullptr, G, 1, sp.noise_on)) return r;
             if (int r = mcts_launch_dirichlet(e, nullptr, G, sp.noise_on, s.cfg.noise_alpha, s.cfg.noise_ratio, sp.seed,
                                               sp.tags))
                 return r;
         }
-        for (int i = 0; i < s.cfg.rollouts; ++i) {
-            if (int r = mcts_launch_rollout(e, nullptr, G, 1, nullptr)) return r;
-            if (int r = mcts_eval_and_backup(e)) return r;
-        }
+        if (int r = mcts_fast_rollouts(e, nullptr, G, s.cfg.rollouts, nullptr)) return r;
         if (int r = mcts_launch_pick(e, nullptr, G, sp.sample, sp.seed, sp.tags, sp.moves)) return r;
         k_sp_record<N><<<wb, GAME_THREADS, 0, e->stream>>>(sp, m.view());
         e->launches++;
@@ -416,6 +423,15 @@ int32_t selfplay_step(tak_engine_t* e, int32_t moves, tak_selfplay_stats_t* out_
         out_stats->kernel_launches = e->launches - launches0;
         out_stats->records = uint64_t(s.h_counts[0] - rec0);
         out_stats->device_ms = ms;
+        out_stats->records_truncated = uint64_t(s.h_counts[2]);
+    }
+    if (r == TAK_OK) {
+        if (!out_stats) cudaMemcpy(s.h_counts, s.counts.p, 16, cudaMemcpyDeviceToHost);
+        if (s.h_counts[2] != 0) {
+            set_error("%d position(s) had more than %d legal moves: their replay records would be truncated",
+                      s.h_counts[2], TAK_REPLAY_MAX_CHILDREN);
+            r = TAK_ERR_CAPACITY;
+        }
     }
     cudaEventDestroy(t0);
     cudaEventDestroy(t1);

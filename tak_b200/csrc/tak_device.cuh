@@ -299,6 +299,31 @@ struct WarpGame {
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
         return s;
     }
+    // possible_moves()[pick(len)] without materialising the list: only the lane whose square owns index `pick`
+    // enumerates its moves.  `total` receives possible_moves().len(); pick(total) must be in [0, total).
+    template <class PickFn>
+    __device__ __forceinline__ uint16_t select_move(PickFn&& pick_of, int& total) const {
+        int n0, n1;
+        count_moves(n0, n1);
+        int inc0 = n0, inc1 = n1;
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) {
+            const int t0 = __shfl_up_sync(FULL, inc0, s);
+            const int t1 = __shfl_up_sync(FULL, inc1, s);
+            if (lane() >= s) { inc0 += t0; inc1 += t1; }
+        }
+        const int tot0 = __shfl_sync(FULL, inc0, 31);
+        total = tot0 + __shfl_sync(FULL, inc1, 31);
+        if (total == 0) return 0xFFFF;
+        const int pick = pick_of(total);
+        uint16_t chosen = 0xFFFF;
+        auto emit = [&](int k, uint16_t mv) { if (k == pick) chosen = mv; };
+        const int b0 = inc0 - n0, b1 = tot0 + inc1 - n1;
+        if (pick >= b0 && pick < b0 + n0) emit_square(lane(), c0, h0, b0, emit);
+        if (TWO && pick >= b1 && pick < b1 + n1) emit_square(lane() + 32, c1, h1, b1, emit);
+        const unsigned m = __ballot_sync(FULL, chosen != 0xFFFF);
+        return uint16_t(__shfl_sync(FULL, int(chosen), m ? __ffs(m) - 1 : 0));
+    }
 
     // ---- Game::play (game.rs:121-209) ---------------------------------------------------------------------
     // CHECK = validate like the reference and return its PlayError code; without CHECK the move must be legal.
@@ -509,6 +534,95 @@ struct ThreadPos {
             }
         }
         return total;
+    }
+};
+
+// ---- one THREAD per child: Game::play (game.rs:121-209) applied IN PLACE to a packed record ---------------------------
+// perft's expansion stages a copy of the parent record per child in shared memory; a child differs from its parent in at
+// most N+1 squares and the 48-byte tail, so one thread patches the copy (a few u64 / u8 accesses) and hands the new tail
+// to ThreadPos for result() / count_moves().  The move must be legal (it comes from possible_moves of the parent).
+template <int N>
+struct RecordPlay {
+    using L = StateLayout<N>;
+    using Col = typename L::Col;
+
+    __device__ __forceinline__ static void apply(uint8_t* rec, uint16_t mv, ThreadPos<N>& tp) {
+        Col* cols = reinterpret_cast<Col*>(rec);
+        uint8_t* hts = rec + L::HTS_OFF;
+        tp.load(rec);
+        StateScalars& sc = tp.sc;
+        const int sq = mv & 63;
+        const unsigned mask = mv >> 8;
+        const int kind = (mv >> 6) & 3;
+        const int o = (sq % N) * N + (sq / N);
+        const uint64_t obit = 1ull << o;
+        const bool swapped = sc.ply < 2;
+        if (mask == 0) {
+            // execute_place (game.rs:147-169)
+            const bool black = swapped ? (sc.to_move == 0) : (sc.to_move == 1);
+            cols[o] = black ? Col(1) : Col(0);
+            hts[o] = 1;
+            if (kind == 1) tp.walls |= obit;
+            if (kind == 2) tp.caps |= obit;
+            if (kind <= 1) {
+                if ((sc.to_move == 0) != swapped) sc.ws -= 1; else sc.bs -= 1;
+            } else {
+                if (sc.to_move == 0) sc.wc -= 1; else sc.bc -= 1;
+            }
+            sc.reversible = 0;
+            tp.occ |= obit;
+            if (black) tp.blk |= obit;
+        } else {
+            // execute_spread (game.rs:171-209)
+            const int p = 8 - (__ffs(mask) - 1);
+            const int drops = __popc(mask);
+            const int delta = kind == 0 ? 1 : kind == 1 ? -1 : kind == 2 ? -N : N;
+            const Col src = cols[o];
+            const int sh = hts[o];
+            const bool src_cap = (tp.caps >> o) & 1, src_wall = (tp.walls >> o) & 1;
+            const unsigned carry = unsigned(src >> (sh - p)) & ((1u << p) - 1);   // bit 0 = bottom-most carried piece
+            const int rem_h = sh - p;
+            const Col rem = src & ((Col(1) << rem_h) - 1);
+            cols[o] = rem;
+            hts[o] = uint8_t(rem_h);
+            if (rem_h == 0) {
+                tp.occ &= ~obit;
+                tp.blk &= ~obit;
+            } else if ((rem >> (rem_h - 1)) & 1) {
+                tp.blk |= obit;
+            } else {
+                tp.blk &= ~obit;
+            }
+            unsigned m = mask;
+            int off = 0, q = o;
+            for (int t = 0; t < drops; ++t) {
+                q += delta;
+                const int dt = __clz(m << 24) + 1;
+                m = (m << dt) & 0xFF;
+                const unsigned seg = (carry >> off) & ((1u << dt) - 1);
+                off += dt;
+                const int qh = hts[q];
+                cols[q] = cols[q] | (Col(seg) << qh);
+                hts[q] = uint8_t(qh + dt);
+                const uint64_t qbit = 1ull << q;
+                tp.occ |= qbit;
+                if ((seg >> (dt - 1)) & 1) tp.blk |= qbit; else tp.blk &= ~qbit;
+            }
+            // top-piece kinds: the source loses its kind; the last drop square takes it (a wall there is flattened)
+            const uint64_t lbit = 1ull << q;
+            tp.walls &= ~(obit | lbit);
+            tp.caps &= ~obit;
+            if (src_wall) tp.walls |= lbit;
+            if (src_cap) tp.caps |= lbit;
+            sc.reversible = uint8_t(sc.reversible + 1);
+        }
+        sc.ply = uint16_t(sc.ply + 1);
+        sc.to_move ^= 1;
+        *reinterpret_cast<uint4*>(rec + L::BB_OFF) =
+            make_uint4(uint32_t(tp.walls), uint32_t(tp.walls >> 32), uint32_t(tp.caps), uint32_t(tp.caps >> 32));
+        *reinterpret_cast<uint4*>(rec + L::SC_OFF) = *reinterpret_cast<const uint4*>(&sc);
+        *reinterpret_cast<uint4*>(rec + L::DER_OFF) =
+            make_uint4(uint32_t(tp.occ), uint32_t(tp.occ >> 32), uint32_t(tp.blk), uint32_t(tp.blk >> 32));
     }
 };
 

@@ -261,7 +261,7 @@ static int train_chunk_t(tak_engine* e, TrainState& t, const float* d_in, const 
             fp.wp = t.fc_wp.as<bf>(); fp.x = t.fc_x.as<bf>(); fp.bias = master + t.pb_off; fp.logits = t.logits.as<float>();
             fp.n_out = J; fp.boards = B; fp.b_pad = b_pad; fp.n_pos = N * N; fp.j_tiles = P; fp.n_tiles = b_pad / FC_NT;
             TB_CUDA(fc_tc_launch(fp, e->num_sms, e->stream));
-            k_policy_stats_dense<<<B, 256, 0, e->stream>>>(t.logits.as<float>(), J, t.stats.as<float2>(), nullptr);
+            k_policy_stats_dense<<<B, 256, 0, e->stream>>>(t.logits.as<float>(), J, t.stats.as<float2>(), nullptr, 0);
             k_value_train<N><<<wblocks, 256, 0, e->stream>>>(trunk, S, master + t.vw_off, master + t.vb_off, B,
                                                              t.values.as<float>());
             t.launches += 4;

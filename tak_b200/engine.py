@@ -194,6 +194,24 @@ class Engine:
         check(self.lib.tak_perft_stats(self._h, C.byref(ms), C.byref(mat), C.byref(launches)))
         return {"ms": ms.value, "materialised": mat.value, "launches": launches.value}
 
+    def perft_profile(self):
+        out = (C.c_double * 6)()
+        check(self.lib.tak_perft_profile(self._h, out))
+        return {"ms": out[0], "expand_ms": out[1], "materialised": int(out[2]), "launches": int(out[3]),
+                "top_children": int(out[4]), "top_ms": out[5]}
+
+    def playouts(self, first: int, count: int, seed: int, max_plies: int, ply_spread: int = 0, game_id_base: int = 0):
+        """Uniform-random playouts of games [first, first+count) on the device (tak_playouts): returns
+        (plies added per game, final GameResult per game, {"plies", "generated", "ms"})."""
+        plies = np.zeros(max(count, 1), dtype=np.int32)
+        res = np.zeros(max(count, 1), dtype=np.uint8)
+        tot = (C.c_uint64 * 2)()
+        ms = C.c_double()
+        check(self.lib.tak_playouts(self._h, first, count, seed, game_id_base, max_plies, ply_spread,
+                                    plies.ctypes.data_as(C.POINTER(C.c_int32)),
+                                    res.ctypes.data_as(C.POINTER(C.c_uint8)), tot, C.byref(ms)))
+        return plies[:count], res[:count], {"plies": int(tot[0]), "generated": int(tot[1]), "ms": ms.value}
+
     # ---- alpha_tak::Network --------------------------------------------------------------------------------
     def net_create(self, arch: int):
         check(self.lib.net_create(self._h, arch))
@@ -229,6 +247,18 @@ class Engine:
         check(self.lib.net_policy_eval(self._h, arr, b, pol.ctypes.data_as(C.POINTER(C.c_float)),
                                        val.ctypes.data_as(C.POINTER(C.c_float))))
         return pol, val
+
+    def policy_logits(self, states: Sequence[TakState]) -> Tuple[np.ndarray, np.ndarray]:
+        """The forward pass of `policy_eval`, returning the pre-softmax policy logits [B, policy_size] and eval [B]."""
+        b = len(states)
+        lg = np.zeros((b, self.policy_size), dtype=np.float32)
+        val = np.zeros(b, dtype=np.float32)
+        if b == 0:
+            return lg, val
+        arr = (TakState * b)(*states)
+        check(self.lib.net_policy_logits(self._h, arr, b, lg.ctypes.data_as(C.POINTER(C.c_float)),
+                                         val.ctypes.data_as(C.POINTER(C.c_float))))
+        return lg, val
 
     def net_forward_timed(self, first: int, count: int, reps: int) -> float:
         ms = C.c_double()
@@ -382,6 +412,13 @@ class Engine:
         p, k, _keep = _ids(ids)
         out = np.zeros(k, dtype=np.uint16)
         check(self.lib.mcts_pick_move(self._h, p, k, out.ctypes.data_as(C.POINTER(C.c_uint16))))
+        return out
+
+    def pick_move_sampled(self, ids, seed: int) -> np.ndarray:
+        """`Node::pick_move(false)`: visit-weighted draw per listed game (counter-based: seed x game id)."""
+        p, k, _keep = _ids(ids)
+        out = np.zeros(k, dtype=np.uint16)
+        check(self.lib.mcts_pick_move_sampled(self._h, p, k, seed, out.ctypes.data_as(C.POINTER(C.c_uint16))))
         return out
 
     def tree_play(self, ids, moves):

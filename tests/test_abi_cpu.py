@@ -38,8 +38,8 @@ def test_struct_layouts_match_header():
     assert C.sizeof(tb.TakState) == 16 + 64 + 64 + 512 + 512 == C.sizeof(oracle.TakState)
     assert C.sizeof(_lib.EngineConfig) == 32
     assert C.sizeof(_lib.SelfplayConfig) == 64
-    assert C.sizeof(_lib.SelfplayStats) == 64
-    assert C.sizeof(tb.ReplayRecord) == 16 + C.sizeof(tb.TakState) + 256 * 2 + 256 * 4
+    assert C.sizeof(_lib.SelfplayStats) == 96
+    assert C.sizeof(tb.ReplayRecord) == 16 + C.sizeof(tb.TakState) + 512 * 2 + 512 * 4
 
 
 def test_no_cpu_fallback():

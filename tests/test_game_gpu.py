@@ -227,3 +227,94 @@ def test_tps_consistency(golden):
             assert (back.to_move, back.ply) == (st.to_move, st.ply)
             assert (back.white_caps, back.white_stones, back.black_caps, back.black_stones) == \
                    (st.white_caps, st.white_stones, st.black_caps, st.black_stones)
+
+
+def test_perft_from_deep_positions_all_sizes():
+    """perf_count (tak/tests/perft.rs:3-18) from positions cut out of long random playouts, N = 3..8: the expansion
+    patches packed records one thread per child (RecordPlay) -- tall stacks, multi-drop spreads, flattening capstones,
+    u128 columns on 7x7 / 8x8 -- and classifies them from the tail it builds; counts must equal the oracle's."""
+    for n, count, depth, lo, hi in ((3, 6, 4, 2, 14), (4, 6, 3, 4, 40), (5, 6, 3, 10, 80), (6, 6, 3, 20, 120),
+                                    (7, 4, 2, 40, 160), (8, 4, 2, 60, 200)):
+        games = random_positions(n, count, seed=300 + n, min_ply=lo, max_ply=hi)
+        eng = tb.Engine(n, 8, nodes_per_game=64)
+        for g in games:
+            st = to_tb_state(g.state())
+            for d in range(1, depth + 1):
+                assert eng.perft(st, d) == g.perft(d), (n, d, g.tps())
+        roots = [to_tb_state(g.state()) for g in games]
+        assert eng.perft_multi(roots, depth) == sum(g.perft(depth) for g in games)
+        eng.close()
+
+
+def test_device_playouts_match_oracle():
+    """tak_playouts: uniform-random playouts on the device (state in registers from the first to the last ply) against
+    the same loop over the oracle -- plies, results and final positions, with a full and a staggered ply budget."""
+    seed = 0x51ED
+    for n, G in ((5, 12), (6, 12), (8, 10)):
+        eng = tb.Engine(n, G, nodes_per_game=64)
+        for max_plies, spread, base in ((10_000, 0, 0), (30, 25, 1000)):
+            eng.reset(0, G, 4)
+            plies, res, tot = eng.playouts(0, G, seed, max_plies, spread, game_id_base=base)
+            states = eng.download(list(range(G)))
+            gen = 0
+            for gid in range(G):
+                g = oracle.Game(n, 4)
+                budget = max_plies + (splitmix(seed ^ splitmix((base + gid) ^ 0xC0FFEE)) % spread if spread else 0)
+                k = 0
+                while g.result() == 0 and k < budget:
+                    moves = g.possible_moves()
+                    gen += len(moves)
+                    ply = g.state().ply
+                    g.play(moves[splitmix(seed ^ splitmix(((base + gid) << 32) | ply)) % len(moves)])
+                    k += 1
+                assert k == int(plies[gid]) and g.result() == int(res[gid]), (n, gid)
+                assert states[gid].key() == bytes(g.state()), (n, gid)
+            assert tot["plies"] == int(plies.sum()) and tot["generated"] == gen
+        eng.close()
+
+
+def test_8x8_stacks_taller_than_64():
+    """u128 stack columns above bit 63 (reference edge case, SURVEY.md section 7: "stacks deeper than 64"): 8x8 positions
+    built from TPS (legal piece counts) with (a) a 70-piece stack owned by the mover -- carries are cut out across the
+    64-bit boundary -- once with a flat and once with a capstone on top, and (b) a 62-piece stack next to a 10-piece stack
+    of the mover -- drops push it over the boundary.  Move lists, every child position, results, the children's own move
+    lists and perft(2) are compared with the oracle."""
+    n = 8
+    alt = lambda k, first: "".join("12"[(i + first) % 2] for i in range(k))
+    cases = [
+        (f"x8/x8/x8/x8/x3,2S,x4/x8/1,x,2,x5/{alt(70, 1)},{alt(24, 0)},x,1S,x4 1 70", 70, 63),   # white flat on 70
+        (f"x8/x8/x8/x8/x3,1S,x4/x8/2,x,1,x5/{alt(69, 1)}2C,{alt(24, 1)},x,2S,x4 2 70", 70, 63),  # black cap on 70
+        (f"x8/x8/x8/x8/x3,2S,x4/x8/1,x,2,x5/{alt(62, 0)},{alt(10, 1)},x,1S,x4 1 60", 62, 70),   # 62 + up to 8 dropped
+    ]
+    for tps, tallest_parent, tallest_child_min in cases:
+        og = oracle.Game.from_tps(n, tps)
+        st = tb.tps_parse(n, tps)
+        assert bytes(st) == bytes(og.state()), tps
+        assert max(st.height) == tallest_parent and max(st.white_stones, st.black_stones) <= 50
+        eng = tb.Engine(n, 512, nodes_per_game=64)
+        eng.upload([0], [st])
+        moves = og.possible_moves()
+        assert list(eng.possible_moves([0])[0]) == moves
+        k = len(moves)
+        ids = list(range(k))
+        eng.upload(ids, [st] * k)
+        assert not eng.play(ids, moves).any()
+        res = eng.result(ids)
+        tallest = 0
+        children = []
+        for i, (child, mv) in enumerate(zip(eng.download(ids), moves)):
+            g = og.clone()
+            assert g.play(mv) == 0
+            assert child.key() == bytes(g.state()), tb.format_move(mv, n)
+            assert int(res[i]) == g.result()
+            tallest = max(tallest, max(child.height))
+            children.append(g)
+        assert tallest >= tallest_child_min and any(any(c.state().stack_hi) for c in children)
+        for depth in (1, 2):
+            assert eng.perft(st, depth) == og.perft(depth)
+        # second ply: children whose stacks sit across the boundary generate moves too
+        lists = eng.possible_moves(ids)
+        for i, g in enumerate(children):
+            if g.result() == 0:
+                assert list(lists[i]) == g.possible_moves()
+        eng.close()

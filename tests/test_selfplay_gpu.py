@@ -90,3 +90,58 @@ def test_selfplay_records_and_restart():
         seen_games.add((rec.game_id, rec.game_serial))
     assert len(seen_games) >= total_games - G  # the last step's games may still be held
     eng.close()
+
+
+def _splitmix(x):
+    x = (x + 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+    x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+    x = ((x ^ (x >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+    return x ^ (x >> 31)
+
+
+@pytest.mark.parametrize("n,arch,G,R,passes", [(3, 0, 12, 40, 40), (4, 0, 12, 40, 40), (5, 5, 6, 32, 8), (6, 6, 6, 32, 8)])
+def test_selfplay_with_instant_win_matches_reference_loop(n, arch, G, R, passes):
+    """The bench's configuration minus the two thread_rng consumers: instant-win shortcut ON, always exploit, noise off.
+    The device loop is compared pass by pass with oracle/selfplay_ref.py (the restatement of self_play.rs:96-262): every
+    slot's position after each pass, and every completed Example (position, (move, visits) list incl. the 1000/1 fake
+    visits of an instant win, result from the mover's perspective) -- including the reference's quirk that a slot reset
+    by an instant win is searched from the empty board in the same pass."""
+    from oracle.selfplay_ref import SelfPlayParallel
+    seed, base = 0x7A4B, 1000
+    eng = _engine(n, arch, G)
+    eng.selfplay_begin(rollouts=R, half_komi=4, instant_win=1, exploit_ply=0, noise_ply=0, seed=seed, game_id_base=base)
+
+    def coin(slot, serial):   # k_sp_opening's draw: a<N> when the hash is odd
+        return bool(_splitmix(seed ^ _splitmix(((base + slot) << 32) | serial)) & 1)
+
+    def policy_eval(states):
+        return eng.policy_eval([to_tb_state(s) for s in states])
+
+    ref = SelfPlayParallel(n, G, R, policy_eval=policy_eval if arch else None, coin=coin, exploit_plies=0,
+                           instant_win=True)
+    ids = list(range(G))
+    got = []
+    instant = 0
+    for it in range(passes):
+        st = eng.selfplay_step(1)
+        assert st.records_truncated == 0
+        got += eng.selfplay_drain(1 << 14)
+        ref.iteration()
+        after = eng.download(ids)
+        for gid in ids:
+            assert after[gid].key() == bytes(ref.games[gid].state()), f"pass {it} slot {gid}: positions differ"
+    want = {(base + e.slot, e.serial, int(e.state.ply)): e for e in ref.examples}
+    seen = set()
+    for rec in got:
+        key = (rec.game_id, rec.game_serial, int(rec.state.ply))
+        assert key in want and key not in seen, key
+        seen.add(key)
+        e = want[key]
+        assert bytes(rec.state) == bytes(e.state)
+        assert [(rec.moves[i], rec.visits[i]) for i in range(rec.n_children)] == e.policy, key
+        assert rec.result == e.result
+        instant += any(v == 1000 for _, v in e.policy) and all(v in (1, 1000) for _, v in e.policy)
+    assert seen == set(want), "completed examples differ"
+    if arch == 0:
+        assert instant >= 3 and ref.completed_games >= G, (instant, ref.completed_games)
+    eng.close()
