@@ -309,6 +309,9 @@ typedef struct tak_replay_record {
 
 int32_t selfplay_begin(tak_engine_t* e, const tak_selfplay_config_t* cfg);
 int32_t selfplay_step(tak_engine_t* e, int32_t moves, tak_selfplay_stats_t* out_stats);
+/* selfplay_drain moves the device-side record ring to the host, completes the records of finished games (result from the
+ * mover's perspective) and pops up to `cap` of them into `out`.  With out == NULL and cap == 0 it only reports how many
+ * completed records are waiting (size a buffer, then call again). */
 int32_t selfplay_drain(tak_engine_t* e, tak_replay_record_t* out, int32_t cap, int32_t* out_count);
 
 /* ---- alpha_tak::Example: replay text format and 8-fold symmetry augmentation -----
@@ -328,6 +331,33 @@ int32_t tak_symmetry_move(int32_t n, uint16_t move, int32_t k, uint16_t* out);
 int32_t tak_symmetry_state(const tak_state_t* s, int32_t k, tak_state_t* out);
 int32_t examples_to_tensors(tak_engine_t* e, const tak_replay_record_t* recs, int32_t count, float* inputs, float* pi,
                             float* z, int32_t on_device);
+
+/* ---- multi-GPU: NCCL inside the boundary -----------------------------------------------------
+ * One engine (one process, one GPU) per rank.  Games never interact, so the rollout loop has no collective; the three
+ * exchanges of the sharded loop run on the engine's stream, ordered with the kernels around them:
+ * tak_comm_unique_id      ncclGetUniqueId: 128 opaque bytes made by ONE rank and handed to the others by the host program
+ *                         (the Rust `train` binary would pass them over its own channel: file, socket, MPI ...)
+ * tak_comm_init           ncclCommInitRank for this engine; collective over all `world` ranks
+ * net_broadcast_weights   the trainer publishes a network (train/src/main.rs:101-105,120 `network = new_network`):
+ *                         rank `root` passes its fp32 blob (net_load_weights layout), every rank ends with that network
+ *                         loaded (BatchNorm folded, operands packed) -- ncclBroadcast over NVLink
+ * selfplay_gather_replay  `examples.extend(...)` across ranks (self_play.rs:165,254): every rank passes the records it
+ *                         drained and receives ALL ranks' records in rank order -- ncclAllGather of fixed-size records
+ * net_train_allreduce     data-parallel Network::train: the gradient accumulators of all ranks are summed in place
+ *                         (ncclAllReduce on the engine stream, i.e. after the chunks that produced them and before the
+ *                         Adam kernel of net_train_step); gradients of chunks add in the reference (network.rs:84-95)
+ * tak_comm_sum_u64 / tak_comm_max_f64   small host-value reductions (perft counts of a sharded frontier, timings)   */
+#define TAK_COMM_ID_BYTES 128
+int32_t tak_comm_unique_id(uint8_t* out, int32_t cap);
+int32_t tak_comm_init(tak_engine_t* e, const uint8_t* unique_id, int32_t rank, int32_t world);
+int32_t tak_comm_destroy(tak_engine_t* e);
+int32_t tak_comm_info(tak_engine_t* e, int32_t* out_rank, int32_t* out_world, uint64_t* out_bytes_moved);
+int32_t net_broadcast_weights(tak_engine_t* e, const float* blob, int64_t elems, int32_t root);
+int32_t selfplay_gather_replay(tak_engine_t* e, const tak_replay_record_t* local, int32_t n_local,
+                               tak_replay_record_t* out, int32_t cap, int32_t* out_count);
+int32_t net_train_allreduce(tak_engine_t* e);
+int32_t tak_comm_sum_u64(tak_engine_t* e, uint64_t* inout, int32_t n);
+int32_t tak_comm_max_f64(tak_engine_t* e, double* inout, int32_t n);
 
 #ifdef __cplusplus
 }

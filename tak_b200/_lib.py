@@ -174,6 +174,15 @@ SYMBOLS = {
     "tak_symmetry_move": (_i32, [_i32, _u16, _i32, _P(_u16)]),
     "tak_symmetry_state": (_i32, [_P(TakState), _i32, _P(TakState)]),
     "examples_to_tensors": (_i32, [_vp, _P(ReplayRecord), _i32, _P(_f32), _P(_f32), _P(_f32), _i32]),
+    "tak_comm_unique_id": (_i32, [_P(C.c_uint8), _i32]),
+    "tak_comm_init": (_i32, [_vp, _P(C.c_uint8), _i32, _i32]),
+    "tak_comm_destroy": (_i32, [_vp]),
+    "tak_comm_info": (_i32, [_vp, _P(_i32), _P(_i32), _P(_u64)]),
+    "net_broadcast_weights": (_i32, [_vp, _P(_f32), C.c_int64, _i32]),
+    "selfplay_gather_replay": (_i32, [_vp, _P(ReplayRecord), _i32, _P(ReplayRecord), _i32, _P(_i32)]),
+    "net_train_allreduce": (_i32, [_vp]),
+    "tak_comm_sum_u64": (_i32, [_vp, _P(_u64), _i32]),
+    "tak_comm_max_f64": (_i32, [_vp, _P(C.c_double), _i32]),
 }
 
 _lib = None
@@ -185,6 +194,24 @@ class TakNativeError(RuntimeError):
         self.code = code
 
 
+def _preload_nccl() -> None:
+    """libtaknative.so needs libnccl.so.2.  PyTorch bundles its own (newer) NCCL under site-packages/nvidia/nccl and loads
+    it by that SONAME too; whichever is loaded first serves both.  Load the bundled one first when it exists so that a
+    later `import torch` in the same process finds the version it was built against; otherwise the system library that
+    the linker recorded is used."""
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        paths = list(spec.submodule_search_locations) if spec and spec.submodule_search_locations else []
+        for base in paths:
+            cand = os.path.join(base, "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                C.CDLL(cand, mode=C.RTLD_GLOBAL)
+                return
+    except Exception:
+        pass
+
+
 def load() -> C.CDLL:
     """dlopen the in-tree shared library and bind every declared symbol (raises if one is missing)."""
     global _lib
@@ -194,6 +221,7 @@ def load() -> C.CDLL:
                 f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(make -C tak_b200/csrc).  tak_b200 has no CPU fallback."
             )
+        _preload_nccl()
         lib = C.CDLL(LIB_PATH)
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(lib, name)  # AttributeError if the library does not export it

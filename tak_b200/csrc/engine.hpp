@@ -70,6 +70,7 @@ struct NetState;      // net.cu
 struct MctsState;     // mcts.cu
 struct SelfplayState; // selfplay.cu
 struct ExamplesState; // examples.cu
+struct CommState;     // comm.cu
 
 }  // namespace tb
 
@@ -121,6 +122,7 @@ struct tak_engine {
     tb::MctsState* mcts = nullptr;
     tb::SelfplayState* selfplay = nullptr;
     tb::ExamplesState* examples = nullptr;
+    tb::CommState* comm = nullptr;
     uint64_t launches = 0;  // kernels launched by this engine (gpu_launches in bench.py)
 };
 
@@ -134,6 +136,7 @@ void net_destroy(tak_engine* e);
 void mcts_destroy(tak_engine* e);
 void selfplay_destroy(tak_engine* e);
 void examples_destroy(tak_engine* e);
+void comm_destroy(tak_engine* e);
 // host helper shared by modules: policy index of a move (alpha_tak::search::move_index)
 int host_move_index(int n, uint16_t mv);
 int host_policy_size(int n);

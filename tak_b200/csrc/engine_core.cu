@@ -3,6 +3,8 @@
 // tak/tests/perft.rs:3-18 (counting rule).
 #include <cub/device/device_scan.cuh>
 
+#include <cstdlib>
+
 #include "engine.hpp"
 #include "game_kernels.cuh"
 
@@ -99,10 +101,19 @@ static int check_ids(tak_engine_t* e, const int32_t* ids, int32_t n) {
 static constexpr size_t PF_CAP = size_t(1) << 24;
 
 // `frontier` holds n parents at `depth_left` >= 2 plies above the counted level; counts[i] = children of parent i
-template <int N>
+static int perft_variant() {
+    static const int v = [] {
+        const char* s = std::getenv("TAK_PERFT_VARIANT");
+        const int x = s ? std::atoi(s) : 3;
+        return x == 0 || x == 1 || x == 5 ? x : 3;
+    }();
+    return v;
+}
+
+template <int N, int V>
 static int perft_level(tak_engine* e, const uint8_t* frontier, size_t n, const uint32_t* d_counts, int depth_left,
                        int level, unsigned long long* d_leaves) {
-    using P = PerftCfg<N>;
+    using P = PerftCfg<N, V>;
     constexpr int S = StateLayout<N>::S;
     TB_CHECK(level < tak_engine::PF_LEVELS, TAK_ERR_BAD_ARG, "perft too deep");
     TB_CHECK(n < (size_t(1) << 31), TAK_ERR_CAPACITY, "perft frontier too large");
@@ -130,8 +141,8 @@ static int perft_level(tak_engine* e, const uint8_t* frontier, size_t n, const u
     if (int r = offset_at(n, &total)) return r;
     if (total == 0) return TAK_OK;
     const bool last = depth_left == 2;   // the children of this frontier are the counted level
-    TB_CUDA(cudaFuncSetAttribute(k_perft_apply<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, P::SMEM));
-    TB_CUDA(cudaFuncSetAttribute(k_perft_apply<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, P::SMEM));
+    TB_CUDA(cudaFuncSetAttribute(k_perft_apply<N, true, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, P::SMEM));
+    TB_CUDA(cudaFuncSetAttribute(k_perft_apply<N, false, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, P::SMEM));
     size_t begin = 0;
     uint64_t begin_off = 0;
     while (begin < n) {
@@ -166,13 +177,13 @@ static int perft_level(tak_engine* e, const uint8_t* frontier, size_t n, const u
             }
             k_perft_moves<N><<<warp_blocks(int(end - begin)), GAME_THREADS, 0, e->stream>>>(
                 frontier + begin * S, int(end - begin), d_counts + begin, d_off + begin, begin_off,
-                lv.moves.as<uint16_t>(), lv.block_parent.as<int>());
+                lv.moves.as<uint16_t>(), lv.block_parent.as<int>(), P::CH);
             if (last)
-                k_perft_apply<N, true><<<n_blocks, P::THREADS, P::SMEM, e->stream>>>(
+                k_perft_apply<N, true, V><<<n_blocks, P::THREADS, P::SMEM, e->stream>>>(
                     frontier + begin * S, int(end - begin), d_off + begin, begin_off, lv.block_parent.as<int>(), n_blocks,
                     int(children), lv.moves.as<uint16_t>(), lv.children.as<uint8_t>(), nullptr, d_leaves);
             else
-                k_perft_apply<N, false><<<n_blocks, P::THREADS, P::SMEM, e->stream>>>(
+                k_perft_apply<N, false, V><<<n_blocks, P::THREADS, P::SMEM, e->stream>>>(
                     frontier + begin * S, int(end - begin), d_off + begin, begin_off, lv.block_parent.as<int>(), n_blocks,
                     int(children), lv.moves.as<uint16_t>(), lv.children.as<uint8_t>(), lv.counts.as<uint32_t>(), d_leaves);
             if (ev1) TB_CUDA(cudaEventRecord(ev1, e->stream));
@@ -180,7 +191,7 @@ static int perft_level(tak_engine* e, const uint8_t* frontier, size_t n, const u
             e->pf_materialised += children;
             TB_CUDA(cudaGetLastError());
             if (!last)
-                if (int r = perft_level<N>(e, lv.children.as<uint8_t>(), children, lv.counts.as<uint32_t>(),
+                if (int r = perft_level<N, V>(e, lv.children.as<uint8_t>(), children, lv.counts.as<uint32_t>(),
                                            depth_left - 1, level + 1, d_leaves))
                     return r;
         }
@@ -203,7 +214,12 @@ static int perft_roots(tak_engine* e, const uint8_t* roots, size_t n, int depth,
     e->pf_launches++;
     TB_CUDA(cudaGetLastError());
     if (last) return TAK_OK;
-    return perft_level<N>(e, roots, n, d_counts, depth, 0, d_leaves);
+    switch (perft_variant()) {
+        case 0: return perft_level<N, 0>(e, roots, n, d_counts, depth, 0, d_leaves);
+        case 1: return perft_level<N, 1>(e, roots, n, d_counts, depth, 0, d_leaves);
+        case 5: return perft_level<N, 5>(e, roots, n, d_counts, depth, 0, d_leaves);
+        default: return perft_level<N, 3>(e, roots, n, d_counts, depth, 0, d_leaves);
+    }
 }
 
 extern "C" {
@@ -248,6 +264,7 @@ int32_t tak_engine_destroy(tak_engine_t* e) {
     if (!e) return TAK_OK;
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
+    comm_destroy(e);
     examples_destroy(e);
     selfplay_destroy(e);
     mcts_destroy(e);

@@ -112,33 +112,39 @@ __global__ void __launch_bounds__(256)
 //   k_perft_moves  one warp per parent: possible_moves -> moves_out[offsets[w] ...]; it also records, for every block
 //                  boundary that falls inside its children, which parent the block starts in (block_parent).
 //   k_perft_apply  per block: (1) every child finds its parent (binary search between the block's first and last
-//                  parent), (2) the parents' records are copied into per-child images in shared memory, 16 B per thread,
-//                  (3) ONE THREAD per child patches its image in place (RecordPlay: at most N+1 squares and the tail)
-//                  and classifies / counts the new position from the tail it just built (ThreadPos: Game::result +
-//                  possible_moves().len()), (4) the block streams its images out as one contiguous run of 16-byte
-//                  stores.  The child counts feed the next level's scan; at the last level they ARE perf_count's
-//                  answer (perft.rs:6-7), so no position is ever re-read by a separate count kernel.
+//                  parent); (2) the parents' heights + tail words are copied into per-child images in shared memory;
+//                  (3) ONE THREAD per child patches its image in place and lists the (at most N) new stack columns
+//                  (ChildPatch: 176 bytes per child on 6x6 instead of a 384-byte record, which is what keeps ~1 300
+//                  children in flight per SM), then classifies / counts the new position from the tail it just built
+//                  (ThreadPos: Game::result + possible_moves().len()); (4) the block streams the children out with
+//                  16-byte stores: stack-column words come from the parent (L1) unless the patch names one of their
+//                  squares, heights + tail from the images.  The child counts feed the next level's scan; at the last
+//                  level they ARE perf_count's answer (perft.rs:6-7): no position is re-read by a separate count kernel.
 // HBM traffic per child: S written + S/b read (the parent, once per block that touches it) + 2 B move written + read
 // + 4 B count -- SURVEY.md 8(d)'s S + S/b + 2 within 2 %.
-template <int N>
+// Variant V (TAK_PERFT_VARIANT, measured on B200, 6x6 perft(5), G states/s of the depth-3 -> 4 expansion):
+//   0: 256 threads, conflict-free (odd) image pitch 9.6 | 1: 256, dense pitch 10.1 | 3: 128, dense 11.1 (default) |
+//   5: 64, dense.  Smaller blocks and the 160-byte pitch put more blocks on an SM (shared memory is the limiter), which
+//   hides the L1 / shared-memory latency of the one-thread-per-child phase better than avoiding its 2-way bank conflicts.
+template <int N, int V = 3>
 struct PerftCfg {
     static constexpr int S = StateLayout<N>::S;
     static constexpr int W = S / 16;                  // 16-byte words per record
-    static constexpr int CH = N <= 6 ? 128 : 64;      // children per block
-    static constexpr int STRIDE = S + 16;             // image pitch in shared memory (16 B of skew against bank conflicts)
-    static constexpr int THREADS = 256;
+    static constexpr int THREADS = 256 >> (V >> 1);
+    static constexpr int CH = THREADS;                // children per block: one patch thread each
+    static constexpr int STRIDE = (V & 1) ? (ChildPatch<N>::RAW + 15) / 16 * 16 : ChildPatch<N>::STRIDE;
     static constexpr int SMEM = CH * STRIDE + CH * 4;
+    static constexpr bool STREAM = false;             // st.global.cs for the children: no effect (measured)
 };
 
 template <int N>
 __global__ void __launch_bounds__(GAME_THREADS)
     k_perft_moves(const uint8_t* frontier, int n, const uint32_t* counts, const uint64_t* offsets, uint64_t base_off,
-                  uint16_t* moves_out, int* block_parent) {
+                  uint16_t* moves_out, int* block_parent, int CH /* children per k_perft_apply block */) {
     const int w = warp_global_id();
     if (w >= n) return;
     const uint32_t cnt = counts[w];
     if (cnt == 0) return;
-    constexpr int CH = PerftCfg<N>::CH;
     WarpGame<N> g;
     g.load(frontier + size_t(w) * StateLayout<N>::S);
     const uint64_t base = offsets[w] - base_off;
@@ -147,20 +153,22 @@ __global__ void __launch_bounds__(GAME_THREADS)
     for (uint64_t b = (base + CH - 1) / CH + (threadIdx.x & 31); b * CH < base + cnt; b += 32) block_parent[b] = w;
 }
 
-template <int N, bool LAST>
-__global__ void __launch_bounds__(PerftCfg<N>::THREADS)
+template <int N, bool LAST, int V = 3>
+__global__ void __launch_bounds__(PerftCfg<N, V>::THREADS)
     k_perft_apply(const uint8_t* frontier, int n_parents, const uint64_t* offsets, uint64_t base_off,
                   const int* block_parent, int n_blocks, int total_children, const uint16_t* moves, uint8_t* out,
                   uint32_t* child_counts, unsigned long long* leaves) {
-    using P = PerftCfg<N>;
-    extern __shared__ __align__(16) uint8_t s_img[];
-    int* s_parent = reinterpret_cast<int*>(s_img + P::CH * P::STRIDE);
+    using P = PerftCfg<N, V>;
+    using CP = ChildPatch<N>;
+    extern __shared__ __align__(16) uint8_t s_patch[];
+    int* s_parent = reinterpret_cast<int*>(s_patch + P::CH * P::STRIDE);
     const int t = threadIdx.x;
     const int c0 = blockIdx.x * P::CH;
     const int nc = min(P::CH, total_children - c0);
+    const uint4* src = reinterpret_cast<const uint4*>(frontier);
+    // (1) owner of child c = the LAST parent whose first child is <= c (parents without children share their offset
+    // with the next parent), searched between the owners of this block's and the next block's first child
     if (t < nc) {
-        // owner of child c = the LAST parent whose first child is <= c (parents without children share their offset
-        // with the next parent), searched between the owners of this block's and the next block's first child
         const uint64_t c = uint64_t(c0 + t);
         int lo = block_parent[blockIdx.x];
         int hi = int(blockIdx.x) + 1 < n_blocks ? block_parent[blockIdx.x + 1] : n_parents - 1;
@@ -171,32 +179,59 @@ __global__ void __launch_bounds__(PerftCfg<N>::THREADS)
         s_parent[t] = lo;
     }
     __syncthreads();
-    const uint4* src = reinterpret_cast<const uint4*>(frontier);
-    for (int idx = t; idx < nc * P::W; idx += P::THREADS) {
-        const int ch = idx / P::W, wd = idx - ch * P::W;
-        *reinterpret_cast<uint4*>(s_img + ch * P::STRIDE + wd * 16) = __ldg(src + size_t(s_parent[ch]) * P::W + wd);
+    // (2) the parents' heights + tail words -> per-child images
+    {
+        constexpr int DCH = P::THREADS / CP::TW, DWD = P::THREADS % CP::TW;
+        int ch = t / CP::TW, wd = t - ch * CP::TW;
+        for (int idx = t; idx < nc * CP::TW; idx += P::THREADS) {
+            *reinterpret_cast<uint4*>(s_patch + ch * P::STRIDE + wd * 16) =
+                __ldg(src + size_t(s_parent[ch]) * P::W + CP::HT0 + wd);
+            ch += DCH;
+            wd += DWD;
+            if (wd >= CP::TW) { wd -= CP::TW; ++ch; }
+        }
     }
     __syncthreads();
+    // (3) one thread per child: patch, classify, count
     unsigned long long add = 0;
     if (t < nc) {
         ThreadPos<N> tp;
-        RecordPlay<N>::apply(s_img + t * P::STRIDE, moves[c0 + t], tp);
+        CP::build(frontier + size_t(s_parent[t]) * P::S, moves[c0 + t], s_patch + t * P::STRIDE, tp);
         uint32_t cnt = 0;
         if (tp.result() != RES_ONGOING) {
             add = 1;                                   // a finished game counts 1 wherever it ends (perft.rs:4)
         } else {
-            const uint32_t total = tp.count_moves();
+            const uint32_t total = tp.count_moves();   // heights come from the patched image
             if (LAST) add = total; else cnt = total;   // depth 1: the number of legal moves (perft.rs:6-7)
         }
         if (!LAST) child_counts[c0 + t] = cnt;
     }
     __syncthreads();
+    // (4) stream the children out: stack-column words (parent's unless patched), then heights + tail from the images
     uint4* dst = reinterpret_cast<uint4*>(out) + size_t(c0) * P::W;
-    for (int idx = t; idx < nc * P::W; idx += P::THREADS) {
-        const int ch = idx / P::W, wd = idx - ch * P::W;
-        dst[idx] = *reinterpret_cast<const uint4*>(s_img + ch * P::STRIDE + wd * 16);
+    {
+        constexpr int DCH = P::THREADS / CP::HT0, DWD = P::THREADS % CP::HT0;
+        int ch = t / CP::HT0, wd = t - ch * CP::HT0;
+        for (int idx = t; idx < nc * CP::HT0; idx += P::THREADS) {
+            const uint4 v = CP::cols_word(src + size_t(s_parent[ch]) * P::W, s_patch + ch * P::STRIDE, wd);
+            if (P::STREAM) __stcs(dst + ch * P::W + wd, v); else dst[ch * P::W + wd] = v;
+            ch += DCH;
+            wd += DWD;
+            if (wd >= CP::HT0) { wd -= CP::HT0; ++ch; }
+        }
     }
-    // block reduction of `add` (only the first CH threads carry a value)
+    {
+        constexpr int DCH = P::THREADS / CP::TW, DWD = P::THREADS % CP::TW;
+        int ch = t / CP::TW, wd = t - ch * CP::TW;
+        for (int idx = t; idx < nc * CP::TW; idx += P::THREADS) {
+            const uint4 v = *reinterpret_cast<const uint4*>(s_patch + ch * P::STRIDE + wd * 16);
+            if (P::STREAM) __stcs(dst + ch * P::W + CP::HT0 + wd, v); else dst[ch * P::W + CP::HT0 + wd] = v;
+            ch += DCH;
+            wd += DWD;
+            if (wd >= CP::TW) { wd -= CP::TW; ++ch; }
+        }
+    }
+    // block reduction of `add`
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) add += __shfl_xor_sync(FULL, add, o);
     __shared__ unsigned long long s_add[P::THREADS / 32];

@@ -5,6 +5,8 @@
 //   finished games are recorded and restarted.
 // The host only sequences kernel launches; no game or tree data crosses the PCIe bus inside the loop.
 #include <cmath>
+#include <climits>
+#include <deque>
 
 #include "game_kernels.cuh"
 #include "mcts.hpp"
@@ -32,7 +34,9 @@ struct SelfplayState {
     DevBuf events;      // SpEvent [ev_cap]
     DevBuf counts;      // int [4]: records, events, truncated children
     int* h_counts = nullptr;  // pinned [4]
-    std::vector<tak_replay_record_t> held;   // records of games that have not finished yet
+    std::vector<std::vector<tak_replay_record_t>> held;   // per slot: records of its game that has not finished yet
+    std::deque<tak_replay_record_t> ready;                // completed records not yet handed to the caller
+    std::vector<tak_replay_record_t> scratch;
     uint64_t move_counter = 0;
 };
 
@@ -439,49 +443,55 @@ int32_t selfplay_step(tak_engine_t* e, int32_t moves, tak_selfplay_stats_t* out_
 }
 
 int32_t selfplay_drain(tak_engine_t* e, tak_replay_record_t* out, int32_t cap, int32_t* out_count) {
-    TB_CHECK(e && out_count && (out || cap == 0), TAK_ERR_BAD_ARG, "selfplay_drain: bad argument");
+    TB_CHECK(e && out_count && (out || cap == 0) && cap >= 0, TAK_ERR_BAD_ARG, "selfplay_drain: bad argument");
     TB_CHECK(e->selfplay && e->selfplay->begun, TAK_ERR_BAD_ARG, "selfplay_drain before selfplay_begin");
     TB_CUDA(cudaSetDevice(e->device));
     SelfplayState& s = *e->selfplay;
+    const int G = e->max_games;
+    // 1. move the device ring to the host: records into their slot's bucket, finish events into a list
     TB_CUDA(cudaMemcpy(s.h_counts, s.counts.p, 16, cudaMemcpyDeviceToHost));
     const int nrec = std::min(s.h_counts[0], s.rec_cap), nev = std::min(s.h_counts[1], s.ev_cap);
-    const size_t held0 = s.held.size();
-    s.held.resize(held0 + size_t(nrec));
-    if (nrec)
-        TB_CUDA(cudaMemcpy(s.held.data() + held0, s.records.p, size_t(nrec) * sizeof(tak_replay_record_t),
+    if (s.held.size() != size_t(G)) s.held.resize(size_t(G));
+    const int base = s.cfg.game_id_base;
+    if (nrec) {
+        s.scratch.resize(size_t(nrec));
+        TB_CUDA(cudaMemcpy(s.scratch.data(), s.records.p, size_t(nrec) * sizeof(tak_replay_record_t),
                            cudaMemcpyDeviceToHost));
+        for (const auto& rec : s.scratch) {
+            const int slot = rec.game_id - base;
+            TB_CHECK(slot >= 0 && slot < G, TAK_ERR_CUDA, "internal: replay record of slot %d", slot);
+            s.held[size_t(slot)].push_back(rec);
+        }
+    }
     std::vector<SpEvent> events(static_cast<size_t>(nev));
     if (nev) TB_CUDA(cudaMemcpy(events.data(), s.events.p, size_t(nev) * sizeof(SpEvent), cudaMemcpyDeviceToHost));
     TB_CUDA(cudaMemset(s.counts.p, 0, 8));
-    // join: a record is complete once its (slot, serial) has a finish event (Example::complete, example.rs:19-25)
-    const int base = s.cfg.game_id_base;
+    // 2. join: a record is complete once its (slot, serial) has a finish event (Example::complete, example.rs:19-25);
+    //    the cost is proportional to the records of the games that finished, not to everything still held
+    for (const auto& ev : events) {
+        auto& bucket = s.held[size_t(ev.slot)];
+        size_t keep = 0;
+        for (size_t i = 0; i < bucket.size(); ++i) {
+            if (bucket[i].game_serial == ev.serial) {
+                bucket[i].result = bucket[i].state.to_move == 0 ? ev.white_result : -ev.white_result;
+                s.ready.push_back(bucket[i]);
+            } else {
+                if (keep != i) bucket[keep] = bucket[i];
+                ++keep;
+            }
+        }
+        bucket.resize(keep);
+    }
+    // 3. hand out completed records (all of them stay queued when the caller only asks for the count)
+    if (!out) {
+        *out_count = int(std::min<size_t>(s.ready.size(), size_t(INT32_MAX)));
+        return TAK_OK;
+    }
     int produced = 0;
-    std::vector<tak_replay_record_t> keep;
-    for (auto& rec : s.held) {
-        const SpEvent* hit = nullptr;
-        for (const auto& ev : events)
-            if (ev.slot + base == rec.game_id && ev.serial == rec.game_serial) { hit = &ev; break; }
-        if (!hit) { keep.push_back(rec); continue; }
-        if (produced < cap) {
-            rec.result = rec.state.to_move == 0 ? hit->white_result : -hit->white_result;
-            out[produced++] = rec;
-        } else {
-            keep.push_back(rec);  // caller buffer full: stays held; its event is re-queued below
-        }
+    while (produced < cap && !s.ready.empty()) {
+        out[produced++] = s.ready.front();
+        s.ready.pop_front();
     }
-    // events whose records did not all fit must survive until the next drain
-    if (!keep.empty() && nev) {
-        std::vector<SpEvent> again;
-        for (const auto& ev : events)
-            for (const auto& rec : keep)
-                if (ev.slot + base == rec.game_id && ev.serial == rec.game_serial) { again.push_back(ev); break; }
-        if (!again.empty()) {
-            TB_CUDA(cudaMemcpy(s.events.p, again.data(), again.size() * sizeof(SpEvent), cudaMemcpyHostToDevice));
-            const int cnt = int(again.size());
-            TB_CUDA(cudaMemcpy(reinterpret_cast<int*>(s.counts.p) + 1, &cnt, 4, cudaMemcpyHostToDevice));
-        }
-    }
-    s.held.swap(keep);
     *out_count = produced;
     return TAK_OK;
 }

@@ -502,6 +502,10 @@ struct ThreadPos {
     }
     // possible_moves().len(), as WarpGame::count_total
     __device__ __forceinline__ uint32_t count_moves() const {
+        return count_moves_h([&](int o) { return int(hts[o]); });
+    }
+    template <class H>
+    __device__ __forceinline__ uint32_t count_moves_h(H&& height_of) const {
         const int empties = __popcll(ALL & ~occ);
         if (sc.ply < 2) return uint32_t(empties);
         const int to_move = sc.to_move;
@@ -512,7 +516,7 @@ struct ThreadPos {
         while (mine) {
             const int o = __ffsll(static_cast<long long>(mine)) - 1;
             mine &= mine - 1;
-            const int h = hts[o];
+            const int h = height_of(o);
             const int maxp = h < N ? h : N;
             const bool is_cap = (caps >> o) & 1;
             const int r = o % N, c = o / N;
@@ -537,19 +541,44 @@ struct ThreadPos {
     }
 };
 
-// ---- one THREAD per child: Game::play (game.rs:121-209) applied IN PLACE to a packed record ---------------------------
-// perft's expansion stages a copy of the parent record per child in shared memory; a child differs from its parent in at
-// most N+1 squares and the 48-byte tail, so one thread patches the copy (a few u64 / u8 accesses) and hands the new tail
-// to ThreadPos for result() / count_moves().  The move must be legal (it comes from possible_moves of the parent).
+// ---- one THREAD per child: Game::play (game.rs:121-209) as a PATCH against the parent's packed record -----------------
+// A child differs from its parent in at most N stack columns (the source of a spread and its <= N-1 drop squares, or the
+// one square of a placement), a few height bytes and the 48-byte tail {walls, caps | scalars | occupied, black tops}.
+// perft's expansion keeps per child, in shared memory, only
+//   [ the record's words from the heights to the end (heights + tail, 96 B on 6x6), patched IN PLACE | the new columns,
+//     sorted by square | the bitboard of the squares whose column changed ]                  = 176 B on 6x6, not 384,
+// which is what lets ~1 300 children be in flight per SM.  The thread that owns the child patches the copy from the
+// parent's record (columns read through L1: ~100 siblings share them), and classifies / counts the new position from the
+// tail and heights it just wrote.  When the block streams the children out, a word of stack columns comes from the parent
+// unless the bitboard names one of its squares; the new column is then entry popcount(bitboard below the square).
+// The move must be legal (it comes from possible_moves of the parent).
 template <int N>
-struct RecordPlay {
+struct ChildPatch {
     using L = StateLayout<N>;
     using Col = typename L::Col;
+    static constexpr int NSQ = N * N;
+    static constexpr int HT0 = L::HTS_OFF / 16;            // first word of the heights = number of stack-column words
+    static constexpr int TW = L::S / 16 - HT0;             // words from the heights to the end of the record
+    static constexpr int OFF_TAIL = 0, OFF_DIRTY = TW * 16, OFF_COLS = OFF_DIRTY + 16;
+    static constexpr int RAW = OFF_COLS + N * int(sizeof(Col));
+    static constexpr int STRIDE = (((RAW + 15) / 16) | 1) * 16;   // an odd number of 16-byte units: conflict-free 16-byte accesses
 
-    __device__ __forceinline__ static void apply(uint8_t* rec, uint16_t mv, ThreadPos<N>& tp) {
-        Col* cols = reinterpret_cast<Col*>(rec);
-        uint8_t* hts = rec + L::HTS_OFF;
-        tp.load(rec);
+    // `img` holds the parent's words [HT0, S/16) on entry and the child's on exit; `tp` returns the child's tail
+    __device__ __forceinline__ static void build(const uint8_t* parent, uint16_t mv, uint8_t* img, ThreadPos<N>& tp) {
+        const Col* pcols = reinterpret_cast<const Col*>(parent);
+        uint8_t* hts = img + OFF_TAIL;                         // the heights are the first bytes of the imaged region
+        uint8_t* tail = img + OFF_TAIL + (L::BB_OFF - L::HTS_OFF);
+        Col* ocols = reinterpret_cast<Col*>(img + OFF_COLS);
+        {   // ThreadPos::load from the image
+            const uint4 bb = *reinterpret_cast<const uint4*>(tail);
+            const uint4 d = *reinterpret_cast<const uint4*>(tail + 32);
+            tp.walls = uint64_t(bb.x) | (uint64_t(bb.y) << 32);
+            tp.caps = uint64_t(bb.z) | (uint64_t(bb.w) << 32);
+            tp.occ = uint64_t(d.x) | (uint64_t(d.y) << 32);
+            tp.blk = uint64_t(d.z) | (uint64_t(d.w) << 32);
+            *reinterpret_cast<uint4*>(&tp.sc) = *reinterpret_cast<const uint4*>(tail + 16);
+            tp.hts = hts;
+        }
         StateScalars& sc = tp.sc;
         const int sq = mv & 63;
         const unsigned mask = mv >> 8;
@@ -557,10 +586,11 @@ struct RecordPlay {
         const int o = (sq % N) * N + (sq / N);
         const uint64_t obit = 1ull << o;
         const bool swapped = sc.ply < 2;
+        uint64_t dirty = obit;
         if (mask == 0) {
             // execute_place (game.rs:147-169)
             const bool black = swapped ? (sc.to_move == 0) : (sc.to_move == 1);
-            cols[o] = black ? Col(1) : Col(0);
+            ocols[0] = black ? Col(1) : Col(0);
             hts[o] = 1;
             if (kind == 1) tp.walls |= obit;
             if (kind == 2) tp.caps |= obit;
@@ -577,13 +607,15 @@ struct RecordPlay {
             const int p = 8 - (__ffs(mask) - 1);
             const int drops = __popc(mask);
             const int delta = kind == 0 ? 1 : kind == 1 ? -1 : kind == 2 ? -N : N;
-            const Col src = cols[o];
+            // the new columns are stored sorted by square: along the ray for Up / Right, against it for Down / Left
+            const bool asc = delta > 0;
+            const Col src = pcols[o];
             const int sh = hts[o];
             const bool src_cap = (tp.caps >> o) & 1, src_wall = (tp.walls >> o) & 1;
             const unsigned carry = unsigned(src >> (sh - p)) & ((1u << p) - 1);   // bit 0 = bottom-most carried piece
             const int rem_h = sh - p;
             const Col rem = src & ((Col(1) << rem_h) - 1);
-            cols[o] = rem;
+            ocols[asc ? 0 : drops] = rem;
             hts[o] = uint8_t(rem_h);
             if (rem_h == 0) {
                 tp.occ &= ~obit;
@@ -595,16 +627,17 @@ struct RecordPlay {
             }
             unsigned m = mask;
             int off = 0, q = o;
-            for (int t = 0; t < drops; ++t) {
+            for (int t = 1; t <= drops; ++t) {
                 q += delta;
                 const int dt = __clz(m << 24) + 1;
                 m = (m << dt) & 0xFF;
                 const unsigned seg = (carry >> off) & ((1u << dt) - 1);
                 off += dt;
                 const int qh = hts[q];
-                cols[q] = cols[q] | (Col(seg) << qh);
+                ocols[asc ? t : drops - t] = pcols[q] | (Col(seg) << qh);
                 hts[q] = uint8_t(qh + dt);
                 const uint64_t qbit = 1ull << q;
+                dirty |= qbit;
                 tp.occ |= qbit;
                 if ((seg >> (dt - 1)) & 1) tp.blk |= qbit; else tp.blk &= ~qbit;
             }
@@ -618,11 +651,36 @@ struct RecordPlay {
         }
         sc.ply = uint16_t(sc.ply + 1);
         sc.to_move ^= 1;
-        *reinterpret_cast<uint4*>(rec + L::BB_OFF) =
-            make_uint4(uint32_t(tp.walls), uint32_t(tp.walls >> 32), uint32_t(tp.caps), uint32_t(tp.caps >> 32));
-        *reinterpret_cast<uint4*>(rec + L::SC_OFF) = *reinterpret_cast<const uint4*>(&sc);
-        *reinterpret_cast<uint4*>(rec + L::DER_OFF) =
-            make_uint4(uint32_t(tp.occ), uint32_t(tp.occ >> 32), uint32_t(tp.blk), uint32_t(tp.blk >> 32));
+        uint4* tw = reinterpret_cast<uint4*>(tail);
+        tw[0] = make_uint4(uint32_t(tp.walls), uint32_t(tp.walls >> 32), uint32_t(tp.caps), uint32_t(tp.caps >> 32));
+        tw[1] = *reinterpret_cast<const uint4*>(&sc);
+        tw[2] = make_uint4(uint32_t(tp.occ), uint32_t(tp.occ >> 32), uint32_t(tp.blk), uint32_t(tp.blk >> 32));
+        *reinterpret_cast<uint2*>(img + OFF_DIRTY) = make_uint2(unsigned(dirty), unsigned(dirty >> 32));
+    }
+
+    // word `wd` < HT0 (stack columns) of the child's record
+    __device__ __forceinline__ static uint4 cols_word(const uint4* parent, const uint8_t* img, int wd) {
+        uint4 v = __ldg(parent + wd);
+        const uint2 dw = *reinterpret_cast<const uint2*>(img + OFF_DIRTY);
+        const uint64_t dirty = uint64_t(dw.x) | (uint64_t(dw.y) << 32);
+        if constexpr (sizeof(Col) == 8) {
+            const int q = 2 * wd;
+            const unsigned hit = unsigned(dirty >> q) & 3u;
+            if (hit) {
+                const int j = __popcll(dirty & ((1ull << q) - 1));      // new columns are sorted by square
+                if (hit & 1) {
+                    const uint2 c = *reinterpret_cast<const uint2*>(img + OFF_COLS + 8 * j);
+                    v.x = c.x; v.y = c.y;
+                }
+                if (hit & 2) {
+                    const uint2 c = *reinterpret_cast<const uint2*>(img + OFF_COLS + 8 * (j + (hit & 1)));
+                    v.z = c.x; v.w = c.y;
+                }
+            }
+        } else {
+            if ((dirty >> wd) & 1) v = *reinterpret_cast<const uint4*>(img + OFF_COLS + 16 * __popcll(dirty & ((1ull << wd) - 1)));
+        }
+        return v;
     }
 };
 

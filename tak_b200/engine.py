@@ -444,11 +444,17 @@ class Engine:
         check(self.lib.selfplay_step(self._h, moves, C.byref(st)))
         return st
 
-    def selfplay_drain(self, cap: int = 4096) -> List[ReplayRecord]:
-        arr = (ReplayRecord * cap)()
+    def selfplay_drain(self, cap: Optional[int] = None) -> List[ReplayRecord]:
+        """Completed replay records (games that finished), at most `cap` of them (default: all that are waiting).  The
+        records are copies: they do not keep the staging array alive."""
         cnt = C.c_int32()
-        check(self.lib.selfplay_drain(self._h, arr, cap, C.byref(cnt)))
-        return [arr[i] for i in range(cnt.value)]
+        check(self.lib.selfplay_drain(self._h, None, 0, C.byref(cnt)))      # how many completed records are waiting
+        k = cnt.value if cap is None else min(cap, cnt.value)
+        if k <= 0:
+            return []
+        arr = (ReplayRecord * k)()
+        check(self.lib.selfplay_drain(self._h, arr, k, C.byref(cnt)))
+        return [ReplayRecord.from_buffer_copy(arr[i]) for i in range(cnt.value)]
 
 
     # ---- alpha_tak::Example::to_tensors, batched (example.rs:63-78) -------------------------------------------
