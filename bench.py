@@ -200,53 +200,199 @@ def in_threads(fns):
 
 
 PERFT6_D5 = 1_253_506_520  # tak/tests/perft.rs:98 (the value the reference keeps commented out)
+PERFT5_D4 = 2_999_784      # tak/tests/perft.rs:64
+STATE_BYTES = {3: 160, 4: 192, 5: 288, 6: 384, 7: 896, 8: 1152}
 
 
-def movegen_mnodes(eng, world, rank, dev, pk):
+def bytes_per_node(n, branching):
+    """S (child state written) + S/b (parent read, amortised over its b children) + 2 B (move)."""
+    S = STATE_BYTES[n]
+    return S + S / max(branching, 1.0) + 2
+
+
+def movegen_mnodes(eng, world, rank, dev, pk, red):
     """The metric's second half: movegen + play + result throughput as perft(5) of the 6x6 opening position through the
-    C ABI (tak_perft), breadth-first on the device.  With N ranks the 1 260 positions two plies below the root are dealt
-    round-robin (tak_perft_multi expands a rank's share as one frontier) and the counts are summed with one all-reduce
-    (SURVEY.md section 8e)."""
-    from tak_b200 import parallel as par
-
+    C ABI (tak_perft), breadth-first on the device.  Two DIFFERENT rates come out of one run and are reported apart:
+      * counted: perft's node count / time -- 99 % of the 1.25e9 nodes are depth-5 leaves that perf_count only COUNTS
+        (perft.rs:6-7: `possible_moves().len()`), in closed form from the tail of their depth-4 parent;
+      * materialised: positions actually generated, applied, classified and written to HBM (depth <= 4: 13.7 M states).
+        The roofline is stated on the largest expansion (depth 3 -> 4, 13.59 M children) with SURVEY 8(d)'s bytes.
+    With N ranks the 1 260 positions two plies below the root are dealt round-robin (tak_perft_multi expands a rank's share
+    as one frontier) and the counts are summed with one all-reduce."""
     depth = 5
     eng.reset(0, 1, 0)                       # slot 0 of this rank's engine (self-play is over) holds the opening
     root = eng.download([0])[0]
-    ms, nodes, mat = 0.0, 0, 0
     eng.perft(root, depth)                   # warm-up at full depth: the frontier arenas are allocated here
-    if world == 1:
-        nodes = eng.perft(root, depth)
-        st = eng.perft_stats()
-        ms, mat = st["ms"], st["materialised"]
-    else:
-        # every rank builds the depth-2 frontier (1 260 positions, host-driven, untimed), takes every world-th position
-        # and expands its share in ONE breadth-first perft of the remaining depth
-        front, ended = eng.frontier(root, 2)
-        mine = front[rank::world]
-        eng.perft_multi(mine, depth - 2)     # warm-up: arenas sized for this share
-        nodes = eng.perft_multi(mine, depth - 2) + (ended if rank == 0 else 0)
-        st = eng.perft_stats()
-        ms, mat = st["ms"], st["materialised"]
-    total = int(par.sum_over_ranks(float(nodes), dev))
-    t_max = par.max_over_ranks(ms, dev)
-    mat_total = par.sum_over_ranks(float(mat), dev)
-    S = 384                                   # packed 6x6 state bytes
-    b = total / mat_total if mat_total else 0.0   # ~ mean branching of the counted level (92 from the opening)
-    # HBM bytes the breadth-first expansion must move: every materialised node is written once (S + 2 B move) and read
-    # once by the next level's count and once by its expand; the 1.25e9 leaves are only counted on chip
-    algo_bytes = mat_total * (3 * S + 2)
-    gbs = algo_bytes / (t_max * 1e-3) / 1e9 if t_max else 0.0
+    best = None
+    for _ in range(3):
+        if world == 1:
+            nodes = eng.perft(root, depth)
+        else:
+            # every rank builds the depth-2 frontier (1 260 positions, host-driven, untimed), takes every world-th
+            # position and expands its share in ONE breadth-first perft of the remaining depth
+            if best is None:
+                front, ended = eng.frontier(root, 2)
+                mine = front[rank::world]
+                eng.perft_multi(mine, depth - 2)     # warm-up: arenas sized for this share
+            nodes = eng.perft_multi(mine, depth - 2) + (ended if rank == 0 else 0)
+        prof = eng.perft_profile()
+        if best is None or prof["ms"] < best[1]["ms"]:
+            best = (nodes, prof)
+    nodes, prof = best
+    total = int(red.sum(nodes))
+    t_max = red.max(prof["ms"])
+    mat_total = red.sum(prof["materialised"])
+    # the largest expansion of this rank: children / parents = branching; bytes by the 8(d) formula
+    parents = max(1, prof["materialised"] - prof["top_children"]) if world == 1 else None
+    b = prof["top_children"] / parents if parents else 100.0
+    bpn = bytes_per_node(6, b)
+    gbs = prof["top_children"] * bpn / (prof["top_ms"] * 1e-3) / 1e9 if prof["top_ms"] else 0.0
     return {"value": total / (t_max * 1e-3) / 1e6 if t_max else None, "unit": "Mnodes/s",
+            "what": "COUNTED rate: perft node count / device time of the whole tak_perft call (best of 3)",
             "workload": "6x6 perft depth 5 from the opening via tak_perft (movegen + play + result, bit-exact count)"
                         + ("" if world == 1 else f"; the 1260 positions two plies down are dealt round-robin over {world} ranks "
                            "(that shallow frontier is built on the host, untimed), each rank's share is one tak_perft_multi"),
-            "nodes": total, "exact": total == PERFT6_D5, "ms": t_max, "materialised_states": int(mat_total),
-            "roofline": {"bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s",
-                         "frac": gbs / pk["hbm"] if pk["hbm"] else None,
-                         "note": "13.7 M states are materialised (depth <= 4: written once, read by the count and the "
-                                 "expand kernels); the 1.25e9 leaves are only counted, one thread per depth-4 parent from "
-                                 "the 96-byte tail of its record (closed-form move counts)",
-                         "mean_branching_last_level": b}}
+            "nodes": total, "exact": total == PERFT6_D5, "ms": t_max,
+            "materialised": {"states": int(mat_total), "gstates_per_s": mat_total / (t_max * 1e-3) / 1e9 if t_max else None,
+                             "what": "positions generated + applied + classified + written to HBM (depth <= 4), over the "
+                                     "time of the WHOLE call incl. scans, move lists and host round trips for the "
+                                     "frontier sizes; the depth-5 leaves are only counted"},
+            "roofline": {"bound": "hbm", "kernel": "k_perft_moves + k_perft_apply, depth 3 -> 4 expansion (rank 0)",
+                         "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"] if pk["hbm"] else None,
+                         "children": prof["top_children"], "ms": prof["top_ms"],
+                         "gstates_per_s": prof["top_children"] / (prof["top_ms"] * 1e-3) / 1e9 if prof["top_ms"] else None,
+                         "bytes_per_node": bpn, "branching": b,
+                         "formula": "S + S/b + 2 per materialised child (SURVEY.md 8d), S = 384",
+                         # dram__bytes_read.sum + dram__bytes_write.sum of k_perft_apply<6,true> for the same expansion
+                         # (ncu --set full, profiles/r02_perft_apply_ncu.txt): 5.16 GB written + 0.08 GB read
+                         "traffic": 5_240_076_000,
+                         "note": "ceiling by the same formula: peak / bytes_per_node = "
+                                 f"{pk['hbm'] / bpn:.1f} G states/s"}}
+
+
+def perft5_rate(local):
+    """configs[0] on the device: 5x5 perft(4) from the opening (tak/tests/perft.rs:57-64), the reference's CPU-runnable
+    case.  43 945 states are materialised, so the call is dominated by launch latency and the host reading back the
+    frontier sizes, not by bandwidth."""
+    import tak_b200 as tb
+    eng = tb.Engine(5, 4, device=local, nodes_per_game=64)
+    eng.reset(0, 1, 0)
+    root = eng.download([0])[0]
+    eng.perft(root, 4)
+    best = None
+    for _ in range(5):
+        nodes = eng.perft(root, 4)
+        prof = eng.perft_profile()
+        if best is None or prof["ms"] < best[1]["ms"]:
+            best = (nodes, prof)
+    eng.close()
+    nodes, prof = best
+    return {"value": nodes / (prof["ms"] * 1e-3) / 1e6, "unit": "Mnodes/s", "nodes": nodes, "exact": nodes == PERFT5_D4,
+            "ms": prof["ms"], "materialised_states": prof["materialised"], "launches": prof["launches"],
+            "workload": "5x5 perft depth 4 from the opening via tak_perft (configs[0]); launch/latency-bound at this size"}
+
+
+def stress8_rates(local, world, rank, red, pk):
+    """configs[4], 8x8 stress (deep stacks, long spreads, u128 columns), every rank on its own games (weak scaling):
+      A. tak_playouts: uniform-random playouts to termination from positions cut at ply 60..200 of other random playouts;
+         nodes = plies played (one generate + select + apply + result each); the game state stays in registers for the
+         whole playout, so this is issue/latency-bound, not HBM-bound (HBM sees one load and one store per game).
+      B. MCTS with the DummyNet prior (alpha-tak/src/search/tests.rs:29-34), 800 rollouts per position, one launch for
+         the whole search (nothing to evaluate, so nothing forces a kernel boundary)."""
+    import tak_b200 as tb
+    G = 148 * 32                          # 800 rollouts x ~200 children per expansion: 262 144 nodes per game and half
+    eng = tb.Engine(8, G, device=local, nodes_per_game=1 << 18, max_batch=64)
+    base = rank * G
+    eng.reset(0, G, 4)
+    eng.playouts(0, G, 0x8A8, 60, 141, game_id_base=base)        # cut positions, ply 60..200 (untimed)
+    ids = np.arange(G, dtype=np.int32)
+    start = eng.download(ids[:64])
+    deep = max(max(s.height) for s in start)
+    # B first (it leaves the positions unchanged)
+    eng.net_create(0)
+    eng.tree_reset(ids)
+    eng.rollouts(ids, 8)                                         # warm-up
+    eng.tree_reset(ids)
+    eng.sync()
+    t0 = time.perf_counter()
+    eng.rollouts(ids, 800)
+    dt_b = red.max(time.perf_counter() - t0)
+    root_visits = eng.root(0)[0]
+    eng.close()
+    # A: its own engine -- no search trees, so tens of thousands of games fit and fill the SMs
+    GA = 148 * 512
+    eng = tb.Engine(8, GA, device=local, nodes_per_game=64, max_batch=64)
+    base = rank * GA
+    eng.reset(0, GA, 4)
+    eng.playouts(0, GA, 0x8A8, 60, 141, game_id_base=base)       # cut positions, ply 60..200 (untimed)
+    plies, res, tot = eng.playouts(0, GA, 0x8A9, 100_000, 0, game_id_base=base)
+    ms_a = red.max(tot["ms"])
+    plies_all = red.sum(tot["plies"])
+    gen_all = red.sum(tot["generated"])
+    eng.close()
+    return {
+        "playouts": {"value": plies_all / (ms_a * 1e-3) / 1e6, "unit": "Mnodes/s", "nodes": int(plies_all),
+                     "moves_generated_per_s": gen_all / (ms_a * 1e-3), "ms": ms_a, "games": GA * world,
+                     "finished": int((res != 0).sum()), "deepest_start_stack": int(deep),
+                     "workload": "8x8 random playouts to termination from ply-60..200 positions (tak_playouts): nodes = "
+                                 "plies = positions generated + applied + classified; state register-resident, "
+                                 "issue/latency-bound (no HBM roofline: one 1152-byte load and store per game)"},
+        "mcts_dummy": {"value": G * world / dt_b, "unit": "moves/s", "rollouts_per_s": 800.0 * G * world / dt_b,
+                       "seconds": dt_b, "games": G * world, "rollouts": 800, "root_visits": int(root_visits),
+                       "workload": "8x8 MCTS, DummyNet prior, 800 rollouts per position on ply-60..200 positions "
+                                   "(mcts_rollouts: select/expand/backup only, ONE launch per search), host-timed"},
+    }
+
+
+def selfplay5_rate(local, world, rank, red, steps, warmup, blob5):
+    """configs[1]: 5x5 self-play, random-init Net5, 800 rollouts/move, Dirichlet noise off, always exploit, 1 B200 (every
+    rank its own games when N > 1)."""
+    import tak_b200 as tb
+    G = 148 * 6 * 8                       # 8 boards per conv tile on 5x5
+    eng = tb.Engine(5, G, device=local, nodes_per_game=1 << 17, max_batch=G)
+    eng.net_create(5)
+    eng.net_load_weights(blob5)
+    eng.selfplay_begin(rollouts=800, half_komi=4, instant_win=1, exploit_ply=0, noise_ply=0, seed=0x55,
+                       game_id_base=rank * G)
+    for _ in range(warmup):
+        eng.selfplay_step(1)
+        eng.selfplay_drain()
+    ms, plies, evals, launches = 0.0, 0, 0, 0
+    for _ in range(steps):
+        st = eng.selfplay_step(1)
+        ms += st.device_ms
+        plies += st.plies_played
+        evals += st.evals
+        launches += st.kernel_launches
+        eng.selfplay_drain()
+    eng.close()
+    t = red.max(ms)
+    return {"value": red.sum(plies) / (t * 1e-3), "unit": "moves/s", "ms_per_step": t / steps, "steps": steps,
+            "games": G * world, "evals_per_s": red.sum(evals) / (t * 1e-3), "launches_per_ply": launches / steps,
+            "frac_of_tensor_peak": red.sum(evals) / world / (t * 1e-3) * 132_198_400 / (pk_sustained() * 1e12),
+            "workload": "5x5 batched self-play, Net5 (random init), 800 rollouts/move, noise off, always exploit, "
+                        "instant-win on (configs[1])"}
+
+
+def pk_sustained():
+    return peaks()["bf16_sustained"]
+
+
+class Reducer:
+    """max / sum over ranks of host values: through the engine's NCCL communicator (C ABI) when there is one."""
+
+    def __init__(self, comm):
+        self.comm = comm
+
+    def max(self, x):
+        return float(self.comm.max_f64([x])[0]) if self.comm else float(x)
+
+    def sum(self, x):
+        if not self.comm:
+            return float(x)
+        if float(x).is_integer() and x >= 0:          # counts: exact
+            return float(self.comm.sum_u64([int(x)])[0])
+        return self.comm.sum_u64([int(round(x * 1e6))])[0] / 1e6   # anything else in micro-units
 
 
 def augment_rate(eng, recs, dev, pk):
@@ -280,18 +426,20 @@ def augment_rate(eng, recs, dev, pk):
             "hbm_write_gbs": out_bytes / dt / 1e9, "hbm_peak_gbs": pk["hbm"]}, (inputs, pi, z)
 
 
-def interactive_rates(local, blob_ptr, elems, states):
-    """The `analysis` / `playtak` / `pit` regime (one game, small batches): latency of Network::policy_eval through the
-    host-buffer ABI (alpha-tak/src/model/network.rs:34) and the rollouts/s of a single `Player` with batch 32
-    (analysis/src/main.rs prints the same figure as nps)."""
+def interactive_rates(local, blob, states):
+    """The `analysis` / `playtak` / `pit` / reference-`train` regime (small batches): latency of Network::policy_eval
+    through the host-buffer ABI (alpha-tak/src/model/network.rs:34), the rollouts/s of a single `Player` with batch 32
+    (analysis/src/main.rs prints the same figure as nps), and self-play at the reference's own size: WORKERS = 32
+    lock-step games x 800 rollouts (train/src/self_play.rs:94) -- the regime where launch latency, not throughput, rules."""
     import tak_b200 as tb
 
     # a search of one game for a second grows a tree of millions of nodes: its own engine with a deep node pool
     eng = tb.Engine(6, 2, device=local, nodes_per_game=1 << 23, max_batch=256)
     eng.net_create(6)
-    eng.net_load_weights_device(blob_ptr, elems)
+    eng.net_load_weights(blob)
     out = {"policy_eval_ms": {}, "what": "net_policy_eval(host states -> full softmax [b, 9036] + value on the host), "
-                                         "median of 20 calls; Player(batch 32).rollout() on one game for 1 s"}
+                                         "median of 20 calls; Player(batch 32).rollout() on one game for 1 s; "
+                                         "selfplay_step on 32 games x 800 rollouts"}
     for b in (1, 32, 256):
         st = states[:b]
         eng.policy_eval(st)
@@ -313,16 +461,30 @@ def interactive_rates(local, blob_ptr, elems, states):
     out["player_nps"] = n * batch / (time.perf_counter() - t0)
     out["player_batch"] = batch
     eng.close()
+    # the reference's own self-play size
+    eng = tb.Engine(6, 32, device=local, nodes_per_game=1 << 18, max_batch=32)
+    eng.net_create(6)
+    eng.net_load_weights(blob)
+    eng.selfplay_begin(rollouts=800, half_komi=4, instant_win=1, exploit_ply=40, noise_ply=80, noise_alpha=0.2,
+                       noise_ratio=0.3, seed=0x7A4B)
+    eng.selfplay_step(1)
+    t0 = time.perf_counter()
+    st = eng.selfplay_step(3)
+    dt = time.perf_counter() - t0
+    out["moves_per_s_32_games"] = st.plies_played / dt
+    out["ms_per_rollout_step_32_games"] = 1e3 * dt / (3 * 801)
+    out["launches_per_ply_32_games"] = st.kernel_launches / 3
+    eng.close()
     return out
 
 
-def train_rate(eng, tensors, world, dist, dev, pk, host_recs=None):
+def train_rate(eng, tensors, world, comm, red, pk, host_recs=None):
     """Network::train_inner + Adam (next row N1, network.rs:37-97) on the augmented examples of this run: chunks of
     500 examples x 8 symmetries = 4000 positions (CHUNK_SIZE, network.rs:19), inputs resident in HBM; with N ranks every
-    rank trains its own chunks and the fp32 gradient blob is all-reduced over NCCL before the Adam step."""
+    rank trains its own chunks and the fp32 gradient blob is all-reduced over NCCL (net_train_allreduce, on the engine's
+    stream) before the Adam step."""
     import torch
 
-    from tak_b200 import parallel as par_mod
     from tak_b200 import weights as W
 
     inputs, pi, z = tensors
@@ -348,24 +510,24 @@ def train_rate(eng, tensors, world, dist, dev, pk, host_recs=None):
         for _ in range(reps):
             eng.train_chunk(*eng.examples_to_tensors(recs, on_device=True))
         torch.cuda.synchronize()
-        dt = par_max((time.perf_counter() - t0) / reps, dev)
+        dt = red.max((time.perf_counter() - t0) / reps)
         e2e = {"value": world * B / dt, "unit": "positions/s", "ms_per_chunk": 1e3 * dt,
                "h2d_bytes_per_step": len(recs) * C.sizeof(type(recs[0])), "d2h_bytes_per_step": 8,
                "what": "host replay records -> examples_to_tensors(on_device) -> net_train_chunk -> (loss_p, loss_z)"}
-    g = eng.train_grad_tensor()
-    if dist:                                  # untimed: NCCL builds its rings / buffers for this size on first use
-        par_mod.allreduce_gradients(torch.zeros_like(g))
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    if dist:
-        par_mod.allreduce_gradients(g)
-        torch.cuda.synchronize()
-    t_ar = time.perf_counter() - t0
+    t_ar = 0.0
+    if comm:                                  # the first call builds NCCL's rings / buffers for this size: untimed
+        comm.allreduce_gradients()
+        eng.sync()
+        t0 = time.perf_counter()
+        comm.allreduce_gradients()
+        eng.sync()
+        t_ar = time.perf_counter() - t0
     t0 = time.perf_counter()
     eng.train_step(1e-4, 1e-4)
+    eng.sync()
     t_step = time.perf_counter() - t0
     ms_chunk = float(np.mean(ms))
-    ms_max = par_max(ms_chunk, dev)
+    ms_max = red.max(ms_chunk)
     flop = 3.0 * FLOP_PER_EVAL_NET6 * B          # forward + dgrad + wgrad
     out = {"value": world * B / (ms_max * 1e-3), "unit": "positions/s", "positions_per_chunk": B,
            "ms_per_chunk": ms_max, "allreduce_ms": 1e3 * t_ar, "adam_step_ms": 1e3 * t_step,
@@ -373,39 +535,34 @@ def train_rate(eng, tensors, world, dist, dev, pk, host_recs=None):
            "tflops": flop / (ms_max * 1e-3) / 1e12, "tensor_peak": pk["bf16_sustained"],
            "frac_of_tensor_peak": flop / (ms_max * 1e-3) / 1e12 / pk["bf16_sustained"], "e2e": e2e,
            "what": "train_inner on 4000 augmented positions (forward_training + loss + backward, CUDA events on the engine "
-                   "stream), then NCCL all-reduce of the gradient blob and the Adam step"}
+                   "stream), then net_train_allreduce (NCCL on the engine stream) and the Adam step"}
     eng.train_end()
     return out
-
-
-def par_max(x, dev):
-    from tak_b200 import parallel as par
-    return par.max_over_ranks(x, dev)
 
 
 def run_b200(args):
     import torch
 
     import tak_b200 as tb
-    from tak_b200 import parallel as par
+    from tak_b200 import comm as tc
     from tak_b200 import weights as W
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     dist = None
+    torch.cuda.set_device(local)
     if world > 1:
+        # torch.distributed is plumbing only (rendezvous: ships the NCCL unique ids, host barrier); every exchange of
+        # data -- weights, replay, gradients, the reductions of the timings -- goes through the engine's own NCCL
+        # communicator behind the C ABI (tak_comm_init, net_broadcast_weights, selfplay_gather_replay, ...)
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    else:
-        torch.cuda.set_device(local)
+        dist.init_process_group("gloo")
     dev = torch.device("cuda", local)
 
     # Games never interact, so a GPU's games are split over `replicas` independent engines (own stream, search trees and
-    # network replica) driven by one host thread each: while one replica's conv tower owns the tensor cores, the other's
-    # MCTS / encode / head kernels run beside it on the same SMs.
+    # network replica) driven by one host thread each.
     E = max(1, args.replicas)
     G = args.games if args.games else 5328 * E          # games per GPU; 5328 = 148 SMs x 6 tiles x 6 boards
     Gr = G // E
@@ -413,15 +570,37 @@ def run_b200(args):
     R, n = args.rollouts, 6
     pk = peaks()
     elems = W.blob_size(6)
-    # weights: rank 0 draws them, NCCL broadcasts the fp32 blob over NVLink, every replica folds/packs its own copy
-    blob_dev = par.broadcast_weights(W.random_weights(6, seed=0) if rank == 0 else None, elems, dev)
-    torch.cuda.synchronize()
     engines = []
     for r in range(E):
         eng = tb.Engine(n, Gr, device=local, nodes_per_game=args.nodes_per_game, max_batch=Gr)
         eng.net_create(6)
-        eng.net_load_weights_device(blob_dev.data_ptr(), elems)
         engines.append(eng)
+    comms = [None] * E
+    if world > 1:
+        uids = [tc.unique_id() if rank == 0 else None for _ in range(E)]
+        dist.broadcast_object_list(uids, src=0)
+        comms = [tc.Comm(engines[r], uids[r], rank, world) for r in range(E)]
+    red = Reducer(comms[0])
+
+    # weights: rank 0 draws them; NCCL (net_broadcast_weights, on each replica's stream) hands the fp32 blob to every
+    # rank, which folds BatchNorm and packs the tensor-core operand images of its own replica
+    blob = W.random_weights(6, seed=0) if rank == 0 else None
+    comm_stats = {}
+    if world > 1:
+        for r in range(E):                                  # first use builds NCCL's channels: untimed
+            comms[r].broadcast_weights(blob, root=0)
+        t0 = time.perf_counter()
+        for r in range(E):
+            comms[r].broadcast_weights(blob, root=0)
+        comm_stats["broadcast_ms"] = 1e3 * red.max(time.perf_counter() - t0) / E
+        comm_stats["broadcast_bytes"] = elems * 4
+        comm_stats["broadcast_what"] = ("net_broadcast_weights: H2D on the root, ncclBroadcast of the fp32 blob, D2H, "
+                                        "BatchNorm folding + operand packing on every rank (per replica)")
+    else:
+        for eng in engines:
+            eng.net_load_weights(blob)
+    if blob is None:
+        blob = W.random_weights(6, seed=0)                  # same seed: only used by the CPU-side sub-benchmarks below
 
     def barrier():
         torch.cuda.synchronize()
@@ -430,32 +609,30 @@ def run_b200(args):
         if dist:
             dist.barrier()
 
-    def max_over_ranks(x: float) -> float:
-        return par.max_over_ranks(x, dev)
-
-    def sum_over_ranks(x: float) -> float:
-        return par.sum_over_ranks(x, dev)
-
     # the conv tower timed ALONE on a cool GPU (3 launches, CUDA events) -> compared with the burst peak below
     engines[0].reset(0, Gr, 4)
     prof_alone = engines[0].net_forward_profile(0, Gr, 3)
 
+    # ---------------- movegen Mnodes/s: 6x6 perft(5) from the opening, root moves sharded over ranks ----------------
+    # (before the self-play steps: afterwards the GPU sits at its power-capped clock for a while)
+    movegen = movegen_mnodes(engines[0], world, rank, dev, pk, red)
+
     # ---------------- device-resident self-play: `value` ----------------
     for r, eng in enumerate(engines):
         eng.selfplay_begin(rollouts=R, half_komi=4, instant_win=1, exploit_ply=40, noise_ply=80, noise_alpha=0.2,
-                           noise_ratio=0.3, seed=0x7A4B, game_id_base=par.game_id_base(rank * E + r, Gr))
+                           noise_ratio=0.3, seed=0x7A4B, game_id_base=(rank * E + r) * Gr)
 
     def warm(eng):
         for _ in range(args.warmup):
             eng.selfplay_step(1)
-            eng.selfplay_drain(4 * Gr)
+            eng.selfplay_drain()
 
     in_threads([lambda eng=eng: warm(eng) for eng in engines])
 
-    def timed(eng):
-        """K searched plies of every game of this replica; device time = CUDA events on the replica's stream."""
+    def timed(eng, steps):
+        """`steps` searched plies of every game of this replica; device time = CUDA events on the replica's stream."""
         tot = {"ms": 0.0, "launches": 0, "evals": 0, "plies": 0, "done": 0, "recs": []}
-        left = args.steps
+        left = steps
         while left > 0:
             k = min(left, 4)                       # the replay ring holds 16 records per game between drains
             st = eng.selfplay_step(k)
@@ -465,15 +642,27 @@ def run_b200(args):
             tot["plies"] += st.plies_played
             tot["done"] += st.games_completed
             left -= k
-            if left > 0:
-                tot["recs"] += eng.selfplay_drain(16 * Gr)
+            tot["recs"] += eng.selfplay_drain()
         return tot
 
+    # The trainer publishes a new network while self-play runs (train/src/main.rs:101-105,120): half way through the timed
+    # plies every rank takes a weight refresh over NCCL.  Its time is reported (comm.refresh_ms) and is part of the wall
+    # clock of the region; `value` counts the searched plies over the device time of the self-play steps themselves.
+    half = args.steps // 2 if (world > 1 and args.steps >= 2) else 0
     sampler = ClockSampler(local)
     barrier()
     sampler.start()
     t_wall = time.perf_counter()
-    res = in_threads([lambda eng=eng: timed(eng) for eng in engines])
+    res = in_threads([lambda eng=eng: timed(eng, args.steps - half) for eng in engines])
+    if half:
+        t0 = time.perf_counter()
+        for r in range(E):
+            comms[r].broadcast_weights(blob if rank == 0 else None, root=0)
+        comm_stats["refresh_ms"] = 1e3 * (time.perf_counter() - t0) / E
+        res2 = in_threads([lambda eng=eng: timed(eng, half) for eng in engines])
+        for a, b2 in zip(res, res2):
+            for k in a:
+                a[k] += b2[k]
     barrier()
     wall_ms = 1e3 * (time.perf_counter() - t_wall)
     clocks = sampler.stop()
@@ -483,24 +672,34 @@ def run_b200(args):
     plies = sum(r["plies"] for r in res)
     games_done = sum(r["done"] for r in res)
     recs = sum((r["recs"] for r in res), [])
-    for eng in engines:
-        recs += eng.selfplay_drain(16 * Gr)
-    # replay gather: fixed-size records, all-gathered over NCCL (outside the timed rollouts, as the trainer would)
-    all_recs = par.gather_replay(recs, tb.ReplayRecord, dev)
-    replay_bytes = len(all_recs) * C.sizeof(tb.ReplayRecord)
-    t_max = max_over_ranks(max(dev_ms, 0.0))           # device time (CUDA events on the engine streams), max over ranks
-    total_plies = sum_over_ranks(float(plies))
+    t_max = red.max(max(dev_ms, 0.0))                   # device time (CUDA events on the engine streams), max over ranks
+    total_plies = red.sum(float(plies))
     value = total_plies / (t_max / 1e3)
-    total_launches = int(sum_over_ranks(float(launches)))
+    total_launches = int(red.sum(float(launches)))
+    wall_max = red.max(wall_ms)
+    if "refresh_ms" in comm_stats:
+        comm_stats["refresh_ms"] = red.max(comm_stats["refresh_ms"])
+    # replay gather: fixed-size records of the finished games, all-gathered over NCCL (selfplay_gather_replay)
+    replay_bytes = len(recs) * C.sizeof(tb.ReplayRecord)
+    if world > 1:
+        mine = recs[:4096]                                  # a bounded payload (17 MB per rank) keeps the bench short
+        comms[0].gather_replay(mine)
+        t0 = time.perf_counter()
+        all_recs = comms[0].gather_replay(mine)
+        comm_stats["gather_ms"] = 1e3 * red.max(time.perf_counter() - t0)
+        comm_stats["gather_records"] = len(all_recs)
+        comm_stats["gather_bytes"] = len(all_recs) * C.sizeof(tb.ReplayRecord)
+        comm_stats["gather_what"] = ("selfplay_gather_replay: H2D of this rank's records, ncclAllGather of the counts and of "
+                                     "the padded records, D2H of all ranks' records")
 
     # ---------------- end to end through the host-buffer ABI: `e2e` ----------------
     ids = np.arange(Gr, dtype=np.int32)
     host_states = [eng.download(ids) for eng in engines]  # the positions self-play reached, now in host memory
-    state_bytes = {5: 288, 6: 384}.get(n, 384)
+    state_bytes = STATE_BYTES[n]
     h2d = G * state_bytes + G * 4
     stride = 256
     d2h = G * stride * 6 + G * 4 + G * 2
-    e2e_steps = max(1, min(args.steps, 2))
+    e2e_steps = max(1, min(args.steps, 5))
 
     def e2e_run(i, steps):
         eng = engines[i]
@@ -517,7 +716,7 @@ def run_b200(args):
     t0 = time.perf_counter()
     e2e_out = in_threads([lambda i=i: e2e_run(i, e2e_steps) for i in range(E)])
     barrier()
-    e2e_t = max_over_ranks(time.perf_counter() - t0)
+    e2e_t = red.max(time.perf_counter() - t0)
     e2e_value = world * G * e2e_steps / e2e_t
 
     # ---------------- roofline of the dominant kernel (conv3x3_tc3_kernel = the whole conv tower), measured live -------
@@ -547,9 +746,6 @@ def run_b200(args):
         "forward_ms": prof["ms_forward"], "conv_share_of_forward": prof["ms_conv"] / prof["ms_forward"],
     }
 
-    # ---------------- movegen Mnodes/s: 6x6 perft(5) from the opening, root moves sharded over ranks ----------------
-    movegen = movegen_mnodes(engines[0], world, rank, dev, pk)
-
     # ---------------- replay augmentation (next row N2): Example::to_tensors x 8 symmetries on the device ------------
     mv0, vis0, cnt0 = e2e_out[0]
     aug_recs = []
@@ -561,11 +757,30 @@ def run_b200(args):
         aug_recs.append(r)
     augment, aug_tensors = augment_rate(engines[0], aug_recs, dev, pk)
 
-    # ---------------- small-batch regime of the analysis / playtak / pit callers (rank 0's first replica) ---------------
-    interactive = interactive_rates(local, blob_dev.data_ptr(), elems, host_states[0]) if rank == 0 else None
-
     # ---------------- training step (next row N1): train_inner + all-reduce + Adam on those examples -----------------
-    train = train_rate(engines[0], aug_tensors, world, dist, dev, pk, aug_recs) if aug_tensors is not None else None
+    train = train_rate(engines[0], aug_tensors, world, comms[0], red, pk, aug_recs) if aug_tensors is not None else None
+    del aug_tensors
+    some_states = host_states[0][:256]
+
+    # ---------------- the other north-star configs; the big engines' node pools are released first ----------------
+    for r in range(1, E):
+        if comms[r]:
+            comms[r].close()
+        engines[r].close()
+    torch.cuda.empty_cache()
+    movegen["perft5x5_d4"] = perft5_rate(local) if rank == 0 else None
+    stress8 = stress8_rates(local, world, rank, red, pk)
+    movegen["playouts8x8"] = stress8["playouts"]
+    if comms[0]:
+        comm_stats["bytes_moved_rank0_replica0"] = comms[0].bytes_moved()
+    # engine 0 (and its communicator, which the reducer uses) stays alive until the sharded sub-benchmarks are done
+    selfplay5 = selfplay5_rate(local, world, rank, red, max(1, min(args.steps, 3)), 2, W.random_weights(5, seed=0))
+
+    # ---------------- small-batch regime of the analysis / playtak / pit callers (rank 0) ---------------
+    if comms[0]:
+        comms[0].close()
+    engines[0].close()
+    interactive = interactive_rates(local, blob, some_states) if rank == 0 else None
 
     if rank == 0 and world == 1:
         # the CPU path beside it: the oracle's literal restatement of perft.rs:3-18 (-O3 -march=native), single-threaded as
@@ -598,25 +813,28 @@ def run_b200(args):
                              "game) and evaluates other leaves; the conv tower keeps a tile group's activations in L2 "
                              "by design and writes 36 KB of logits per leaf to HBM",
                        "parallelism": f"games sharded over {world} rank(s) x {E} engine replica(s), no collective in "
-                                      "the rollout loop"},
+                                      "the rollout loop; weights / replay / gradients over NCCL through the C ABI"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps,
                     "what": "host game states -> tak_games_upload -> mcts_rollouts(800) -> mcts_children_batch + "
                             "mcts_pick_move -> host"},
             "gpu_launches": total_launches,
             "roofline": roofline,
             "movegen": movegen,
+            "selfplay5x5": selfplay5,
+            "mcts8x8_dummy": stress8["mcts_dummy"],
+            "comm": comm_stats or None,
             "augment": augment,
             "train": train,
             "interactive": interactive,
             "cpu_baseline": {"value": cpu["value"], "unit": UNIT, "cores": cpu["cores"], "kind": "port",
                              "sample": cpu["sample"]} if cpu else None,
             "clocks": clocks,
-            "extra": {"wall_ms_per_step": wall_ms / args.steps, "evals_per_step": evals / max(1, args.steps),
-                      "games_completed": games_done, "replay_records_gathered_bytes": replay_bytes,
+            "extra": {"wall_ms_per_step": wall_max / args.steps, "wall_moves_per_s": total_plies / (wall_max / 1e3),
+                      "evals_per_step": evals / max(1, args.steps), "launches_per_ply_per_replica": launches / max(1, args.steps) / E,
+                      "games_completed": games_done, "replay_records_bytes": replay_bytes,
                       "net_evals_per_s": evals / (dev_ms / 1e3) if dev_ms else None},
         }
-    for eng in engines:
-        eng.close()
     if dist:
         dist.barrier()
         dist.destroy_process_group()

@@ -255,6 +255,7 @@ __global__ void __launch_bounds__(GAME_THREADS) k_sp_play(SpView sp, MctsView mv
     WarpGame<N> g;
     g.load(sp.states + size_t(w) * S);
     g.template play<false>(sp.moves[w]);
+    if (l == 0) atomicAdd(mv.counters + 2, 1ull);   // searched plies actually played (tak_selfplay_stats_t::plies_played)
     uint8_t r = g.result();
     if (r == RES_ONGOING && sp.max_plies > 0 && g.ply >= sp.max_plies) r = RES_DRAW;  // safety cap (not in the reference)
     if (r != RES_ONGOING) {
@@ -396,8 +397,8 @@ int32_t selfplay_step(tak_engine_t* e, int32_t moves, tak_selfplay_stats_t* out_
     TB_CUDA(cudaStreamSynchronize(e->stream));
     TB_CHECK(s.h_counts[0] + 2 * G * moves <= s.rec_cap, TAK_ERR_CAPACITY,
              "replay buffer would overflow: call selfplay_drain (holds %d of %d records)", s.h_counts[0], s.rec_cap);
-    unsigned long long c0[2] = {0, 0}, c1[2] = {0, 0};
-    TB_CUDA(cudaMemcpy(c0, e->mcts->counters.p, 16, cudaMemcpyDeviceToHost));
+    unsigned long long c0[3] = {0, 0, 0}, c1[3] = {0, 0, 0};
+    TB_CUDA(cudaMemcpy(c0, e->mcts->counters.p, 24, cudaMemcpyDeviceToHost));
     const int ev0 = s.h_counts[1], rec0 = s.h_counts[0];
     const uint64_t launches0 = e->launches;
     cudaEvent_t t0, t1;
@@ -417,10 +418,10 @@ int32_t selfplay_step(tak_engine_t* e, int32_t moves, tak_selfplay_stats_t* out_
     if (r == TAK_OK && out_stats) {
         float ms = 0;
         cudaEventElapsedTime(&ms, t0, t1);
-        cudaMemcpy(c1, e->mcts->counters.p, 16, cudaMemcpyDeviceToHost);
+        cudaMemcpy(c1, e->mcts->counters.p, 24, cudaMemcpyDeviceToHost);
         cudaMemcpy(s.h_counts, s.counts.p, 16, cudaMemcpyDeviceToHost);
         std::memset(out_stats, 0, sizeof(*out_stats));
-        out_stats->plies_played = uint64_t(G) * moves;
+        out_stats->plies_played = c1[2] - c0[2];          // counted on the device by k_sp_play
         out_stats->games_completed = uint64_t(s.h_counts[1] - ev0);
         out_stats->rollouts = c1[0] - c0[0];
         out_stats->evals = c1[1] - c0[1];

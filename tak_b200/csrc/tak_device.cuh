@@ -53,16 +53,22 @@ struct StateScalars {  // 16 bytes
 };
 static_assert(sizeof(StateScalars) == 16, "scalars must be 16 bytes");
 
-// number of compositions of p into at most f parts / into exactly f+1 parts whose last part is 1
-static __constant__ uint8_t c_comp_le[9][8] = {
-    {0, 0, 0, 0, 0, 0, 0, 0},      {0, 1, 1, 1, 1, 1, 1, 1},       {0, 1, 2, 2, 2, 2, 2, 2},
-    {0, 1, 3, 4, 4, 4, 4, 4},      {0, 1, 4, 7, 8, 8, 8, 8},       {0, 1, 5, 11, 15, 16, 16, 16},
-    {0, 1, 6, 16, 26, 31, 32, 32}, {0, 1, 7, 22, 42, 57, 63, 64},  {0, 1, 8, 29, 64, 99, 120, 127}};
-static __constant__ uint8_t c_comp_flat[9][8] = {
-    // [p][f] = C(p-2, f-1) for f>=1 (p-1 >= f), and [p][0] = (p == 1)
-    {0, 0, 0, 0, 0, 0, 0, 0}, {1, 0, 0, 0, 0, 0, 0, 0},  {0, 1, 0, 0, 0, 0, 0, 0},
-    {0, 1, 1, 0, 0, 0, 0, 0}, {0, 1, 2, 1, 0, 0, 0, 0},  {0, 1, 3, 3, 1, 0, 0, 0},
-    {0, 1, 4, 6, 4, 1, 0, 0}, {0, 1, 5, 10, 10, 5, 1, 0}, {0, 1, 6, 15, 20, 15, 6, 1}};
+// Move counts of one stack in one direction, summed over the pickup sizes p = 1..maxp:
+//   d_sum_le[maxp][f]   = sum_p #(compositions of p into at most f parts)        (f = free squares along the ray)
+//   d_sum_flat[maxp][f] = sum_p #(compositions of p into exactly f+1 parts whose last part is 1)   (a capstone flattening
+//                         the wall that ends the ray; [p][0] counts p == 1)
+// The lanes of a warp index these with different (maxp, f), so they live in global memory and are read through L1
+// (__ldg): a __constant__ table serialises divergent indices.
+static __device__ uint16_t d_sum_le[9][8] = {
+    {0, 0, 0, 0, 0, 0, 0, 0},       {0, 1, 1, 1, 1, 1, 1, 1},        {0, 2, 3, 3, 3, 3, 3, 3},
+    {0, 3, 6, 7, 7, 7, 7, 7},       {0, 4, 10, 14, 15, 15, 15, 15},  {0, 5, 15, 25, 30, 31, 31, 31},
+    {0, 6, 21, 41, 56, 62, 63, 63}, {0, 7, 28, 63, 98, 119, 126, 127}, {0, 8, 36, 92, 162, 218, 246, 254}};
+static __device__ uint16_t d_sum_flat[9][8] = {
+    {0, 0, 0, 0, 0, 0, 0, 0}, {1, 0, 0, 0, 0, 0, 0, 0},  {1, 1, 0, 0, 0, 0, 0, 0},
+    {1, 2, 1, 0, 0, 0, 0, 0}, {1, 3, 3, 1, 0, 0, 0, 0},  {1, 4, 6, 4, 1, 0, 0, 0},
+    {1, 5, 10, 10, 5, 1, 0, 0}, {1, 6, 15, 20, 15, 6, 1, 0}, {1, 7, 21, 35, 35, 21, 7, 1}};
+__device__ __forceinline__ int sum_le(int maxp, int f) { return __ldg(&d_sum_le[maxp][f]); }
+__device__ __forceinline__ int sum_flat(int maxp, int f) { return __ldg(&d_sum_flat[maxp][f]); }
 
 // GameResult byte (include/taknative.h): 0 ongoing, 1 white, 2 black, 3 draw, |0x10 road / reversible
 enum : uint8_t { RES_ONGOING = 0, RES_WHITE = 1, RES_BLACK = 2, RES_DRAW = 3, RES_FLAG = 0x10 };
@@ -220,7 +226,7 @@ struct WarpGame {
             bool wall_after;
             free_run(o, d, free, wall_after);
             const bool flatten = wall_after && is_cap;
-            for (int p = 1; p <= maxp; ++p) total += c_comp_le[p][free] + (flatten ? c_comp_flat[p][free] : 0);
+            total += sum_le(maxp, free) + (flatten ? sum_flat(maxp, free) : 0);
         }
         return total;
     }
@@ -451,16 +457,6 @@ struct WarpGame {
 // perft's counting levels need only Game::result (game.rs:220-267) and possible_moves().len() (move_gen.rs:7-102), both
 // functions of {heights, walls, caps, occupied, black tops, scalars} = the last 96 bytes of a 6x6 record.  A warp per
 // position spends its 32 lanes on identical bitboard arithmetic; a thread per position does the same work once.
-// sum over p = 1..maxp of c_comp_le[p][f] / c_comp_flat[p][f]  (move counts of one stack in one direction)
-static __constant__ uint16_t c_sum_le[9][8] = {
-    {0, 0, 0, 0, 0, 0, 0, 0},       {0, 1, 1, 1, 1, 1, 1, 1},        {0, 2, 3, 3, 3, 3, 3, 3},
-    {0, 3, 6, 7, 7, 7, 7, 7},       {0, 4, 10, 14, 15, 15, 15, 15},  {0, 5, 15, 25, 30, 31, 31, 31},
-    {0, 6, 21, 41, 56, 62, 63, 63}, {0, 7, 28, 63, 98, 119, 126, 127}, {0, 8, 36, 92, 162, 218, 246, 254}};
-static __constant__ uint16_t c_sum_flat[9][8] = {
-    {0, 0, 0, 0, 0, 0, 0, 0}, {1, 0, 0, 0, 0, 0, 0, 0},  {1, 1, 0, 0, 0, 0, 0, 0},
-    {1, 2, 1, 0, 0, 0, 0, 0}, {1, 3, 3, 1, 0, 0, 0, 0},  {1, 4, 6, 4, 1, 0, 0, 0},
-    {1, 5, 10, 10, 5, 1, 0, 0}, {1, 6, 15, 20, 15, 6, 1, 0}, {1, 7, 21, 35, 35, 21, 7, 1}};
-
 template <int N>
 struct ThreadPos {
     using L = StateLayout<N>;
@@ -534,7 +530,7 @@ struct ThreadPos {
                     }
                     ++free;
                 }
-                total += c_sum_le[maxp][free] + ((wall_after && is_cap) ? c_sum_flat[maxp][free] : 0);
+                total += sum_le(maxp, free) + ((wall_after && is_cap) ? sum_flat(maxp, free) : 0);
             }
         }
         return total;

@@ -1,12 +1,15 @@
-"""Multi-GPU plumbing of the self-play path (one process per GPU, torch.distributed).
+"""Multi-GPU plumbing of the self-play path (one process per GPU).
 
 Games never interact, so each rank owns a contiguous block of global game ids, its own search trees and a network
 replica; the rollout loop has no collective.  Exactly two exchanges exist:
-  * `broadcast_weights`  rank 0's fp32 weight blob -> every rank (NCCL broadcast over NVLink; gloo in CPU tests)
-  * `gather_replay`      fixed-size replay records of all ranks -> every rank (all_gather of padded byte tensors)
+  * `broadcast_weights`  rank 0's fp32 weight blob -> every rank
+  * `gather_replay`      fixed-size replay records of all ranks -> every rank
 The training step (next row N1) adds the one collective data-parallel training needs:
   * `allreduce_gradients` sum of every rank's fp32 gradient blob, in place, before the Adam step -- every rank then takes
                           the identical step, which is the reference's single-process step over world x as many chunks
+On GPUs these run INSIDE the C ABI (tak_b200.comm.Comm over csrc/comm.cu: NCCL on the engine's stream, ordered with the
+kernels around it); this module is the thin caller.  The torch.distributed versions below are the host-side fallback
+used by the CPU tests (gloo, world_size 2) and by callers that have a process group but no engine communicator.
 The reference has no distributed code (single process, single GPU: alpha-tak/src/lib.rs:21-23).
 """
 from __future__ import annotations
@@ -62,10 +65,27 @@ def gather_replay(records: Sequence, record_type, device: torch.device) -> List:
 def allreduce_gradients(grad: torch.Tensor) -> torch.Tensor:
     """In-place sum over ranks of the gradient blob (`Engine.train_grad_tensor()`: a zero-copy view of the engine's
     accumulator).  Gradients of chunks ADD in the reference (`total_loss.backward()` per chunk, one `opt.step()` per
-    CHUNKS_IN_STEP chunks, network.rs:84-95), so the sum over ranks is the single-process gradient of all their chunks."""
+    CHUNKS_IN_STEP chunks, network.rs:84-95), so the sum over ranks is the single-process gradient of all their chunks.
+
+    torch.distributed enqueues NCCL on ITS stream and returns; the engine's Adam kernel runs on the engine's own
+    non-blocking stream, which nothing orders after it.  So this fallback waits for the reduction to finish before it
+    returns.  (`Comm.allreduce_gradients` needs no wait: it issues NCCL on the engine's stream.)"""
     if dist.is_initialized() and dist.get_world_size() > 1:
+        if grad.is_cuda:
+            torch.cuda.synchronize(grad.device)      # the chunks' kernels (engine stream) have written `grad`
         dist.all_reduce(grad, op=dist.ReduceOp.SUM)
+        if grad.is_cuda:
+            torch.cuda.synchronize(grad.device)      # ... and the sum is complete before net_train_step is enqueued
     return grad
+
+
+def engine_allreduce(eng, comm=None) -> None:
+    """The all-reduce `train_loop.train_network` calls before each step: through the engine's communicator when there is
+    one (NCCL on the engine stream), else the torch.distributed fallback above."""
+    if comm is not None:
+        comm.allreduce_gradients()
+    else:
+        allreduce_gradients(eng.train_grad_tensor())
 
 
 def max_over_ranks(x: float, device: torch.device) -> float:

@@ -36,9 +36,10 @@ def train_network(eng: Engine, examples: Sequence[ReplayRecord], rng: np.random.
     (weights incl. BatchNorm running statistics).
 
     Data-parallel (world > 1): every rank holds the same examples and the same `rng` state, so all ranks draw the same
-    shuffle; chunk i is trained by rank i % world, and before every step `allreduce(grad_tensor)`
-    (parallel.allreduce_gradients) sums the ranks' accumulators -- the step is then the reference's single-process step
-    over the same `chunks_in_step` chunks.  (BatchNorm running statistics follow each rank's own chunks.)"""
+    shuffle; chunk i is trained by rank i % world, and before every step `allreduce(eng)` (parallel.engine_allreduce:
+    net_train_allreduce on the engine's stream, or the synchronised torch.distributed fallback) sums the ranks'
+    accumulators -- the step is then the reference's single-process step over the same `chunks_in_step` chunks.
+    (BatchNorm running statistics follow each rank's own chunks.)"""
     log(f"starting training with {len(examples)} examples")
     eng.train_begin(8 * chunk_size)                       # Adam { wd, ..Default }.build(vs, lr): fresh moments
     order = rng.permutation(len(examples))                # refs.shuffle(&mut thread_rng())
@@ -52,7 +53,7 @@ def train_network(eng: Engine, examples: Sequence[ReplayRecord], rng: np.random.
             log(f"p={lp:.4f}\t z={lz:.4f}")
         if (i + 1) % chunks_in_step == 0:
             if allreduce is not None:
-                allreduce(eng.train_grad_tensor())
+                allreduce(eng)                # sums the ranks' gradient accumulators; ordered before the step
             log("making step!")
             eng.train_step(lr, weight_decay)
     blob = eng.train_get(0)
@@ -122,7 +123,7 @@ def training_iteration(current: Engine, candidate: Engine, blob: np.ndarray, exa
 def distributed_iteration(current: Engine, candidate: Engine, blob: np.ndarray, examples: List[ReplayRecord], seed: int,
                           device, pit_games: int = 128, pit_rollouts: int = 50, pit_batch: int = 16,
                           min_new_examples: int = 1000, train_kw: Optional[dict] = None,
-                          selfplay_kw: Optional[dict] = None, log: Callable = print):
+                          selfplay_kw: Optional[dict] = None, log: Callable = print, comm=None):
     """One turn of `training_loop` on N GPUs (one process per GPU, torch.distributed already initialised):
       * training is data-parallel (chunks dealt round-robin, NCCL all-reduce of the gradient blob before each step),
       * the pit games are split over the ranks and the win / loss / draw counts summed,
@@ -138,8 +139,10 @@ def distributed_iteration(current: Engine, candidate: Engine, blob: np.ndarray, 
     if examples:
         candidate.net_load_weights(blob)
         rng = np.random.default_rng(seed)                 # same shuffle on every rank
-        new_blob = train_network(candidate, examples, rng, log=log, allreduce=par.allreduce_gradients, rank=rank,
-                                 world=world, **(train_kw or {}))
+        # `comm`: a tak_b200.comm.Comm on `candidate` (NCCL on its stream); without one, torch.distributed + a sync
+        new_blob = train_network(candidate, examples, rng, log=log,
+                                 allreduce=lambda e: par.engine_allreduce(e, comm), rank=rank, world=world,
+                                 **(train_kw or {}))
         t = torch.from_numpy(new_blob).to(device)         # running statistics: mean over ranks; weights already agree
         dist.all_reduce(t)
         new_blob = (t / world).cpu().numpy()

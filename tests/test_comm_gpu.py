@@ -49,6 +49,15 @@ def _worker(rank, world, uid_pipe, out_q):
         eng.train_step(1e-4, 1e-4)
         w_after = eng.train_get(0)
         eng.train_end()
+        # 4. the same through train_loop.train_network (Network::train, data-parallel): chunk i goes to rank i % world and
+        #    the hook sums the accumulators on the engine stream right before each Adam step -- no host synchronisation
+        #    between the all-reduce and the step (the race the torch.distributed route had)
+        import numpy as np
+        from tak_b200 import train_loop as TL
+        eng.net_load_weights(W.random_weights(6, seed=31))
+        tn_blob = TL.train_network(eng, allrec[:32], np.random.default_rng(3), chunk_size=8, chunks_in_step=2, lr=1e-3,
+                                   allreduce=lambda e: cm.allreduce_gradients(), log=lambda *_: None, rank=rank,
+                                   world=world)
         total = cm.sum_u64([len(mine), 7])
         mx = cm.max_f64([float(rank), 1.5])
         moved = cm.bytes_moved()
@@ -56,7 +65,7 @@ def _worker(rank, world, uid_pipe, out_q):
         eng.close()
         out_q.put((rank, {"pol": pol[0][:64].copy(), "val": float(val[0]), "n_mine": len(mine),
                           "ids": [(r.game_id, r.game_serial, int(r.state.ply)) for r in allrec],
-                          "g_local": g_local, "g_sum": g_sum, "w_after": w_after, "total": total, "mx": mx,
+                          "g_local": g_local, "g_sum": g_sum, "w_after": w_after, "tn_blob": tn_blob, "total": total, "mx": mx,
                           "moved": moved}))
     except BaseException as ex:  # noqa: BLE001
         import traceback
@@ -92,6 +101,12 @@ def test_nccl_entry_points_two_ranks_no_torch_distributed():
     want = a["g_local"].astype(np.float64) + b["g_local"].astype(np.float64)
     assert np.abs(a["g_sum"] - want).max() <= 1e-6 * max(1.0, np.abs(want).max())
     assert np.abs(a["g_local"]).max() > 0 and not np.array_equal(a["g_local"], b["g_local"])
+    # train_network on two ranks: identical trainable weights on both (BatchNorm running statistics follow each rank's own
+    # chunks), and they moved away from the start
+    from tak_b200 import weights as W
+    mask = np.concatenate([np.full(int(np.prod(s)), "running_" not in n) for n, s in W.spec(6)])
+    assert np.array_equal(a["tn_blob"][mask], b["tn_blob"][mask])
+    assert not np.array_equal(a["tn_blob"][mask], W.random_weights(6, seed=31)[mask])
     assert a["total"] == b["total"] == [a["n_mine"] + b["n_mine"], 14]
     assert a["mx"] == b["mx"] == [1.0, 1.5]
     assert a["moved"] > 20_000_000            # weight blob + gradient blob at least

@@ -37,7 +37,7 @@ class FakeEngine:
 def run(rank, world, n_examples=23, chunk=4, cis=2):
     eng, reduced = FakeEngine(), []
     TL.train_network(eng, list(range(n_examples)), np.random.default_rng(7), chunk_size=chunk, chunks_in_step=cis,
-                     allreduce=reduced.append, log=lambda *_: None, rank=rank, world=world)
+                     allreduce=lambda e: reduced.append(e.train_grad_tensor()), log=lambda *_: None, rank=rank, world=world)
     return eng.log, reduced
 
 
