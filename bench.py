@@ -119,6 +119,7 @@ def cpu_selfplay_sample(rollouts_sample: int, full_rollouts: int, workers: int =
     from oracle.net_ref import RefNet
     from tak_b200 import weights as W
 
+    oracle.use_native_build()     # -O3 -march=native on this box's CPU, as .cargo/config.toml:2 builds the reference
     n = 6
     # torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core it can
     torch.set_num_threads(max(1, os.cpu_count() or 1))
@@ -679,18 +680,7 @@ def run_b200(args):
     wall_max = red.max(wall_ms)
     if "refresh_ms" in comm_stats:
         comm_stats["refresh_ms"] = red.max(comm_stats["refresh_ms"])
-    # replay gather: fixed-size records of the finished games, all-gathered over NCCL (selfplay_gather_replay)
     replay_bytes = len(recs) * C.sizeof(tb.ReplayRecord)
-    if world > 1:
-        mine = recs[:4096]                                  # a bounded payload (17 MB per rank) keeps the bench short
-        comms[0].gather_replay(mine)
-        t0 = time.perf_counter()
-        all_recs = comms[0].gather_replay(mine)
-        comm_stats["gather_ms"] = 1e3 * red.max(time.perf_counter() - t0)
-        comm_stats["gather_records"] = len(all_recs)
-        comm_stats["gather_bytes"] = len(all_recs) * C.sizeof(tb.ReplayRecord)
-        comm_stats["gather_what"] = ("selfplay_gather_replay: H2D of this rank's records, ncclAllGather of the counts and of "
-                                     "the padded records, D2H of all ranks' records")
 
     # ---------------- end to end through the host-buffer ABI: `e2e` ----------------
     ids = np.arange(Gr, dtype=np.int32)
@@ -756,6 +746,17 @@ def run_b200(args):
         C.memmove(r.visits, vis0[i].ctypes.data, 4 * r.n_children)
         aug_recs.append(r)
     augment, aug_tensors = augment_rate(engines[0], aug_recs, dev, pk)
+    # replay gather over NCCL (selfplay_gather_replay): every rank contributes the records above (fixed-size, 4.3 KB each);
+    # in a training run these are the completed games' records selfplay_drain hands out
+    if world > 1:
+        comms[0].gather_replay(aug_recs)                    # first use: untimed
+        t0 = time.perf_counter()
+        all_recs = comms[0].gather_replay(aug_recs)
+        comm_stats["gather_ms"] = 1e3 * red.max(time.perf_counter() - t0)
+        comm_stats["gather_records"] = len(all_recs)
+        comm_stats["gather_bytes"] = len(all_recs) * C.sizeof(tb.ReplayRecord)
+        comm_stats["gather_what"] = ("selfplay_gather_replay: H2D of this rank's records, ncclAllGather of the counts and of "
+                                     "the padded records, D2H of all ranks' records (host-timed, incl. the ctypes copies)")
 
     # ---------------- training step (next row N1): train_inner + all-reduce + Adam on those examples -----------------
     train = train_rate(engines[0], aug_tensors, world, comms[0], red, pk, aug_recs) if aug_tensors is not None else None
@@ -786,6 +787,7 @@ def run_b200(args):
         # the CPU path beside it: the oracle's literal restatement of perft.rs:3-18 (-O3 -march=native), single-threaded as
         # the reference's test is, and one subtree per host thread
         import oracle
+        native = oracle.use_native_build()
         og = oracle.Game(6, 0)
         t0 = time.perf_counter()
         n4 = og.perft(4)
@@ -795,6 +797,7 @@ def run_b200(args):
         t2 = time.perf_counter()
         movegen["cpu_baseline"] = {"kind": "port", "single_thread_mnodes_s": n4 / (t1 - t0) / 1e6,
                                    "all_threads_mnodes_s": n5 / (t2 - t1) / 1e6, "cores": threads,
+                                   "march_native": bool(native),
                                    "sample": "6x6 perft(4) on one thread, perft(5) over all host threads; counts "
                                              f"{n4} / {n5}", "exact": n4 == 13_586_048 and n5 == PERFT6_D5}
     line = None

@@ -50,13 +50,28 @@ def build(force: bool = False) -> str:
 
 
 _lib = None
+_native = False
+
+
+def use_native_build() -> bool:
+    """bench.py's CPU-baseline legs: compile liboracle_native.so with -march=native on THIS machine and use it (must be
+    called before the first oracle call).  Falls back to the portable build if the compiler is missing."""
+    global _native
+    if _lib is not None:
+        return _native
+    try:
+        subprocess.check_call(["make", "-C", _HERE, "-s", "native"])
+        _native = os.path.exists(os.path.join(_HERE, "liboracle_native.so"))
+    except Exception:
+        _native = False
+    return _native
 
 
 def lib():
     global _lib
     if _lib is None:
         build()
-        L = C.CDLL(_LIB_PATH)
+        L = C.CDLL(os.path.join(_HERE, "liboracle_native.so") if _native else _LIB_PATH)
         vp, i32, u16, u64, f32 = C.c_void_p, C.c_int, C.c_uint16, C.c_uint64, C.c_float
         sig = {
             "orc_game_new": (vp, [i32, i32]),

@@ -173,16 +173,26 @@ int mcts_eval_and_backup(tak_engine* e) {
 static int launch_step(tak_engine* e, const int* d_ids, int n, const uint8_t* d_enable, const FastEval& fe,
                        const PriorSource& ps, int do_backup, int do_rollout, int reps) {
     MctsState& m = *e->mcts;
-    // 2 warps per block: at 128 registers per thread a block takes 8 192 registers, which fits beside a resident
-    // conv-tower CTA of the other engine replica on the same SM (it leaves 11 776 free), so one replica's search hides
-    // under the other's tower.  TAK_STEP_WARPS overrides it for measurements.
-    static const int warps = [] {
-        const char* s = std::getenv("TAK_STEP_WARPS");
-        const int v = s ? std::atoi(s) : 2;
-        return v >= 1 && v <= 4 ? v : 2;
+    // With a network, the search of one engine replica should run BESIDE the other replica's conv tower: a tower CTA
+    // (352 threads x 168 registers) leaves 6 400 registers free on its SM, so the step kernel is built with a 64-register
+    // cap (32 bytes of spills) and launched in 64-thread blocks = 4 096 registers.  Measured on one box, 2 replicas x
+    // 5 328 games: 3 707 moves/s against 3 623 with the uncapped 132-register build, whose blocks do not fit
+    // (TAK_STEP_REGS=128 selects it; the DummyNet loop has no tower to hide under and always uses it).
+    static const int regs = [] {
+        const char* s = std::getenv("TAK_STEP_REGS");
+        return s ? std::atoi(s) : 64;
     }();
-    TB_DISPATCH_N(e->n, (k_mcts_step<N_><<<(n + warps - 1) / warps, 32 * warps, 0, e->stream>>>(
-                            m.view(), e->states.as<uint8_t>(), d_ids, n, d_enable, fe, ps, do_backup, do_rollout, reps)));
+    const bool capped = regs != 128 && ps.arch != 0 && (e->n == 5 || e->n == 6);
+    if (capped && e->n == 6) {
+        k_mcts_step<6, 64, 16><<<(n + 1) / 2, 64, 0, e->stream>>>(m.view(), e->states.as<uint8_t>(), d_ids, n, d_enable, fe,
+                                                                  ps, do_backup, do_rollout, reps);
+    } else if (capped && e->n == 5) {
+        k_mcts_step<5, 64, 16><<<(n + 1) / 2, 64, 0, e->stream>>>(m.view(), e->states.as<uint8_t>(), d_ids, n, d_enable, fe,
+                                                                  ps, do_backup, do_rollout, reps);
+    } else {
+        TB_DISPATCH_N(e->n, (k_mcts_step<N_><<<(n + 3) / 4, 128, 0, e->stream>>>(
+                                m.view(), e->states.as<uint8_t>(), d_ids, n, d_enable, fe, ps, do_backup, do_rollout, reps)));
+    }
     e->launches++;
     TB_CUDA(cudaGetLastError());
     return TAK_OK;

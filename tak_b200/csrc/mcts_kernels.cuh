@@ -358,8 +358,11 @@ __global__ void __launch_bounds__(GAME_THREADS)
 // (its network outputs are in place), then run the next virtual rollout and queue / encode its leaf.  Both halves touch
 // only this game's tree, so they need no grid-wide ordering and live in one launch: the loop is {k_mcts_step; tower} x R.
 // With the DummyNet (arch 0: prior 1, eval 0 -- nothing to evaluate) the whole loop of `reps` rollouts is ONE launch.
-template <int N>
-__global__ void __launch_bounds__(128)
+// MINB = minimum resident blocks per SM the compiler must allow for (register cap = 65536 / (MAXT * MINB)): the default
+// build lets the kernel have its 128 registers; the capped builds (TAK_STEP_REGS) exist to measure whether a block that
+// fits beside a resident conv-tower CTA buys overlap.
+template <int N, int MAXT = 128, int MINB = 1>
+__global__ void __launch_bounds__(MAXT, MINB)
     k_mcts_step(MctsView v, const uint8_t* states, const int* ids, int n, const uint8_t* enable, FastEval fe,
                 PriorSource ps, int do_backup, int do_rollout, int reps) {
     if (blockIdx.x == 0 && threadIdx.x == 0 && fe.eval_count_reset) *fe.eval_count_reset = 0;

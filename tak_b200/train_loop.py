@@ -26,6 +26,10 @@ LEARNING_RATE = 1e-4        # network.rs:14
 WEIGHT_DECAY = 1e-4         # network.rs:15
 MAX_EXAMPLES = 400_000      # train/src/main.rs:25
 WIN_RATE_THRESHOLD = 0.55   # train/src/main.rs:27
+# self_play_parallel's constants (train/src/self_play.rs:12-18): what `training_iteration` / `collect_self_play` use
+# unless the caller overrides them.  (Engine.selfplay_begin's own defaults -- noise off -- are the PARITY configuration.)
+SELF_PLAY_DEFAULTS = dict(rollouts=10_000, noise_ply=80, noise_alpha=0.2, noise_ratio=0.3, exploit_ply=40, instant_win=1,
+                          half_komi=4)
 
 
 def train_network(eng: Engine, examples: Sequence[ReplayRecord], rng: np.random.Generator,
@@ -65,11 +69,11 @@ def train_network(eng: Engine, examples: Sequence[ReplayRecord], rng: np.random.
 def collect_self_play(eng: Engine, min_examples: int, max_steps: int = 10_000, **selfplay_cfg) -> List[ReplayRecord]:
     """`self_play_parallel(&network)` until at least `min_examples` completed-game records exist (the reference plays a
     fixed number of games; the device loop keeps every slot busy and hands back the records of finished games)."""
-    eng.selfplay_begin(**selfplay_cfg)
+    eng.selfplay_begin(**{**SELF_PLAY_DEFAULTS, **selfplay_cfg})
     out: List[ReplayRecord] = []
     for _ in range(max_steps):
         eng.selfplay_step(1)
-        out += eng.selfplay_drain(16 * eng.max_games)
+        out += eng.selfplay_drain()
         if len(out) >= min_examples:
             break
     return out
