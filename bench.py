@@ -375,6 +375,42 @@ def selfplay5_rate(local, world, rank, red, steps, warmup, blob5):
                         "instant-win on (configs[1])"}
 
 
+def late_game_rate(local, blob, steps):
+    """The headline steps start from the forced opening, so they cover plies 2..30.  This leg runs the same self-play
+    configuration from MID-GAME positions (every game advanced by 10..70 uniform-random plies with tak_playouts first):
+    more pieces on the board, taller stacks, wider move lists, terminal rollouts that need no evaluation."""
+    import tak_b200 as tb
+    G = 5328
+    eng = tb.Engine(6, G, device=local, nodes_per_game=1 << 18, max_batch=G)
+    eng.net_create(6)
+    eng.net_load_weights(blob)
+    eng.reset(0, G, 4)
+    plies, res, _ = eng.playouts(0, G, 0x1A7E, 10, 61)
+    for i in np.nonzero(res)[0]:
+        eng.reset(int(i), 1, 4)                                            # a finished playout restarts from the opening
+    start = eng.download(np.arange(256, dtype=np.int32))
+    eng.selfplay_begin(rollouts=800, half_komi=4, instant_win=1, exploit_ply=40, noise_ply=80, noise_alpha=0.2,
+                       noise_ratio=0.3, seed=0x7A4C, keep_positions=True)
+    eng.selfplay_step(1)
+    eng.selfplay_drain()
+    ms, plies_played, evals, rollouts, done_games = 0.0, 0, 0, 0, 0
+    for _ in range(steps):
+        st = eng.selfplay_step(1)
+        ms += st.device_ms
+        plies_played += st.plies_played
+        evals += st.evals
+        rollouts += st.rollouts
+        done_games += st.games_completed
+        eng.selfplay_drain()
+    eng.close()
+    return {"value": plies_played / (ms * 1e-3), "unit": "moves/s", "games": G, "replicas": 1, "steps": steps,
+            "mean_start_ply": float(np.mean([s.ply for s in start])), "max_start_ply": int(max(s.ply for s in start)),
+            "evals_per_rollout": evals / max(1, rollouts), "games_completed": int(done_games),
+            "workload": "6x6 self-play as in the headline, but every game starts 10..70 random plies into the game "
+                        "(one engine replica of 5 328 games; throughput does not depend on the number of replicas, so it "
+                        "compares directly with the headline value)"}
+
+
 def pk_sustained():
     return peaks()["bf16_sustained"]
 
@@ -782,6 +818,7 @@ def run_b200(args):
         comms[0].close()
     engines[0].close()
     interactive = interactive_rates(local, blob, some_states) if rank == 0 else None
+    late = late_game_rate(local, blob, max(1, min(args.steps, 3))) if rank == 0 else None
 
     if rank == 0 and world == 1:
         # the CPU path beside it: the oracle's literal restatement of perft.rs:3-18 (-O3 -march=native), single-threaded as
@@ -830,6 +867,7 @@ def run_b200(args):
             "augment": augment,
             "train": train,
             "interactive": interactive,
+            "late_game": late,
             "cpu_baseline": {"value": cpu["value"], "unit": UNIT, "cores": cpu["cores"], "kind": "port",
                              "sample": cpu["sample"]} if cpu else None,
             "clocks": clocks,

@@ -277,7 +277,7 @@ typedef struct tak_selfplay_config {
     uint64_t seed;           /* counter-based RNG key (openings, sampling, noise) */
     int32_t max_plies;       /* safety cap per game (0 => none) */
     int32_t game_id_base;    /* global id of local game 0 (rank sharding: openings/seeds use global ids) */
-    int32_t reserved[4];
+    int32_t reserved[4];     /* [0] != 0: keep the positions the games hold now (mid-game starts) instead of resetting */
 } tak_selfplay_config_t;
 
 typedef struct tak_selfplay_stats {

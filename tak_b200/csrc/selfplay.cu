@@ -378,7 +378,10 @@ int32_t selfplay_begin(tak_engine_t* e, const tak_selfplay_config_t* cfg) {
     TB_CUDA(cudaMemsetAsync(s->serial.p, 0, size_t(G) * 4, e->stream));
     TB_CUDA(cudaMemsetAsync(s->counts.p, 0, 16, e->stream));
     TB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&s->h_counts), 16));
-    if (int r = tak_games_reset(e, 0, G, cfg->half_komi)) return r;
+    // reserved[0] != 0 ("keep_positions"): the games keep the positions they hold (e.g. mid-game positions uploaded or
+    // produced by tak_playouts) instead of starting from the empty board; slots that finish restart as usual
+    if (!cfg->reserved[0])
+        if (int r = tak_games_reset(e, 0, G, cfg->half_komi)) return r;
     if (int r = mcts_launch_tree_reset(e, nullptr, G)) return r;
     TB_CUDA(cudaMemsetAsync(e->mcts->counters.p, 0, 64, e->stream));
     TB_CUDA(cudaStreamSynchronize(e->stream));

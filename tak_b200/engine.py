@@ -437,6 +437,7 @@ class Engine:
                              noise_ply=kw.get("noise_ply", 0), noise_alpha=kw.get("noise_alpha", 0.2),
                              noise_ratio=kw.get("noise_ratio", 0.3), seed=kw.get("seed", 0x7A4B),
                              max_plies=kw.get("max_plies", 0), game_id_base=kw.get("game_id_base", 0))
+        cfg.reserved[0] = 1 if kw.get("keep_positions", False) else 0     # start from the positions the slots hold now
         check(self.lib.selfplay_begin(self._h, C.byref(cfg)))
 
     def selfplay_step(self, moves: int = 1) -> SelfplayStats:
