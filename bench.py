@@ -474,18 +474,21 @@ def interactive_rates(local, blob, states):
     eng = tb.Engine(6, 2, device=local, nodes_per_game=1 << 23, max_batch=256)
     eng.net_create(6)
     eng.net_load_weights(blob)
-    out = {"policy_eval_ms": {}, "what": "net_policy_eval(host states -> full softmax [b, 9036] + value on the host), "
-                                         "median of 20 calls; Player(batch 32).rollout() on one game for 1 s; "
+    out = {"policy_eval_ms": {}, "what": "net_policy_eval(host states -> full softmax [b, 9036] + value in pinned host buffers "
+                                         "(tak_host_alloc; _pageable: ordinary numpy arrays)), median of 20 calls; Player(batch 32).rollout() on one game for 1 s; "
                                          "selfplay_step on 32 games x 800 rollouts"}
+    out["policy_eval_ms_pageable"] = {}
     for b in (1, 32, 256):
-        st = states[:b]
-        eng.policy_eval(st)
-        ts = []
-        for _ in range(20):
-            t0 = time.perf_counter()
-            eng.policy_eval(st)
-            ts.append(time.perf_counter() - t0)
-        out["policy_eval_ms"][str(b)] = 1e3 * float(np.median(ts))
+        st = (tb.TakState * b)(*states[:b])            # the caller's games as one POD array
+        pinned = (eng.pinned_array((b, eng.policy_size)), eng.pinned_array((b,)))   # result buffers from tak_host_alloc
+        for key, buf in (("policy_eval_ms", pinned), ("policy_eval_ms_pageable", None)):
+            eng.policy_eval(st, out=buf)
+            ts = []
+            for _ in range(20):
+                t0 = time.perf_counter()
+                eng.policy_eval(st, out=buf)
+                ts.append(time.perf_counter() - t0)
+            out[key][str(b)] = 1e3 * float(np.median(ts))
     gid, batch = 0, 32
     eng.reset(gid, 1, 4)
     pl = tb.Player(eng, gid, batch)

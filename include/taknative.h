@@ -170,6 +170,11 @@ int32_t net_policy_eval(tak_engine_t* e, const tak_state_t* states, int32_t b, f
 /* the same forward pass, but out_logits[B][policy_size] holds the PRE-softmax policy logits (net6.rs:99-100 / net5.rs:108
  * before `softmax`): the surface the network tolerance is stated on (max abs 1e-2 against an fp32 forward) */
 int32_t net_policy_logits(tak_engine_t* e, const tak_state_t* states, int32_t b, float* out_logits, float* out_value);
+/* Page-locked host memory for the buffers a caller hands to the entry points above and below (cudaMallocHost /
+ * cudaFreeHost): device <-> host copies into pinned memory are plain DMA at PCIe speed; into pageable memory the driver
+ * stages them (measured: net_policy_eval of 32 positions, 1.16 MB of policy out: 0.69 ms into a pageable buffer). */
+int32_t tak_host_alloc(size_t bytes, void** out);
+int32_t tak_host_free(void* p);
 /* device-resident variant used by bench.py `value`: evaluates the states of games [first, first+count) in place;
  * returns device milliseconds for `reps` forward passes */
 int32_t net_forward_timed(tak_engine_t* e, int32_t first, int32_t count, int32_t reps, double* out_ms);

@@ -140,6 +140,8 @@ SYMBOLS = {
     "net_game_repr": (_i32, [_vp, _P(TakState), _i32, _P(_f32)]),
     "net_policy_eval": (_i32, [_vp, _P(TakState), _i32, _P(_f32), _P(_f32)]),
     "net_policy_logits": (_i32, [_vp, _P(TakState), _i32, _P(_f32), _P(_f32)]),
+    "tak_host_alloc": (_i32, [C.c_size_t, _P(_vp)]),
+    "tak_host_free": (_i32, [_vp]),
     "net_forward_timed": (_i32, [_vp, _i32, _i32, _i32, _P(C.c_double)]),
     "net_forward_profile": (_i32, [_vp, _i32, _i32, _i32, _P(C.c_double)]),
     "net_train_begin": (_i32, [_vp, _i32]),

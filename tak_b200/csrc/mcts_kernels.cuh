@@ -224,6 +224,7 @@ static __global__ void __launch_bounds__(1024)
     __shared__ int s_warp[32];
     __shared__ int s_carry;
     if (threadIdx.x == 0) s_carry = 0;
+    if (threadIdx.x < 32) s_warp[threadIdx.x] = 0;   // the block may have fewer than 32 warps: unused entries scan as 0
     __syncthreads();
     for (int base = 0; base < n_games; base += blockDim.x) {
         const int g = base + threadIdx.x;

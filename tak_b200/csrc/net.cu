@@ -384,15 +384,18 @@ int32_t net_load_weights_device(tak_engine_t* e, const void* device_blob, int64_
 
 static int stage_states(tak_engine_t* e, const tak_state_t* states, int b) {
     NetState& ns = *e->net;
-    std::vector<uint8_t> packed(size_t(b) * e->state_bytes);
+    // packed into the engine's pinned staging buffer: the H2D copy is then a plain stream-ordered DMA (every caller
+    // synchronises the stream before it returns, so the buffer is free again by the next call)
+    const size_t bytes = size_t(b) * e->state_bytes;
+    TB_CUDA(e->ensure_pinned(bytes));
+    uint8_t* packed = static_cast<uint8_t*>(e->h_stage);
     for (int i = 0; i < b; ++i) {
         TB_CHECK(states[i].n == e->n, TAK_ERR_BAD_ARG, "state %d has board size %d, engine has %d", i, states[i].n,
                  e->n);
-        pack_state(e->n, states[i], packed.data() + size_t(i) * e->state_bytes);
+        pack_state(e->n, states[i], packed + size_t(i) * e->state_bytes);
     }
-    TB_CUDA(ns.stage_states.ensure(packed.size()));
-    TB_CUDA(cudaMemcpyAsync(ns.stage_states.p, packed.data(), packed.size(), cudaMemcpyHostToDevice, e->stream));
-    TB_CUDA(cudaStreamSynchronize(e->stream));
+    TB_CUDA(ns.stage_states.ensure(bytes));
+    TB_CUDA(cudaMemcpyAsync(ns.stage_states.p, packed, bytes, cudaMemcpyHostToDevice, e->stream));
     return TAK_OK;
 }
 
@@ -450,6 +453,17 @@ static int32_t policy_eval_impl(tak_engine_t* e, const tak_state_t* states, int3
         TB_CUDA(cudaMemcpyAsync(out_value + done, ns.values.p, size_t(cur) * 4, cudaMemcpyDeviceToHost, e->stream));
         TB_CUDA(cudaStreamSynchronize(e->stream));
     }
+    return TAK_OK;
+}
+
+int32_t tak_host_alloc(size_t bytes, void** out) {
+    TB_CHECK(out && bytes > 0, TAK_ERR_BAD_ARG, "tak_host_alloc: bad argument");
+    TB_CUDA(cudaMallocHost(out, bytes));
+    return TAK_OK;
+}
+
+int32_t tak_host_free(void* p) {
+    if (p) TB_CUDA(cudaFreeHost(p));
     return TAK_OK;
 }
 

@@ -92,6 +92,9 @@ class Engine:
         if getattr(self, "_h", None):
             self.lib.tak_engine_destroy(self._h)
             self._h = None
+        for ptr in getattr(self, "_pinned", []):
+            self.lib.tak_host_free(ptr)
+        self._pinned = []
 
     def __del__(self):
         try:
@@ -236,14 +239,32 @@ class Engine:
         check(self.lib.net_game_repr(self._h, arr, b, out.ctypes.data_as(C.POINTER(C.c_float))))
         return out
 
-    def policy_eval(self, states: Sequence[TakState]) -> Tuple[np.ndarray, np.ndarray]:
-        """`Network::policy_eval(&[Game])` -> (policy [B, policy_size], eval [B])."""
+    def pinned_array(self, shape, dtype=np.float32) -> np.ndarray:
+        """A numpy array in page-locked host memory (tak_host_alloc); it lives as long as the engine object."""
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape))
+        ptr = C.c_void_p()
+        check(self.lib.tak_host_alloc(max(1, n * dtype.itemsize), C.byref(ptr)))
+        self._pinned = getattr(self, "_pinned", [])
+        self._pinned.append(ptr)
+        buf = (C.c_uint8 * (n * dtype.itemsize)).from_address(ptr.value)
+        return np.frombuffer(buf, dtype=dtype, count=n).reshape(shape)
+
+    def policy_eval(self, states, out: Optional[Tuple[np.ndarray, np.ndarray]] = None) -> Tuple[np.ndarray, np.ndarray]:
+        """`Network::policy_eval(&[Game])` -> (policy [B, policy_size], eval [B]).  `states`: a sequence of TakState or a
+        ctypes array of them; `out`: preallocated (policy, eval) arrays, e.g. from `pinned_array` (DMA instead of the
+        driver's staged copy into pageable memory)."""
         b = len(states)
-        pol = np.zeros((b, self.policy_size), dtype=np.float32)
-        val = np.zeros(b, dtype=np.float32)
+        if out is not None:
+            pol, val = out
+            assert pol.shape == (b, self.policy_size) and val.shape == (b,) and pol.dtype == val.dtype == np.float32
+            assert pol.flags.c_contiguous and val.flags.c_contiguous
+        else:
+            pol = np.zeros((b, self.policy_size), dtype=np.float32)
+            val = np.zeros(b, dtype=np.float32)
         if b == 0:
             return pol, val
-        arr = (TakState * b)(*states)
+        arr = states if isinstance(states, C.Array) else (TakState * b)(*states)
         check(self.lib.net_policy_eval(self._h, arr, b, pol.ctypes.data_as(C.POINTER(C.c_float)),
                                        val.ctypes.data_as(C.POINTER(C.c_float))))
         return pol, val
