@@ -53,15 +53,33 @@ _lib = None
 _native = False
 
 
+def _cpu_tag() -> str:
+    """Identifies this machine's CPU (model + ISA flags): a -march=native library must never run on another one."""
+    import hashlib
+    try:
+        with open("/proc/cpuinfo") as f:
+            lines = [ln for ln in f if ln.startswith(("model name", "flags"))][:2]
+        return hashlib.sha1("".join(lines).encode()).hexdigest()[:10]
+    except OSError:
+        return "unknown"
+
+
+_native_path = None
+
+
 def use_native_build() -> bool:
-    """bench.py's CPU-baseline legs: compile liboracle_native.so with -march=native on THIS machine and use it (must be
-    called before the first oracle call).  Falls back to the portable build if the compiler is missing."""
-    global _native
+    """bench.py's CPU-baseline legs: compile the oracle with -march=native on THIS machine (file name keyed by the CPU, so
+    a library built elsewhere and carried along in the tree is never loaded) and use it.  Must be called before the
+    first oracle call; falls back to the portable build if the compiler is missing."""
+    global _native, _native_path
     if _lib is not None:
         return _native
+    path = os.path.join(_HERE, f"liboracle_native_{_cpu_tag()}.so")
     try:
-        subprocess.check_call(["make", "-C", _HERE, "-s", "native"])
-        _native = os.path.exists(os.path.join(_HERE, "liboracle_native.so"))
+        if not os.path.exists(path):
+            subprocess.check_call(["g++", "-O3", "-march=native", "-std=c++17", "-fPIC", "-ffp-contract=off", "-pthread",
+                                   "-shared", "-o", path, os.path.join(_HERE, "oracle_capi.cpp")])
+        _native, _native_path = True, path
     except Exception:
         _native = False
     return _native
@@ -71,7 +89,7 @@ def lib():
     global _lib
     if _lib is None:
         build()
-        L = C.CDLL(os.path.join(_HERE, "liboracle_native.so") if _native else _LIB_PATH)
+        L = C.CDLL(_native_path if _native else _LIB_PATH)
         vp, i32, u16, u64, f32 = C.c_void_p, C.c_int, C.c_uint16, C.c_uint64, C.c_float
         sig = {
             "orc_game_new": (vp, [i32, i32]),
