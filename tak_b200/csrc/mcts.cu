@@ -183,7 +183,14 @@ static int launch_step(tak_engine* e, const int* d_ids, int n, const uint8_t* d_
         return s ? std::atoi(s) : 64;
     }();
     const bool capped = regs != 128 && ps.arch != 0 && (e->n == 5 || e->n == 6);
-    if (capped && e->n == 6) {
+    static const int cwarps = [] {
+        const char* s = std::getenv("TAK_STEP_WARPS");
+        return s ? std::atoi(s) : 2;
+    }();
+    if (capped && e->n == 6 && cwarps == 3) {      // 3 warps x 64 registers = 6 144 of the 6 400 a tower CTA leaves free
+        k_mcts_step<6, 96, 10><<<(n + 2) / 3, 96, 0, e->stream>>>(m.view(), e->states.as<uint8_t>(), d_ids, n, d_enable, fe,
+                                                                  ps, do_backup, do_rollout, reps);
+    } else if (capped && e->n == 6) {
         k_mcts_step<6, 64, 16><<<(n + 1) / 2, 64, 0, e->stream>>>(m.view(), e->states.as<uint8_t>(), d_ids, n, d_enable, fe,
                                                                   ps, do_backup, do_rollout, reps);
     } else if (capped && e->n == 5) {

@@ -233,7 +233,7 @@ static int train_chunk_t(tak_engine* e, TrainState& t, const float* d_in, const 
         // conv2 of a block adds the block input before the ReLU (res_block.rs:21-22)
         const bool is_conv2 = l >= 2 && (l % 2) == 0;
         const bf* res = is_conv2 ? t.layers[l - 2].z.as<bf>() : nullptr;
-        k_bn_apply<N><<<ew_blocks, 256, 0, e->stream>>>(L.y.as<bf>(), res, sums, count, master + L.gamma_off,
+        k_bn_apply<N><<<ew_grid(S), 256, 0, e->stream>>>(L.y.as<bf>(), res, sums, count, master + L.gamma_off,
                                                         master + L.beta_off, master + L.rm_off, master + L.rv_off, mean,
                                                         rstd, B, S, L.z.as<bf>());
         t.launches += 1;
@@ -344,7 +344,7 @@ static int train_chunk_t(tak_engine* e, TrainState& t, const float* d_in, const 
         TB_CUDA(cudaMemsetAsync(t.bwd_sums.p, 0, 256 * 8, e->stream));
         k_bn_bwd_reduce<<<dim3(BNR_SPLIT, 16), 256, 0, e->stream>>>(gin, L.z.as<bf>(), L.y.as<bf>(), mean, rstd, S,
                                                                     t.bwd_sums.as<double>());
-        k_bn_bwd_apply<N><<<ew_blocks, 256, 0, e->stream>>>(gin, L.z.as<bf>(), L.y.as<bf>(), mean, rstd,
+        k_bn_bwd_apply<N><<<ew_grid(S), 256, 0, e->stream>>>(gin, L.z.as<bf>(), L.y.as<bf>(), mean, rstd,
                                                             master + L.gamma_off, t.bwd_sums.as<double>(), count,
                                                             grad + L.gamma_off, grad + L.beta_off, B, S, dy_out, gmasked);
         t.launches += 2;

@@ -98,13 +98,18 @@ __global__ void __launch_bounds__(256) k_nchw_to_planes(const float* in, int n_b
 // 8-channel chunk; its first 8 threads turn the conv epilogue's double sums into mean / rstd and the affine a, b, and the
 // first block of every chunk also stores mean / rstd for backward and updates the running statistics (momentum 0.1,
 // unbiased variance, as libtorch).
+// Elementwise passes over the strip planes: grid = (ceil(S / (256 * EW_UNROLL)), 16 channel chunks); a thread handles
+// EW_UNROLL slots 256 apart and issues all its 16-byte loads before it touches the first value (the one-element-per-thread
+// version ran at 0.57-0.68 of the HBM peak: too few bytes in flight per SM).
+constexpr int EW_UNROLL = 4;
+inline dim3 ew_grid(int S) { return dim3(unsigned((S + 256 * EW_UNROLL - 1) / (256 * EW_UNROLL)), 16); }
+
 template <int N>
 __global__ void __launch_bounds__(256) k_bn_apply(const __nv_bfloat16* y, const __nv_bfloat16* res, const double* sums,
                                                   double count, const float* gamma, const float* beta,
                                                   float* running_mean, float* running_var, float* mean_out,
                                                   float* rstd_out, int n_boards, int S, __nv_bfloat16* z) {
-    const size_t idx = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    const int chunk = int((size_t(blockIdx.x) * blockDim.x) / S);
+    const int chunk = blockIdx.y;
     __shared__ float s_a[8], s_b[8];
     if (threadIdx.x < 8) {
         const int c = chunk * 8 + threadIdx.x;
@@ -115,7 +120,7 @@ __global__ void __launch_bounds__(256) k_bn_apply(const __nv_bfloat16* y, const 
         const double a = double(gamma[c]) * rstd;
         s_a[threadIdx.x] = float(a);
         s_b[threadIdx.x] = float(double(beta[c]) - mean * a);
-        if ((size_t(blockIdx.x) * blockDim.x) % S == 0) {
+        if (blockIdx.x == 0) {
             mean_out[c] = float(mean);
             rstd_out[c] = float(rstd);
             const double unbiased = count > 1 ? var * count / (count - 1) : var;
@@ -123,22 +128,39 @@ __global__ void __launch_bounds__(256) k_bn_apply(const __nv_bfloat16* y, const 
             running_var[c] = float((1.0 - TRAIN_BN_MOMENTUM) * running_var[c] + TRAIN_BN_MOMENTUM * unbiased);
         }
     }
-    __syncthreads();
-    if (idx >= size_t(16) * S) return;
-    const size_t slot = idx % S;
-    float o[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if (slot_valid<N>(slot, n_boards)) {
-        float f[8], r[8];
-        unpack8(*reinterpret_cast<const uint4*>(y + idx * 8), f);
-        if (res) unpack8(*reinterpret_cast<const uint4*>(res + idx * 8), r);
+    const int s0 = blockIdx.x * (256 * EW_UNROLL) + threadIdx.x;
+    uint4 yv[EW_UNROLL], rv[EW_UNROLL];
+    bool ok[EW_UNROLL];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            float v = f[j] * s_a[j] + s_b[j];
-            if (res) v += r[j];
-            o[j] = fmaxf(v, 0.f);
+    for (int u = 0; u < EW_UNROLL; ++u) {
+        const int slot = s0 + 256 * u;
+        ok[u] = slot < S && slot_valid<N>(size_t(slot), n_boards);
+        yv[u] = rv[u] = make_uint4(0, 0, 0, 0);
+        if (ok[u]) {
+            const size_t idx = size_t(chunk) * S + slot;
+            yv[u] = *reinterpret_cast<const uint4*>(y + idx * 8);
+            if (res) rv[u] = *reinterpret_cast<const uint4*>(res + idx * 8);
         }
     }
-    *reinterpret_cast<uint4*>(z + idx * 8) = pack8(o);
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < EW_UNROLL; ++u) {
+        const int slot = s0 + 256 * u;
+        if (slot >= S) continue;
+        float o[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (ok[u]) {
+            float f[8], r[8];
+            unpack8(yv[u], f);
+            unpack8(rv[u], r);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float v = f[j] * s_a[j] + s_b[j];
+                if (res) v += r[j];
+                o[j] = fmaxf(v, 0.f);
+            }
+        }
+        *reinterpret_cast<uint4*>(z + (size_t(chunk) * S + slot) * 8) = pack8(o);
+    }
 }
 
 // ---- BatchNorm backward ---------------------------------------------------------------------------------------------
@@ -158,17 +180,32 @@ static __global__ void __launch_bounds__(256) k_bn_bwd_reduce(const __nv_bfloat1
         r[j] = rstd[chunk * 8 + j];
         a1[j] = a2[j] = 0.f;
     }
-    for (int s = s0 + threadIdx.x; s < s1; s += blockDim.x) {
-        const size_t idx = size_t(chunk) * S + s;
-        float gv[8], yv[8], zv[8];
-        unpack8(*reinterpret_cast<const uint4*>(g + idx * 8), gv);
-        unpack8(*reinterpret_cast<const uint4*>(y + idx * 8), yv);
-        if (zout) unpack8(*reinterpret_cast<const uint4*>(zout + idx * 8), zv);
+    for (int sb = s0 + threadIdx.x; sb < s1; sb += blockDim.x * EW_UNROLL) {
+        uint4 gq[EW_UNROLL], yq[EW_UNROLL], zq[EW_UNROLL];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float gg = (!zout || zv[j] > 0.f) ? gv[j] : 0.f;
-            a1[j] += gg;
-            a2[j] += gg * ((yv[j] - m[j]) * r[j]);
+        for (int u = 0; u < EW_UNROLL; ++u) {      // all loads of this round first
+            const int sl = sb + u * blockDim.x;
+            gq[u] = yq[u] = zq[u] = make_uint4(0, 0, 0, 0);
+            if (sl < s1) {
+                const size_t idx = size_t(chunk) * S + sl;
+                gq[u] = *reinterpret_cast<const uint4*>(g + idx * 8);
+                yq[u] = *reinterpret_cast<const uint4*>(y + idx * 8);
+                if (zout) zq[u] = *reinterpret_cast<const uint4*>(zout + idx * 8);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < EW_UNROLL; ++u) {
+            if (sb + u * blockDim.x >= s1) continue;   // (a zero gradient would add m*r*0 = 0 anyway)
+            float gv[8], yv[8], zv[8];
+            unpack8(gq[u], gv);
+            unpack8(yq[u], yv);
+            unpack8(zq[u], zv);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float gg = (!zout || zv[j] > 0.f) ? gv[j] : 0.f;
+                a1[j] += gg;
+                a2[j] += gg * ((yv[j] - m[j]) * r[j]);
+            }
         }
     }
     __shared__ float sh[8][16];
@@ -206,38 +243,58 @@ __global__ void __launch_bounds__(256) k_bn_bwd_apply(const __nv_bfloat16* g, co
                                                       const float* gamma, const double* sums, double count,
                                                       float* grad_gamma, float* grad_beta,
                                                       int n_boards, int S, __nv_bfloat16* dy, __nv_bfloat16* gmasked) {
-    const size_t idx = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    const int chunk = int((size_t(blockIdx.x) * blockDim.x) / S);
-    __shared__ float c1[8], c2[8];
+    const int chunk = blockIdx.y;
+    __shared__ float c1[8], c2[8], s_m[8], s_r[8], s_gr[8];
     if (threadIdx.x < 8) {
         const int c = chunk * 8 + threadIdx.x;
         c1[threadIdx.x] = float(sums[c] / count);
         c2[threadIdx.x] = float(sums[128 + c] / count);
-        if ((size_t(blockIdx.x) * blockDim.x) % S == 0) {
+        s_m[threadIdx.x] = mean[c];
+        s_r[threadIdx.x] = rstd[c];
+        s_gr[threadIdx.x] = gamma[c] * rstd[c];
+        if (blockIdx.x == 0) {
             grad_beta[c] += float(sums[c]);
             grad_gamma[c] += float(sums[128 + c]);
         }
     }
-    __syncthreads();
-    if (idx >= size_t(16) * S) return;
-    const size_t slot = idx % S;
-    float o[8] = {0, 0, 0, 0, 0, 0, 0, 0}, gm[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if (slot_valid<N>(slot, n_boards)) {
-        float gv[8], yv[8], zv[8];
-        unpack8(*reinterpret_cast<const uint4*>(g + idx * 8), gv);
-        unpack8(*reinterpret_cast<const uint4*>(y + idx * 8), yv);
-        if (zout) unpack8(*reinterpret_cast<const uint4*>(zout + idx * 8), zv);
+    const int s0 = blockIdx.x * (256 * EW_UNROLL) + threadIdx.x;
+    uint4 gq[EW_UNROLL], yq[EW_UNROLL], zq[EW_UNROLL];
+    bool ok[EW_UNROLL];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int c = chunk * 8 + j;
-            const float gg = (!zout || zv[j] > 0.f) ? gv[j] : 0.f;
-            const float xhat = (yv[j] - mean[c]) * rstd[c];
-            gm[j] = gg;
-            o[j] = gamma[c] * rstd[c] * (gg - c1[j] - xhat * c2[j]);
+    for (int u = 0; u < EW_UNROLL; ++u) {
+        const int slot = s0 + 256 * u;
+        ok[u] = slot < S && slot_valid<N>(size_t(slot), n_boards);
+        gq[u] = yq[u] = zq[u] = make_uint4(0, 0, 0, 0);
+        if (ok[u]) {
+            const size_t idx = size_t(chunk) * S + slot;
+            gq[u] = *reinterpret_cast<const uint4*>(g + idx * 8);
+            yq[u] = *reinterpret_cast<const uint4*>(y + idx * 8);
+            if (zout) zq[u] = *reinterpret_cast<const uint4*>(zout + idx * 8);
         }
     }
-    *reinterpret_cast<uint4*>(dy + idx * 8) = pack8(o);
-    if (gmasked) *reinterpret_cast<uint4*>(gmasked + idx * 8) = pack8(gm);
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < EW_UNROLL; ++u) {
+        const int slot = s0 + 256 * u;
+        if (slot >= S) continue;
+        float o[8] = {0, 0, 0, 0, 0, 0, 0, 0}, gm[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (ok[u]) {
+            float gv[8], yv[8], zv[8];
+            unpack8(gq[u], gv);
+            unpack8(yq[u], yv);
+            unpack8(zq[u], zv);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float gg = (!zout || zv[j] > 0.f) ? gv[j] : 0.f;
+                const float xhat = (yv[j] - s_m[j]) * s_r[j];
+                gm[j] = gg;
+                o[j] = s_gr[j] * (gg - c1[j] - xhat * c2[j]);
+            }
+        }
+        const size_t idx = size_t(chunk) * S + slot;
+        *reinterpret_cast<uint4*>(dy + idx * 8) = pack8(o);
+        if (gmasked) *reinterpret_cast<uint4*>(gmasked + idx * 8) = pack8(gm);
+    }
 }
 
 // ---- heads ----------------------------------------------------------------------------------------------------------
