@@ -98,7 +98,14 @@ static int check_ids(tak_engine_t* e, const int32_t* ids, int32_t n) {
 // games count 1 (perft.rs:4).  When a frontier's children exceed PF_CAP states, the parents are cut into slices by
 // binary search on the scanned offsets and each slice is expanded and recursed into separately, so memory is bounded
 // by PF_CAP states per level.
-static constexpr size_t PF_CAP = size_t(1) << 24;
+static size_t pf_cap() {   // states per level; TAK_PERFT_CAP overrides it (the tests force the slicing path with it)
+    static const size_t cap = [] {
+        const char* s = std::getenv("TAK_PERFT_CAP");
+        const long long v = s ? std::atoll(s) : 0;
+        return v >= 4096 ? size_t(v) : size_t(1) << 24;
+    }();
+    return cap;
+}
 
 // `frontier` holds n parents at `depth_left` >= 2 plies above the counted level; counts[i] = children of parent i
 static int perft_variant() {
@@ -141,6 +148,7 @@ static int perft_level(tak_engine* e, const uint8_t* frontier, size_t n, const u
     if (int r = offset_at(n, &total)) return r;
     if (total == 0) return TAK_OK;
     const bool last = depth_left == 2;   // the children of this frontier are the counted level
+    const size_t PF_CAP = pf_cap();
     TB_CUDA(cudaFuncSetAttribute(k_perft_apply<N, true, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, P::SMEM));
     TB_CUDA(cudaFuncSetAttribute(k_perft_apply<N, false, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, P::SMEM));
     size_t begin = 0;

@@ -318,3 +318,28 @@ def test_8x8_stacks_taller_than_64():
             if g.result() == 0:
                 assert list(lists[i]) == g.possible_moves()
         eng.close()
+
+
+def test_perft_sliced_frontiers():
+    """A frontier whose children exceed the per-level arena is cut into slices of parents that are expanded and recursed
+    into one after the other (memory stays bounded for deep perfts).  TAK_PERFT_CAP = 20 000 states forces that path at
+    several levels of 6x6 perft(4) / 5x5 perft(4) and of a deep 8x8 position; the counts must not change."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import sys; sys.path.insert(0, '.'); sys.path.insert(0, 'tests')\n"
+        "import tak_b200 as tb\n"
+        "from util import random_positions, to_tb_state\n"
+        "assert tb.Game.default(5).perft(4) == 2999784\n"
+        "g = random_positions(8, 1, seed=5, min_ply=80, max_ply=120)[0]\n"
+        "e = tb.Engine(8, 4, nodes_per_game=64)\n"
+        "assert e.perft(to_tb_state(g.state()), 3) == g.perft(3, threads=8)\n"
+        "e6 = tb.Engine(6, 4, nodes_per_game=64)\n"
+        "assert e6.perft(tb.state_init(6, 0), 4) == 13586048\n"
+        "print('sliced ok', e6.perft_profile()['launches'])\n")
+    env = dict(os.environ, TAK_PERFT_CAP="20000")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "sliced ok" in out.stdout, out.stdout + out.stderr
+    assert int(out.stdout.split()[-1]) >= 20         # an unsliced 6x6 perft(4) is 13 launches; the 132 720-state level alone is 7 slices
