@@ -349,7 +349,7 @@ def selfplay5_rate(local, world, rank, red, steps, warmup, blob5):
     """configs[1]: 5x5 self-play, random-init Net5, 800 rollouts/move, Dirichlet noise off, always exploit, 1 B200 (every
     rank its own games when N > 1)."""
     import tak_b200 as tb
-    G = 148 * 6 * 8                       # 8 boards per conv tile on 5x5
+    G = 148 * 6 * tb.boards_per_tile(5)   # 6 conv tiles per SM (10 boards per tile on the pad-free 5x5 strip)
     eng = tb.Engine(5, G, device=local, nodes_per_game=1 << 17, max_batch=G)
     eng.net_create(5)
     eng.net_load_weights(blob5)
@@ -380,7 +380,8 @@ def late_game_rate(local, blob, steps):
     configuration from MID-GAME positions (every game advanced by 10..70 uniform-random plies with tak_playouts first):
     more pieces on the board, taller stacks, wider move lists, terminal rollouts that need no evaluation."""
     import tak_b200 as tb
-    G = 5328
+    bpt = tb.boards_per_tile(6)
+    G = 148 * (5 if bpt == 7 else 6) * bpt
     eng = tb.Engine(6, G, device=local, nodes_per_game=1 << 18, max_batch=G)
     eng.net_create(6)
     eng.net_load_weights(blob)
@@ -407,7 +408,7 @@ def late_game_rate(local, blob, steps):
             "mean_start_ply": float(np.mean([s.ply for s in start])), "max_start_ply": int(max(s.ply for s in start)),
             "evals_per_rollout": evals / max(1, rollouts), "games_completed": int(done_games),
             "workload": "6x6 self-play as in the headline, but every game starts 10..70 random plies into the game "
-                        "(one engine replica of 5 328 games; throughput does not depend on the number of replicas, so it "
+                        "(one engine replica; throughput does not depend on the number of replicas, so it "
                         "compares directly with the headline value)"}
 
 
@@ -604,7 +605,11 @@ def run_b200(args):
     # Games never interact, so a GPU's games are split over `replicas` independent engines (own stream, search trees and
     # network replica) driven by one host thread each.
     E = max(1, args.replicas)
-    G = args.games if args.games else 5328 * E          # games per GPU; 5328 = 148 SMs x 6 tiles x 6 boards
+    # games per GPU and replica: a whole number of conv tiles per SM -- 148 SMs x 5 tiles x 7 boards = 5 180 on the pad-free
+    # strip (148 x 6 x 6 = 5 328 on the padded one); the node pools of two replicas then take ~130 GB of the 180 GB
+    bpt = tb.boards_per_tile(6)
+    per_replica = 148 * (5 if bpt == 7 else 6) * bpt
+    G = args.games if args.games else per_replica * E
     Gr = G // E
     G = Gr * E
     R, n = args.rollouts, 6
@@ -762,7 +767,7 @@ def run_b200(args):
         "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"],
         # dram__bytes_read.sum + dram__bytes_write.sum of one tower launch over 5328 boards (ncu --set full,
         # profiles/r01_conv_tc3_ncu_full.txt), scaled to this launch's boards: logits + write-backs of the activations
-        "traffic": 829_248_512 * Gr / 5328,
+        "traffic": 809_880_064 * Gr / 5328,
         "peak_kind": "sustained bf16 (kernel timed in a back-to-back loop under the step's power cap, CUDA events around "
                      "each launch), " + pk["source"],
         "avg_launch_us": 1e3 * prof["ms_conv"] / prof["conv_launches"],
@@ -893,7 +898,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--games", type=int, default=0,
-                    help="concurrent games per GPU (default 5328 per replica = 148 SMs x 6 conv tiles x 6 boards)")
+                    help="concurrent games per GPU (default per replica: 148 SMs x 5 conv tiles x 7 boards = 5180)")
     ap.add_argument("--replicas", type=int, default=2, help="independent engine replicas per GPU (host thread each)")
     ap.add_argument("--rollouts", type=int, default=800)
     ap.add_argument("--nodes-per-game", type=int, default=1 << 18)

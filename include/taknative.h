@@ -165,6 +165,9 @@ int32_t net_weights_size(tak_engine_t* e, int64_t* out_elems);
 int32_t net_load_weights(tak_engine_t* e, const float* blob, int64_t elems);
 int32_t net_load_weights_device(tak_engine_t* e, const void* device_blob, int64_t elems);
 int32_t net_input_channels(int32_t n, int32_t* out_channels);
+/* positions per 256-row tile of the conv tower (7 on 6x6, 10 on 5x5): evaluation batches that are a multiple of
+ * 148 SMs x k tiles x this number fill the machine evenly (sizing hint, e.g. for the number of concurrent games) */
+int32_t net_boards_per_tile(int32_t n, int32_t* out_boards);
 int32_t net_game_repr(tak_engine_t* e, const tak_state_t* states, int32_t b, float* out);
 int32_t net_policy_eval(tak_engine_t* e, const tak_state_t* states, int32_t b, float* out_policy, float* out_value);
 /* the same forward pass, but out_logits[B][policy_size] holds the PRE-softmax policy logits (net6.rs:99-100 / net5.rs:108

@@ -8,7 +8,7 @@ from ._lib import LIB_PATH, ReplayRecord, SelfplayStats, TakNativeError, TakStat
 from .engine import (  # noqa: F401
     RESULT_BLACK, RESULT_DRAW, RESULT_FLAG, RESULT_ONGOING, RESULT_WHITE, Engine, Game, Player, default_starting_stones,
     format_move,
-    example_format, example_parse, input_channels, move_index, parse_move, policy_size, state_init, symmetry_move,
+    boards_per_tile, example_format, example_parse, input_channels, move_index, parse_move, policy_size, state_init, symmetry_move,
     symmetry_state, tps_format, tps_parse,
 )
 

@@ -137,6 +137,7 @@ SYMBOLS = {
     "net_load_weights": (_i32, [_vp, _P(_f32), C.c_int64]),
     "net_load_weights_device": (_i32, [_vp, _vp, C.c_int64]),
     "net_input_channels": (_i32, [_i32, _P(_i32)]),
+    "net_boards_per_tile": (_i32, [_i32, _P(_i32)]),
     "net_game_repr": (_i32, [_vp, _P(TakState), _i32, _P(_f32)]),
     "net_policy_eval": (_i32, [_vp, _P(TakState), _i32, _P(_f32), _P(_f32)]),
     "net_policy_logits": (_i32, [_vp, _P(TakState), _i32, _P(_f32), _P(_f32)]),

@@ -47,9 +47,12 @@
 namespace tb {
 
 // strip layout shared by every kernel that touches activations / logits
-template <int N>
+// PF (pad-free, the inference tower): no pad column -- BW = N, 7 boards of 6x6 (10 of 5x5) per tile, 252 (250) of the
+// 256 MMA rows are real squares; the horizontal taps read masked copies of the slab instead (see the kernel).  The
+// training path keeps the pad column (its weight-gradient kernel relies on it).
+template <int N, bool PF = false>
 struct SlotMap {
-    static constexpr int BW = N + 1;               // board width incl. its zero pad column
+    static constexpr int BW = PF ? N : N + 1;      // board width incl. its zero pad column (none when pad-free)
     static constexpr int BPT = 256 / (N * BW);     // boards per 256-slot tile (strip)
     static constexpr int PITCH = BPT * BW;         // slots per strip row
     static constexpr int USED = N * PITCH;         // slots of a tile that map to a (board, y, x or pad column)
@@ -58,6 +61,13 @@ struct SlotMap {
         return size_t(b / BPT) * 256 + size_t(y * PITCH + (b % BPT) * BW + x);
     }
 };
+
+// The inference path (encode, tower, heads, the search's prior gather) uses the pad-free strip; -DTAK_PADFREE=0 builds it
+// on the padded strip of the training path instead (A/B and fallback).
+#ifndef TAK_PADFREE
+#define TAK_PADFREE 1
+#endif
+constexpr bool INFER_PF = TAK_PADFREE != 0;
 
 constexpr int C3_TILE_M = 256;
 constexpr int C3_HALO = 56;                                // >= PITCH + 1 (43 for 6x6, 49 for 5x5)
@@ -69,6 +79,12 @@ constexpr int C3_STAGES = 4;                               // ring depth (one st
 constexpr int C3_MAX_SLABS = 8;                            // 128 input channels
 constexpr int C3_THREADS = 352;                            // producer, MMA issuer, 8 epilogue warps, janitor
 constexpr int C3_SMEM_BYTES = C3_STAGES * C3_STAGE_BYTES + 3072;
+// Pad-free strip (inference tower): a stage holds THREE copies of the activation slab -- as loaded (kx = 0 taps), with the
+// rows of board column N-1 zeroed (kx = -1 taps: the left neighbour of column 0 is not the previous board's last column)
+// and with the rows of column 0 zeroed (kx = +1 taps) -- and the ring is 3 deep (measured: a 3-stage ring costs nothing).
+constexpr int C3_PF_STAGES = 3;
+constexpr int C3_PF_STAGE_BYTES = 3 * C3_SLAB_BYTES + C3_W_SLAB_BYTES;   // 72192
+constexpr int C3_PF_SMEM_BYTES = C3_PF_STAGES * C3_PF_STAGE_BYTES + 3072; // 219648
 constexpr size_t C3_W_LAYER_ELEMS = size_t(C3_MAX_SLABS) * 9 * 2 * 128 * 8;  // bf16 elements per packed layer
 constexpr int C3_TILE_ALIGN = 1;
 
@@ -123,7 +139,7 @@ struct ConvParams {
                                 // search loop counts its leaves on the device; tile_end = tile_begin + tiles(boards) and
                                 // the launch is sized for the largest batch) -- no host round trip per evaluation
     int n;                      // board size N
-    int bw;                     // N + 1
+    int bw;                     // N + 1 (padded strip) or N (pad-free strip)
     int bpt;                    // boards per tile
     int pitch;                  // bpt * bw
 };
@@ -135,7 +151,9 @@ enum : int {
     C3B_ACC_FULL = C3B_EMPTY + C3_STAGES,  // [2]
     C3B_ACC_EMPTY = C3B_ACC_FULL + 2,      // [2]
     C3B_READY = C3B_ACC_EMPTY + 2,         // [C3_GROUP] outputs of (layer, tile-in-group) stored by all 8 epilogue warps
-    C3B_COUNT = C3B_READY + C3_GROUP
+    C3B_MASKED = C3B_READY + C3_GROUP,     // [C3_STAGES] pad-free: the two masked copies of the stage's slab are written
+    C3B_AFULL = C3B_MASKED + C3_STAGES,    // [C3_STAGES] pad-free: the stage's ACTIVATION slab has landed (its weights: FULL)
+    C3B_COUNT = C3B_AFULL + C3_STAGES
 };
 
 // one round of the 8x8 block transpose across the 8 lanes of a channel chunk (blocks = x[8i + b], i = 0..3)
@@ -167,11 +185,16 @@ struct TowerWalk {
     __device__ int group_size(int g) const { return base + (g < rem ? 1 : 0); }
 };
 
-template <bool TRAIN>
+template <bool TRAIN, bool PF = false>
 static __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc3_kernel(const __grid_constant__ ConvParams p) {
+    static_assert(!(TRAIN && PF), "the training build keeps the padded strip");
+    constexpr int STAGES = PF ? C3_PF_STAGES : C3_STAGES;
+    constexpr int STAGE_BYTES = PF ? C3_PF_STAGE_BYTES : C3_STAGE_BYTES;
+    constexpr int COPIES = PF ? 3 : 1;                       // activation slab copies per stage
+    constexpr int W_OFF = COPIES * C3_SLAB_BYTES;            // the stage's weight slab follows them
     extern __shared__ __align__(1024) uint8_t smem[];
-    uint8_t* stage_buf = smem;                               // C3_STAGES x {activation slab, weight slab}
-    uint8_t* tail = smem + C3_STAGES * C3_STAGE_BYTES;
+    uint8_t* stage_buf = smem;                               // STAGES x {activation slab (x3 when pad-free), weight slab}
+    uint8_t* tail = smem + STAGES * STAGE_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(tail);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail + C3B_COUNT * 8);
     float* s_bias = reinterpret_cast<float*>(tail + C3B_COUNT * 8 + 16);   // [2][128]
@@ -186,9 +209,11 @@ static __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc3_kernel(const
     auto BAR = [&](int i) { return bar0 + 8u * i; };
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < C3_STAGES; ++i) {
+        for (int i = 0; i < STAGES; ++i) {
             mbar_init(BAR(C3B_FULL + i), 1);
             mbar_init(BAR(C3B_EMPTY + i), 1);
+            mbar_init(BAR(C3B_MASKED + i), 1);
+            mbar_init(BAR(C3B_AFULL + i), 1);
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(BAR(C3B_ACC_FULL + i), 1);
@@ -201,9 +226,10 @@ static __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc3_kernel(const
     // griddep_wait() (barrier init, halo fill, TMEM alloc, first weight slab) overlaps the previous kernel's tail.
     griddep_launch_dependents();
     // zero halos: the rows above / below the 256 loaded rows of every slab buffer are never written by the bulk copies
-    for (int i = threadIdx.x; i < C3_STAGES * 2 * 2 * C3_HALO; i += C3_THREADS) {
-        const int row = i % C3_HALO, side = (i / C3_HALO) & 1, plane = i / (2 * C3_HALO);  // plane = stage*2 + kchunk
-        uint8_t* dst = stage_buf + (plane >> 1) * C3_STAGE_BYTES + (plane & 1) * (C3_ROWS * 16) +
+    for (int i = threadIdx.x; i < STAGES * COPIES * 2 * 2 * C3_HALO; i += C3_THREADS) {
+        const int row = i % C3_HALO, side = (i / C3_HALO) & 1, plane = i / (2 * C3_HALO);  // plane = (stage*COPIES + copy)*2 + kchunk
+        const int kc = plane & 1, copy = (plane >> 1) % COPIES, stage = (plane >> 1) / COPIES;
+        uint8_t* dst = stage_buf + stage * STAGE_BYTES + copy * C3_SLAB_BYTES + kc * (C3_ROWS * 16) +
                        (side ? (C3_HALO + C3_TILE_M + row) : row) * 16;
         *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
     }
@@ -239,16 +265,31 @@ static __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc3_kernel(const
                         const int tile = tile0 + (j0 + jj) * int(gridDim.x);
                         const uint8_t* src0 = reinterpret_cast<const uint8_t*>(ld.in) + static_cast<size_t>(tile) * (C3_TILE_M * 16);
                         for (int k = 0; k < ld.slabs; ++k, ++cnt) {
-                            const int sb = cnt % C3_STAGES;
+                            const int sb = cnt % STAGES;
 #if defined(CONV_EXP) && (CONV_EXP & 4)
-                            if (cnt >= C3_STAGES) continue;
+                            if (cnt >= STAGES) continue;
 #endif
-                            if (cnt >= C3_STAGES) mbar_wait(BAR(C3B_EMPTY + sb), ((cnt / C3_STAGES) & 1) ^ 1);
-                            mbar_expect_tx(BAR(C3B_FULL + sb), 2 * C3_TILE_M * 16 + C3_W_SLAB_BYTES);
-                            // weights never depend on anything computed here: they go out first
-                            bulk_g2s(smem_u32(stage_buf + sb * C3_STAGE_BYTES + C3_SLAB_BYTES),
+                            if (cnt >= STAGES) mbar_wait(BAR(C3B_EMPTY + sb), ((cnt / STAGES) & 1) ^ 1);
+                            // pad-free: the activation slab reports on its own barrier, so that the masking warp can start
+                            // on it while the (4.5x larger) weight slab is still in flight; for k > 0 it also goes out first
+                            const uint32_t abar = PF ? BAR(C3B_AFULL + sb) : BAR(C3B_FULL + sb);
+                            const uint32_t dst = smem_u32(stage_buf + sb * STAGE_BYTES) + C3_HALO * 16;
+                            if (PF) {
+                                mbar_expect_tx(BAR(C3B_AFULL + sb), 2 * C3_TILE_M * 16);
+                                mbar_expect_tx(BAR(C3B_FULL + sb), C3_W_SLAB_BYTES);
+                                if (k > 0) {
+                                    bulk_g2s(dst, src0 + static_cast<size_t>(2 * k) * plane_bytes, C3_TILE_M * 16, abar);
+                                    bulk_g2s(dst + C3_ROWS * 16, src0 + static_cast<size_t>(2 * k + 1) * plane_bytes,
+                                             C3_TILE_M * 16, abar);
+                                }
+                            } else {
+                                mbar_expect_tx(BAR(C3B_FULL + sb), 2 * C3_TILE_M * 16 + C3_W_SLAB_BYTES);
+                            }
+                            // weights never depend on anything computed here: at k == 0 they go out first
+                            bulk_g2s(smem_u32(stage_buf + sb * STAGE_BYTES + W_OFF),
                                      reinterpret_cast<const uint8_t*>(ld.w) + static_cast<size_t>(k) * C3_W_SLAB_BYTES,
                                      C3_W_SLAB_BYTES, BAR(C3B_FULL + sb));
+                            if (PF && k > 0) continue;
                             if (k == 0) {
                                 if (first_a) {
                                     griddep_wait();  // the tower's input planes are written by the previous kernel
@@ -258,10 +299,9 @@ static __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc3_kernel(const
                                 // once per work item of slot jj, the latest one being (L-1, this tile)
                                 if (L > 0) mbar_wait(BAR(C3B_READY + jj), (items_of[jj] - 1) & 1);
                             }
-                            const uint32_t dst = smem_u32(stage_buf + sb * C3_STAGE_BYTES) + C3_HALO * 16;
-                            bulk_g2s(dst, src0 + static_cast<size_t>(2 * k) * plane_bytes, C3_TILE_M * 16, BAR(C3B_FULL + sb));
+                            bulk_g2s(dst, src0 + static_cast<size_t>(2 * k) * plane_bytes, C3_TILE_M * 16, abar);
                             bulk_g2s(dst + C3_ROWS * 16, src0 + static_cast<size_t>(2 * k + 1) * plane_bytes,
-                                     C3_TILE_M * 16, BAR(C3B_FULL + sb));
+                                     C3_TILE_M * 16, abar);
                         }
                         items_of[jj]++;
                     }
@@ -285,20 +325,52 @@ static __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc3_kernel(const
                         const uint32_t d_base = tmem_base + as * 256;
 #pragma unroll 1
                         for (int k = 0; k < n_slabs; ++k, ++scnt) {
-                            const int sb = scnt % C3_STAGES;
+                            const int sb = scnt % STAGES;
 #if defined(CONV_EXP) && (CONV_EXP & 4)
-                            if (scnt < C3_STAGES)
+                            if (scnt < STAGES)
 #endif
-                            mbar_wait(BAR(C3B_FULL + sb), (scnt / C3_STAGES) & 1);
+                            mbar_wait(BAR(C3B_FULL + sb), (scnt / STAGES) & 1);
+                            if (PF) mbar_wait(BAR(C3B_AFULL + sb), (scnt / STAGES) & 1);
                             tc_fence_after();
-                            const uint32_t a_base = smem_u32(stage_buf + sb * C3_STAGE_BYTES) + C3_HALO * 16;
-                            const uint32_t w_base = smem_u32(stage_buf + sb * C3_STAGE_BYTES + C3_SLAB_BYTES);
+                            const uint32_t a_base = smem_u32(stage_buf + sb * STAGE_BYTES) + C3_HALO * 16;
+                            const uint32_t w_base = smem_u32(stage_buf + sb * STAGE_BYTES + W_OFF);
+                            if constexpr (!PF) {
 #pragma unroll
-                            for (int tap = 0; tap < 9; ++tap) {
-                                const int shift = (tap / 3 - 1) * p.pitch + (tap % 3 - 1);
-                                const uint64_t wdesc = umma_desc_kmajor_noswz(w_base + tap * 4096, 128 * 16, 128);
-                                const uint64_t xdesc = umma_desc_kmajor_noswz(a_base + shift * 16, C3_ROWS * 16, 128);
-                                umma_bf16(d_base, wdesc, xdesc, idesc, (k | tap) != 0);
+                                for (int tap = 0; tap < 9; ++tap) {
+                                    const int shift = (tap / 3 - 1) * p.pitch + (tap % 3 - 1);
+                                    const uint64_t wdesc = umma_desc_kmajor_noswz(w_base + tap * 4096, 128 * 16, 128);
+                                    const uint64_t xdesc = umma_desc_kmajor_noswz(a_base + shift * 16, C3_ROWS * 16, 128);
+                                    umma_bf16(d_base, wdesc, xdesc, idesc, (k | tap) != 0);
+                                }
+                            } else {
+                                // the three centre-column taps read the slab as loaded; they are issued first so that the
+                                // masking warp has ~450 cycles of tensor work to hide behind on top of its head start
+#pragma unroll
+                                for (int ky = 0; ky < 3; ++ky) {
+                                    const int tap = ky * 3 + 1, shift = (ky - 1) * p.pitch;
+                                    const uint64_t wdesc = umma_desc_kmajor_noswz(w_base + tap * 4096, 128 * 16, 128);
+                                    const uint64_t xdesc = umma_desc_kmajor_noswz(a_base + shift * 16, C3_ROWS * 16, 128);
+                                    umma_bf16(d_base, wdesc, xdesc, idesc, (k | ky) != 0);
+                                }
+#if !(defined(CONV_EXP) && (CONV_EXP & 256))
+                                mbar_wait(BAR(C3B_MASKED + sb), (scnt / STAGES) & 1);
+                                tc_fence_after();
+#endif
+#pragma unroll
+                                for (int side = 0; side < 2; ++side) {       // kx = -1 taps on copy 1, kx = +1 taps on copy 2
+#pragma unroll
+                                    for (int ky = 0; ky < 3; ++ky) {
+                                        const int tap = ky * 3 + 2 * side, shift = (ky - 1) * p.pitch + (2 * side - 1);
+                                        const uint64_t wdesc = umma_desc_kmajor_noswz(w_base + tap * 4096, 128 * 16, 128);
+#if defined(CONV_EXP) && (CONV_EXP & 512)
+                                        const uint64_t xdesc = umma_desc_kmajor_noswz(a_base + shift * 16, C3_ROWS * 16, 128);
+#else
+                                        const uint64_t xdesc = umma_desc_kmajor_noswz(
+                                            a_base + (1 + side) * C3_SLAB_BYTES + shift * 16, C3_ROWS * 16, 128);
+#endif
+                                        umma_bf16(d_base, wdesc, xdesc, idesc, true);
+                                    }
+                                }
                             }
                             // ONE commit per slab: tcgen05.commit costs the issue stream ~200 cycles (measured), so
                             // the activation slab and its weights are released together
@@ -530,6 +602,77 @@ static __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc3_kernel(const
         }
     }
 
+    else if (warp == 10 && PF) {
+        // ===================== masking warp (pad-free strip) + janitor =====================
+        // For every stage: once the bulk copies have landed (FULL), write the two masked copies of the activation slab
+        // -- rows of board column N-1 zeroed for the kx = -1 taps, rows of column 0 zeroed for the kx = +1 taps, the tile
+        // remainder (rows >= N*PITCH) zeroed in both -- then publish them to the tensor core (fence.proxy.async) and
+        // arrive on MASKED.  8 KiB read + 16 KiB written per slab: measured cost of that shared-memory traffic beside
+        // the MMAs' operand fetches: +2.2 % per tile-layer, for 7 boards per tile instead of 6.
+        // The L2 discards of dead activation tiles ride along one layer late: when slab 0 of (L, tile) is FULL the
+        // producer has passed READY of (L-1, tile), so that item's input / residual are dead.
+        uint32_t zl = 0, zr = 0;                         // bit i: row lane + 32 i is zero in the left / right copy
+        const int used = p.n * p.pitch;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int r = lane + 32 * i;
+            if (r >= used) {
+                zl |= 1u << i;
+                zr |= 1u << i;
+            } else {
+                const int x = (r % p.pitch) % p.bw;      // pad-free: bw == n
+                if (x == p.n - 1) zl |= 1u << i;
+                if (x == 0) zr |= 1u << i;
+            }
+        }
+        uint32_t mcnt = 0;
+        for (int g = 0, j0 = 0; g < walk.n_groups; j0 += walk.group_size(g), ++g) {
+            const int gs = walk.group_size(g);
+            for (int L = 0; L < p.n_layers; ++L) {
+                const ConvLayerDesc& ld = p.layers[L];
+                for (int jj = 0; jj < gs; ++jj) {
+                    const int tile = tile0 + (j0 + jj) * int(gridDim.x);
+                    for (int k = 0; k < ld.slabs; ++k, ++mcnt) {
+                        const int sb = mcnt % STAGES;
+                        mbar_wait(BAR(C3B_AFULL + sb), (mcnt / STAGES) & 1);
+                        const uint32_t o = smem_u32(stage_buf + sb * STAGE_BYTES) + (C3_HALO + lane) * 16;
+#if defined(CONV_EXP) && (CONV_EXP & 2048)
+                        if (p.S == -7)                       // experiment: no masking traffic at all
+#endif
+#pragma unroll
+                        for (int kc = 0; kc < 2; ++kc) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const uint32_t at = o + kc * (C3_ROWS * 16) + i * 512;
+                                uint32_t a, b, c, d;
+                                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(at));
+                                const bool kl = !((zl >> i) & 1), kr = !((zr >> i) & 1);
+                                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(at + C3_SLAB_BYTES), "r"(kl ? a : 0u),
+                                             "r"(kl ? b : 0u), "r"(kl ? c : 0u), "r"(kl ? d : 0u) : "memory");
+                                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(at + 2 * C3_SLAB_BYTES), "r"(kr ? a : 0u),
+                                             "r"(kr ? b : 0u), "r"(kr ? c : 0u), "r"(kr ? d : 0u) : "memory");
+                            }
+                        }
+#if !(defined(CONV_EXP) && (CONV_EXP & 1024))
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(BAR(C3B_MASKED + sb));
+                        if (k == 0 && L > 0 && p.layers[L - 1].discard) {
+                            const ConvLayerDesc& pd = p.layers[L - 1];
+                            for (int idx = lane; idx < 16 * (C3_TILE_M / 8); idx += 32) {    // (chunk, 128-byte line of 8 slots)
+                                const size_t off = (static_cast<size_t>(idx >> 5) * p.S + static_cast<size_t>(tile) * C3_TILE_M +
+                                                    (idx & 31) * 8) * 8;
+                                if (pd.discard & 1) l2_discard_128(pd.in + off);
+                                if ((pd.discard & 2) && pd.res) l2_discard_128(pd.res + off);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+
     else if (warp == 10) {
         // ===================== janitor =====================
         // Dead activations: once the epilogue of a work item is done (READY), the tile's input (fully consumed by the
@@ -572,14 +715,16 @@ static __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc3_kernel(const
 }
 
 // Host-side launch (layers 0..n_layers-1 over tiles [tile_begin, tile_end)). `stream` is the engine's stream.
-template <bool TRAIN = false>
+template <bool TRAIN = false, bool PF = false>
 inline cudaError_t conv3x3_tc3_launch(const ConvParams& p, int num_sms, cudaStream_t stream) {
+    constexpr int SMEM = PF ? C3_PF_SMEM_BYTES : C3_SMEM_BYTES;
+    if (PF != (p.bw == p.n)) return cudaErrorInvalidValue;   // the layout fields must match the kernel build
     // Set on every launch (a sub-microsecond host call): the kernel has internal linkage, so each translation unit that
     // includes this header owns its own copy of it, while a function-local `static bool` of this inline function would
     // be shared between them.
     {
-        cudaError_t e = cudaFuncSetAttribute(conv3x3_tc3_kernel<TRAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             C3_SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(conv3x3_tc3_kernel<TRAIN, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             SMEM);
         if (e != cudaSuccess) return e;
     }
     const int tiles = p.tile_end - p.tile_begin;
@@ -589,21 +734,21 @@ inline cudaError_t conv3x3_tc3_launch(const ConvParams& p, int num_sms, cudaStre
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(C3_THREADS);
-    cfg.dynamicSmemBytes = C3_SMEM_BYTES;
+    cfg.dynamicSmemBytes = SMEM;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // PDL: see griddep_* in the kernel
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, conv3x3_tc3_kernel<TRAIN>, p);
+    return cudaLaunchKernelEx(&cfg, conv3x3_tc3_kernel<TRAIN, PF>, p);
 }
 
-// fill the layout fields of ConvParams for board size n
-inline void conv_params_set_layout(ConvParams& p, int n) {
+// fill the layout fields of ConvParams for board size n (pad_free: the inference strip without pad columns)
+inline void conv_params_set_layout(ConvParams& p, int n, bool pad_free = false) {
     p.n = n;
-    p.bw = n + 1;
-    p.bpt = 256 / (n * (n + 1));
+    p.bw = pad_free ? n : n + 1;
+    p.bpt = 256 / (n * p.bw);
     p.pitch = p.bpt * p.bw;
 }
 

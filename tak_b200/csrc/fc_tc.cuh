@@ -43,7 +43,7 @@ struct FcParams {
 };
 
 // trunk output strip planes -> X[pos][chunk][board][8]; boards >= n_boards (padding up to b_pad) are written as zero
-template <int N>
+template <int N, bool PF = false>
 __global__ void __launch_bounds__(256) k_fc_repack(const __nv_bfloat16* act, int S, int n_boards, int b_pad,
                                                    __nv_bfloat16* x) {
     const size_t idx = size_t(blockIdx.x) * blockDim.x + threadIdx.x;     // (pos, chunk, board)
@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(256) k_fc_repack(const __nv_bfloat16* act, int
     const int b = int(idx % b_pad), chunk = int((idx / b_pad) % 16), pos = int(idx / (size_t(b_pad) * 16));
     uint4 v = make_uint4(0, 0, 0, 0);
     if (b < n_boards)
-        v = *reinterpret_cast<const uint4*>(act + (size_t(chunk) * S + SlotMap<N>::slot(b, pos / N, pos % N)) * 8);
+        v = *reinterpret_cast<const uint4*>(act + (size_t(chunk) * S + SlotMap<N, PF>::slot(b, pos / N, pos % N)) * 8);
     *reinterpret_cast<uint4*>(x + idx * 8) = v;
 }
 

@@ -283,7 +283,7 @@ __device__ __forceinline__ void backup_leaf(const MctsView& v, uint4* stat, cons
             atomicOr(v.err, MERR_BAD_MOVE);
         } else if (ps.arch == 6) {
             const int ch = idx / NSQ, sq = idx % NSQ, row = sq / N, col = sq % N;
-            const float lg = ps.logits[size_t(ch) * ps.S + SlotMap<N>::slot(ei, row, col)];
+            const float lg = ps.logits[size_t(ch) * ps.S + SlotMap<N, INFER_PF>::slot(ei, row, col)];
             prior = __fdiv_rn(expf(__fsub_rn(lg, mx)), sum);
         } else if (ps.arch == 5) {
             prior = __fdiv_rn(expf(__fsub_rn(ps.logits[size_t(ei) * ps.psz + idx], mx)), sum);
@@ -380,7 +380,7 @@ __global__ void __launch_bounds__(MAXT, MINB)
             const int ei = ps.arch != 0 ? fe.eval_slot[slot] : 0;
             float mx = 0.f, sum = 1.f, eval = 0.f;
             if (ps.arch == 6) {
-                const float2 st = warp_policy_stats<N>(ps.partials, ps.S, ps.groups, ei);
+                const float2 st = warp_policy_stats<N, INFER_PF>(ps.partials, ps.S, ps.groups, ei);
                 mx = st.x;
                 sum = st.y;
             } else if (ps.arch == 5) {
@@ -388,7 +388,7 @@ __global__ void __launch_bounds__(MAXT, MINB)
                 mx = st.x;
                 sum = st.y;
             }
-            if (ps.arch != 0) eval = warp_value<N>(ps.trunk, ps.S, ps.value_w, ps.value_b, ei);
+            if (ps.arch != 0) eval = warp_value<N, INFER_PF>(ps.trunk, ps.S, ps.value_w, ps.value_b, ei);
             backup_leaf<N>(v, stat, link, slot, ei, ps, mx, sum, eval);
             if ((threadIdx.x & 31) == 0) v.pend_cnt[gid] = 0;
             __syncwarp();

@@ -132,7 +132,7 @@ int net_load_blob(tak_engine* e, const float* blob, int64_t elems) {
 // tiles of `boards` boards, rounded up to the cluster granularity of the conv kernel (the extra tiles hold no boards:
 // their activations stay zero)
 static int tiles_for(int n, int boards) {
-    const int t = n == 5 ? SlotMap<5>::tiles(boards) : SlotMap<6>::tiles(boards);
+    const int t = n == 5 ? SlotMap<5, INFER_PF>::tiles(boards) : SlotMap<6, INFER_PF>::tiles(boards);
     return (t + C3_TILE_ALIGN - 1) / C3_TILE_ALIGN * C3_TILE_ALIGN;
 }
 
@@ -172,7 +172,7 @@ static int launch_tower(tak_engine* e, int boards, const int* d_count) {
     __nv_bfloat16* t = ns.act[1].as<__nv_bfloat16>();
     __nv_bfloat16* y = ns.act[2].as<__nv_bfloat16>();
     ConvParams p{};
-    conv_params_set_layout(p, N);
+    conv_params_set_layout(p, N, INFER_PF);
     p.S = S; p.tile_begin = 0; p.tile_end = tiles; p.n_boards = boards; p.n_boards_dev = d_count;
     auto conv = [&](const ConvLayer& L, const __nv_bfloat16* in, const __nv_bfloat16* res, __nv_bfloat16* out,
                     int mode, int slabs, int grp, int ch_valid, int discard = 0) {
@@ -198,7 +198,7 @@ static int launch_tower(tak_engine* e, int boards, const int* d_count) {
                  std::min(128, ns.policy_ch - grp * 128), std::getenv("TAK_NO_STCS") ? 0 : 4);
     NetProfile* prof = ns.profile;
     if (prof) TB_CUDA(cudaEventRecord(prof->ev[2 * prof->n], e->stream));
-    TB_CUDA(conv3x3_tc3_launch(p, e->num_sms, e->stream));
+    TB_CUDA((conv3x3_tc3_launch<false, INFER_PF>(p, e->num_sms, e->stream)));
     e->launches++;
     if (prof) {
         TB_CUDA(cudaEventRecord(prof->ev[2 * prof->n + 1], e->stream));
@@ -209,7 +209,7 @@ static int launch_tower(tak_engine* e, int boards, const int* d_count) {
         const int b_pad = (boards + FC_NT - 1) / FC_NT * FC_NT;
         TB_CUDA(ns.fc_x.ensure(size_t(N * N) * 16 * b_pad * 16));
         const size_t items = size_t(N * N) * 16 * b_pad;
-        k_fc_repack<N><<<unsigned((items + 255) / 256), 256, 0, e->stream>>>(x, S, boards, b_pad,
+        k_fc_repack<N, INFER_PF><<<unsigned((items + 255) / 256), 256, 0, e->stream>>>(x, S, boards, b_pad,
                                                                             ns.fc_x.as<__nv_bfloat16>());
         FcParams fp{};
         fp.wp = ns.fc_policy_w.as<__nv_bfloat16>(); fp.x = ns.fc_x.as<__nv_bfloat16>();
@@ -236,7 +236,7 @@ static int forward_t(tak_engine* e, const uint8_t* d_states, const int* d_index,
     if (int r = launch_tower<N>(e, boards, nullptr)) return r;
     // heads
     if (ns.arch == 6) {
-        k_policy_stats_conv<N><<<wblocks, 256, 0, e->stream>>>(ns.partials.as<float2>(), S, ns.policy_groups * 4, boards,
+        k_policy_stats_conv<N, INFER_PF><<<wblocks, 256, 0, e->stream>>>(ns.partials.as<float2>(), S, ns.policy_groups * 4, boards,
                                                                ns.stats.as<float2>());
         if (d_policy_out) {
             e->launches++;
@@ -328,6 +328,12 @@ void net_destroy(tak_engine* e) {
 using namespace tb;
 
 extern "C" {
+
+int32_t net_boards_per_tile(int32_t n, int32_t* out_boards) {
+    TB_CHECK((n == 5 || n == 6) && out_boards, TAK_ERR_BAD_ARG, "net_boards_per_tile: n must be 5 or 6");
+    *out_boards = n == 5 ? SlotMap<5, INFER_PF>::BPT : SlotMap<6, INFER_PF>::BPT;
+    return TAK_OK;
+}
 
 int32_t net_input_channels(int32_t n, int32_t* out_channels) {
     TB_CHECK(n >= 3 && n <= 8 && out_channels, TAK_ERR_BAD_ARG, "net_input_channels: bad argument");

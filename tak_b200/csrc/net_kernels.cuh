@@ -58,7 +58,7 @@ __device__ __forceinline__ float repr_plane(const ReprCtx<N>& cx, int ch, Col co
 // game_repr of the game a warp holds in registers -> strip planes of evaluation slot w.  Pad columns and the tile
 // remainder are zero already: the input planes (NetState::act_in) are zero-filled at allocation and only real squares
 // are ever written to them.
-template <int N>
+template <int N, bool PF = INFER_PF>
 __device__ __forceinline__ void encode_board(const WarpGame<N>& g, int w, __nv_bfloat16* planes, int S) {
     ReprCtx<N> cx;
     cx.to_move = g.to_move; cx.ws = g.ws; cx.wc = g.wc; cx.bs = g.bs; cx.bc = g.bc;
@@ -73,7 +73,7 @@ __device__ __forceinline__ void encode_board(const WarpGame<N>& g, int w, __nv_b
         const int h = half ? g.h1 : g.h0;
         const int kind = ((g.walls >> o) & 1) ? 1 : ((g.caps >> o) & 1) ? 2 : 0;
         const int x = o / N, y = o % N;
-        const size_t slot = SlotMap<N>::slot(w, y, x);
+        const size_t slot = SlotMap<N, PF>::slot(w, y, x);
         for (int chunk = 0; chunk < 16; ++chunk) {
             uint4 v;
             __nv_bfloat162* vb = reinterpret_cast<__nv_bfloat162*>(&v);
@@ -153,33 +153,34 @@ __device__ __forceinline__ float block_reduce_sum(float v, float* s_tmp) {
 // Net6-style head (policy conv): softmax statistics over ALL channels x squares of one board (net6.rs:100-103).
 // The conv epilogue already reduced every slot's channels to {max, sum exp(l - max)} per 32-channel lane quarter
 // (partials[group*4 + quarter][S]); one warp per board merges the N*N x parts partials: stats[b] = {max, sum of exp(l - max)}.
-template <int N>
+template <int N, bool PF>
 __device__ __forceinline__ float2 warp_policy_stats(const float2* partials, int S, int groups, int b) {
     constexpr int NSQ = N * N;
     const int l = threadIdx.x & 31;
     float mx = -INFINITY;
     for (int i = l; i < NSQ * groups; i += 32) {
         const int g = i / NSQ, sq = i % NSQ;
-        mx = fmaxf(mx, partials[size_t(g) * S + SlotMap<N>::slot(b, sq / N, sq % N)].x);
+        mx = fmaxf(mx, partials[size_t(g) * S + SlotMap<N, PF>::slot(b, sq / N, sq % N)].x);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, o));
     float sum = 0.f;
     for (int i = l; i < NSQ * groups; i += 32) {
         const int g = i / NSQ, sq = i % NSQ;
-        const float2 pr = partials[size_t(g) * S + SlotMap<N>::slot(b, sq / N, sq % N)];
+        const float2 pr = partials[size_t(g) * S + SlotMap<N, PF>::slot(b, sq / N, sq % N)];
         sum += pr.y * expf(pr.x - mx);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(FULL, sum, o);
     return make_float2(mx, sum);
 }
-template <int N>
+// (PF: which strip layout the partials are in -- the training path uses the padded one, the default)
+template <int N, bool PF = false>
 __global__ void __launch_bounds__(256)
     k_policy_stats_conv(const float2* partials, int S, int groups, int n_boards, float2* stats) {
     const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (b >= n_boards) return;
-    const float2 st = warp_policy_stats<N>(partials, S, groups, b);
+    const float2 st = warp_policy_stats<N, PF>(partials, S, groups, b);
     if ((threadIdx.x & 31) == 0) stats[b] = st;
 }
 // full softmax vector [b][n_ch * N*N] (index = ch*N*N + row*N + col) from the logits and the board statistics: the
@@ -193,7 +194,7 @@ __global__ void __launch_bounds__(256)
     float* dst = policy_out + size_t(b) * n_ch * NSQ;
     for (int i = threadIdx.x; i < n_ch * NSQ; i += blockDim.x) {
         const int ch = i / NSQ, sq = i % NSQ;
-        const float lg = logits[size_t(ch) * S + SlotMap<N>::slot(b, sq / N, sq % N)];
+        const float lg = logits[size_t(ch) * S + SlotMap<N, INFER_PF>::slot(b, sq / N, sq % N)];
         dst[i] = raw ? lg : __fdiv_rn(expf(__fsub_rn(lg, st.x)), st.y);   // raw: the pre-softmax logits (parity surface)
     }
 }
@@ -217,14 +218,14 @@ static __global__ void __launch_bounds__(256)
 }
 
 // value head (net6.rs:104-107 / net5.rs:109): tanh(fc(flatten_NCHW(s)))  -- one warp per board
-template <int N>
+template <int N, bool PF>
 __device__ __forceinline__ float warp_value(const __nv_bfloat16* act, int S, const float* wv /*[128*NSQ]*/, float bv, int w) {
     constexpr int NSQ = N * N;
     const int l = threadIdx.x & 31;
     float acc = 0.f;
     for (int pos = l; pos < NSQ; pos += 32) {
         const int y = pos / N, x = pos % N;
-        const size_t slot = SlotMap<N>::slot(w, y, x);
+        const size_t slot = SlotMap<N, PF>::slot(w, y, x);
         for (int chunk = 0; chunk < 16; ++chunk) {
             const uint4 v = *reinterpret_cast<const uint4*>(act + (size_t(chunk) * S + slot) * 8);
             const __nv_bfloat162* vb = reinterpret_cast<const __nv_bfloat162*>(&v);
@@ -245,7 +246,7 @@ __global__ void __launch_bounds__(256)
     k_value(const __nv_bfloat16* act, int S, const float* wv /*[128*NSQ]*/, float bv, int n_boards, float* out) {
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (w >= n_boards) return;
-    const float val = warp_value<N>(act, S, wv, bv, w);
+    const float val = warp_value<N, INFER_PF>(act, S, wv, bv, w);
     if ((threadIdx.x & 31) == 0) out[w] = val;
 }
 

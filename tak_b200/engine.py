@@ -55,6 +55,13 @@ def input_channels(n: int) -> int:
     return out.value
 
 
+def boards_per_tile(n: int) -> int:
+    """Positions per 256-row tile of the conv tower (sizing hint: 148 SMs x k tiles x this many games)."""
+    out = C.c_int32()
+    check(_lib.load().net_boards_per_tile(n, C.byref(out)))
+    return out.value
+
+
 def state_init(n: int, half_komi: int = 0) -> TakState:
     s = TakState()
     check(_lib.load().tak_state_init(n, half_komi, C.byref(s)))

@@ -3,7 +3,8 @@
 // strips, pad columns or halos) on random data, checks that every pad slot is written as zero, checks the per-slot
 // softmax partials of the policy mode, then times the kernel.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -I tak_b200/csrc tests/cuda/conv_selftest.cu -o build/conv_selftest
-// Usage: conv_selftest [boards=2000] [N=6] [slabs=8]
+// Usage: conv_selftest [boards=2000] [N=6] [slabs=8] [pad_free=0]   (pad_free = 1: the inference tower's strip without pad
+//        columns, conv3x3_tc3_kernel<false, true>: 7 boards of 6x6 per tile, masked slab copies for the horizontal taps)
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -53,16 +54,21 @@ int main(int argc, char** argv) {
     const int n_boards = argc > 1 ? atoi(argv[1]) : 2000;
     const int N = argc > 2 ? atoi(argv[2]) : 6;
     const int slabs = argc > 3 ? atoi(argv[3]) : 8;
+    const bool pad_free = argc > 4 && atoi(argv[4]) != 0;
     if (N != 5 && N != 6) { printf("N must be 5 or 6\n"); return 2; }
     ConvParams lay{};
-    conv_params_set_layout(lay, N);
+    conv_params_set_layout(lay, N, pad_free);
+    auto launch = [&](const ConvParams& q, int sms, cudaStream_t st) {
+        return pad_free ? conv3x3_tc3_launch<false, true>(q, sms, st) : conv3x3_tc3_launch<false, false>(q, sms, st);
+    };
     const int tiles = ((n_boards + lay.bpt - 1) / lay.bpt + C3_TILE_ALIGN - 1) / C3_TILE_ALIGN * C3_TILE_ALIGN;
     const int S = tiles * C3_TILE_M;
     const int c_in = slabs * 16;
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, 0));
-    printf("device %s sms %d  boards %d N %d bpt %d pitch %d tiles %d S %d slabs %d smem %d\n", prop.name,
-           prop.multiProcessorCount, n_boards, N, lay.bpt, lay.pitch, tiles, S, slabs, C3_SMEM_BYTES);
+    printf("device %s sms %d  boards %d N %d bpt %d pitch %d tiles %d S %d slabs %d smem %d pad_free %d\n", prop.name,
+           prop.multiProcessorCount, n_boards, N, lay.bpt, lay.pitch, tiles, S, slabs,
+           pad_free ? C3_PF_SMEM_BYTES : C3_SMEM_BYTES, int(pad_free));
     auto slot_of = [&](int b, int y, int x) { return (size_t)(b / lay.bpt) * 256 + y * lay.pitch + (b % lay.bpt) * lay.bw + x; };
 
     const size_t act_elems = (size_t)16 * S * 8;
@@ -141,7 +147,7 @@ int main(int argc, char** argv) {
             CK(cudaMemset(d_out, 0xFF, act_elems * 2));  // poison: every slot of every tile must be written
             CK(cudaMemset(d_logits, 0xFF, (size_t)128 * S * 4));
             CK(cudaMemset(d_part, 0xFF, (size_t)4 * S * 8));
-            CK(conv3x3_tc3_launch(p, sms, 0));
+            CK(launch(p, sms, 0));
             cudaError_t e = cudaDeviceSynchronize();
             if (e != cudaSuccess) {
                 printf("mode %d sms %d: kernel failed: %s\n", mode, sms, cudaGetErrorString(e));
@@ -226,11 +232,11 @@ int main(int argc, char** argv) {
                 if (pass == 0) {
                     for (const ConvLayerDesc& l : {l0, l1, l2}) {
                         q.n_layers = 1; q.layers[0] = l;
-                        CK(conv3x3_tc3_launch(q, sms, 0));
+                        CK(launch(q, sms, 0));
                     }
                 } else {
                     q.n_layers = 3; q.layers[0] = l0; q.layers[1] = l1; q.layers[2] = l2;
-                    CK(conv3x3_tc3_launch(q, sms, 0));
+                    CK(launch(q, sms, 0));
                 }
                 cudaError_t e = cudaDeviceSynchronize();
                 if (e != cudaSuccess) { printf("tower pass %d sms %d: kernel failed: %s\n", pass, sms, cudaGetErrorString(e)); return 3; }
@@ -252,10 +258,10 @@ int main(int argc, char** argv) {
         cudaEvent_t e0, e1;
         CK(cudaEventCreate(&e0));
         CK(cudaEventCreate(&e1));
-        for (int i = 0; i < 5; ++i) CK(conv3x3_tc3_launch(p, prop.multiProcessorCount, 0));
+        for (int i = 0; i < 5; ++i) CK(launch(p, prop.multiProcessorCount, 0));
         CK(cudaEventRecord(e0));
         const int reps = 50;
-        for (int i = 0; i < reps; ++i) CK(conv3x3_tc3_launch(p, prop.multiProcessorCount, 0));
+        for (int i = 0; i < reps; ++i) CK(launch(p, prop.multiProcessorCount, 0));
         CK(cudaEventRecord(e1));
         CK(cudaEventSynchronize(e1));
         float ms;
@@ -269,10 +275,10 @@ int main(int argc, char** argv) {
         ConvParams q = p;
         q.n_layers = 32;
         for (int l = 0; l < 32; ++l) q.layers[l] = layer(l & 1 ? d_out : d_in, nullptr, l & 1 ? d_in : d_out, 0, 128);
-        for (int i = 0; i < 2; ++i) CK(conv3x3_tc3_launch(q, prop.multiProcessorCount, 0));
+        for (int i = 0; i < 2; ++i) CK(launch(q, prop.multiProcessorCount, 0));
         CK(cudaEventRecord(e0));
         const int reps2 = 5;
-        for (int i = 0; i < reps2; ++i) CK(conv3x3_tc3_launch(q, prop.multiProcessorCount, 0));
+        for (int i = 0; i < reps2; ++i) CK(launch(q, prop.multiProcessorCount, 0));
         CK(cudaEventRecord(e1));
         CK(cudaEventSynchronize(e1));
         CK(cudaEventElapsedTime(&ms, e0, e1));
