@@ -765,9 +765,9 @@ def run_b200(args):
     roofline = {
         "bound": "tensor", "kernel": "conv3x3_tc3_kernel", "achieved": achieved, "peak": pk["bf16_sustained"],
         "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"],
-        # dram__bytes_read.sum + dram__bytes_write.sum of one tower launch over 5328 boards (ncu --set full,
-        # profiles/r01_conv_tc3_ncu_full.txt), scaled to this launch's boards: logits + write-backs of the activations
-        "traffic": 809_880_064 * Gr / 5328,
+        # dram__bytes_read.sum + dram__bytes_write.sum of one tower launch over 5180 boards (ncu --set full,
+        # profiles/r02_conv_tc3_padfree_ncu_full.txt), scaled to this launch's boards: logits + write-backs of activations
+        "traffic": 678_200_320 * Gr / 5180,
         "peak_kind": "sustained bf16 (kernel timed in a back-to-back loop under the step's power cap, CUDA events around "
                      "each launch), " + pk["source"],
         "avg_launch_us": 1e3 * prof["ms_conv"] / prof["conv_launches"],
