@@ -34,7 +34,13 @@
 //   warp 1     TMEM allocator + single-thread tcgen05.mma issuer; tcgen05.commit -> empty / acc_full
 //   warps 2-9  epilogue: residual prefetch, tcgen05.ld (software pipelined) -> 8x8 shfl transpose -> +bias (+residual)
 //              -> ReLU -> pad mask -> bf16 strip planes, or fp32 logits + per-slot softmax partials (policy head)
-//   warp 10    janitor: L2-discards the dead input / residual tiles of finished work items (inference tower only)
+//   warp 10    janitor: L2-discards the dead input / residual tiles of finished work items (inference tower only);
+//              on the pad-free strip (template parameter PF, the inference build) it is also the MASKING warp: the strip
+//              has no pad column (7 boards of 6x6 per tile, 252 of 256 MMA rows real), so the kx = -1 / +1 taps read
+//              copies of the activation slab with the rows of board column N-1 / 0 zeroed, which this warp writes into
+//              the stage (3 slab copies + weights = 70.5 KiB per stage, 3 stages) as soon as the slab has landed.
+//              Timing-only experiment switches of that build: CONV_EXP & 512 (all taps read the unmasked slab),
+//              & 1024 (no proxy fence after masking), & 2048 (no masking traffic) -- results are wrong with any of them.
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -352,10 +358,8 @@ static __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc3_kernel(const
                                     const uint64_t xdesc = umma_desc_kmajor_noswz(a_base + shift * 16, C3_ROWS * 16, 128);
                                     umma_bf16(d_base, wdesc, xdesc, idesc, (k | ky) != 0);
                                 }
-#if !(defined(CONV_EXP) && (CONV_EXP & 256))
                                 mbar_wait(BAR(C3B_MASKED + sb), (scnt / STAGES) & 1);
                                 tc_fence_after();
-#endif
 #pragma unroll
                                 for (int side = 0; side < 2; ++side) {       // kx = -1 taps on copy 1, kx = +1 taps on copy 2
 #pragma unroll
