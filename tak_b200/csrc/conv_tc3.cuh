@@ -198,6 +198,11 @@ static __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc3_kernel(const
     constexpr int STAGE_BYTES = PF ? C3_PF_STAGE_BYTES : C3_STAGE_BYTES;
     constexpr int COPIES = PF ? 3 : 1;                       // activation slab copies per stage
     constexpr int W_OFF = COPIES * C3_SLAB_BYTES;            // the stage's weight slab follows them
+#if defined(CONV_PF_BULK3)
+    constexpr int PF_COPIES_LOADED = 3;   // variant: the bulk-copy engine fills all three copies, the masking warp only zeroes
+#else
+    constexpr int PF_COPIES_LOADED = 1;   // the masking warp reads the loaded slab and writes the two masked copies
+#endif
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* stage_buf = smem;                               // STAGES x {activation slab (x3 when pad-free), weight slab}
     uint8_t* tail = smem + STAGES * STAGE_BYTES;
@@ -281,12 +286,16 @@ static __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc3_kernel(const
                             const uint32_t abar = PF ? BAR(C3B_AFULL + sb) : BAR(C3B_FULL + sb);
                             const uint32_t dst = smem_u32(stage_buf + sb * STAGE_BYTES) + C3_HALO * 16;
                             if (PF) {
-                                mbar_expect_tx(BAR(C3B_AFULL + sb), 2 * C3_TILE_M * 16);
+                                mbar_expect_tx(BAR(C3B_AFULL + sb), PF_COPIES_LOADED * 2 * C3_TILE_M * 16);
                                 mbar_expect_tx(BAR(C3B_FULL + sb), C3_W_SLAB_BYTES);
                                 if (k > 0) {
-                                    bulk_g2s(dst, src0 + static_cast<size_t>(2 * k) * plane_bytes, C3_TILE_M * 16, abar);
-                                    bulk_g2s(dst + C3_ROWS * 16, src0 + static_cast<size_t>(2 * k + 1) * plane_bytes,
-                                             C3_TILE_M * 16, abar);
+#pragma unroll
+                                    for (int c = 0; c < PF_COPIES_LOADED; ++c) {
+                                        bulk_g2s(dst + c * C3_SLAB_BYTES, src0 + static_cast<size_t>(2 * k) * plane_bytes,
+                                                 C3_TILE_M * 16, abar);
+                                        bulk_g2s(dst + c * C3_SLAB_BYTES + C3_ROWS * 16,
+                                                 src0 + static_cast<size_t>(2 * k + 1) * plane_bytes, C3_TILE_M * 16, abar);
+                                    }
                                 }
                             } else {
                                 mbar_expect_tx(BAR(C3B_FULL + sb), 2 * C3_TILE_M * 16 + C3_W_SLAB_BYTES);
@@ -305,9 +314,13 @@ static __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc3_kernel(const
                                 // once per work item of slot jj, the latest one being (L-1, this tile)
                                 if (L > 0) mbar_wait(BAR(C3B_READY + jj), (items_of[jj] - 1) & 1);
                             }
-                            bulk_g2s(dst, src0 + static_cast<size_t>(2 * k) * plane_bytes, C3_TILE_M * 16, abar);
-                            bulk_g2s(dst + C3_ROWS * 16, src0 + static_cast<size_t>(2 * k + 1) * plane_bytes,
-                                     C3_TILE_M * 16, abar);
+#pragma unroll
+                            for (int c = 0; c < (PF ? PF_COPIES_LOADED : 1); ++c) {
+                                bulk_g2s(dst + c * C3_SLAB_BYTES, src0 + static_cast<size_t>(2 * k) * plane_bytes, C3_TILE_M * 16,
+                                         abar);
+                                bulk_g2s(dst + c * C3_SLAB_BYTES + C3_ROWS * 16,
+                                         src0 + static_cast<size_t>(2 * k + 1) * plane_bytes, C3_TILE_M * 16, abar);
+                            }
                         }
                         items_of[jj]++;
                     }
@@ -643,6 +656,19 @@ static __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc3_kernel(const
 #if defined(CONV_EXP) && (CONV_EXP & 2048)
                         if (p.S == -7)                       // experiment: no masking traffic at all
 #endif
+#if defined(CONV_PF_BULK3)
+#pragma unroll
+                        for (int kc = 0; kc < 2; ++kc) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const uint32_t at = o + kc * (C3_ROWS * 16) + i * 512;
+                                if ((zl >> i) & 1)
+                                    asm volatile("st.shared.v4.u32 [%0], {%1,%1,%1,%1};" ::"r"(at + C3_SLAB_BYTES), "r"(0u) : "memory");
+                                if ((zr >> i) & 1)
+                                    asm volatile("st.shared.v4.u32 [%0], {%1,%1,%1,%1};" ::"r"(at + 2 * C3_SLAB_BYTES), "r"(0u) : "memory");
+                            }
+                        }
+#else
 #pragma unroll
                         for (int kc = 0; kc < 2; ++kc) {
 #pragma unroll
@@ -657,6 +683,7 @@ static __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc3_kernel(const
                                              "r"(kr ? b : 0u), "r"(kr ? c : 0u), "r"(kr ? d : 0u) : "memory");
                             }
                         }
+#endif
 #if !(defined(CONV_EXP) && (CONV_EXP & 1024))
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 #endif
