@@ -3,6 +3,7 @@
 #include <algorithm>
 #include "mcts.hpp"
 
+#include <climits>
 #include <cmath>
 #include <cstdlib>
 
@@ -108,11 +109,13 @@ int mcts_launch_rollout(tak_engine* e, const int* d_ids, int n, int k, const uin
     return TAK_OK;
 }
 
-int mcts_launch_compact(tak_engine* e) {
+int mcts_launch_compact(tak_engine* e, bool clamp_to_batch) {
     MctsState& m = *e->mcts;
     k_mcts_compact<<<1, 256, 0, e->stream>>>(m.pend_cnt.as<int>(), e->max_games, m.kcap, m.limits_on ? m.limits.as<int>() : nullptr,
-                                             m.eval_index.as<int>(),
-                                              m.eval_slot.as<int>(), m.eval_count.as<int>());
+                                             m.eval_index.as<int>(), m.eval_slot.as<int>(), m.eval_count.as<int>(),
+                                             clamp_to_batch ? int(std::min<long long>(e->max_batch, (long long)e->max_games * m.kcap))
+                                                            : INT_MAX,
+                                             m.err.as<int>());
     e->launches++;
     TB_CUDA(cudaGetLastError());
     return TAK_OK;
@@ -141,21 +144,19 @@ int mcts_eval_and_backup(tak_engine* e) {
     TB_CHECK(e->net, TAK_ERR_NO_NETWORK, "no network: call net_create first");
     MctsState& m = *e->mcts;
     NetState& ns = *e->net;
-    if (int r = mcts_launch_compact(e)) return r;
+    if (int r = mcts_launch_compact(e, ns.arch != 0)) return r;
     PriorSource ps{};
     ps.arch = ns.arch;
     ps.psz = ns.policy_out;
     if (ns.arch != 0) {
-        int count = 0;
-        if (int r = mcts_read_eval_count(e, &count)) return r;
-        if (count > 0) {
-            // leaves are evaluated in chunks of max_batch; each chunk is backed up before the next one only when a
-            // single chunk suffices -- otherwise all chunks are evaluated first (queue order is preserved either way
-            // because the backup kernel walks each game's queue in order and outputs are indexed by compact slot).
-            TB_CHECK(count <= e->max_batch, TAK_ERR_CAPACITY, "%d queued leaves exceed max_batch %d", count,
-                     e->max_batch);
-            if (int r = net_forward(e, m.leaf_states.as<uint8_t>(), m.eval_index.as<int>(), count, nullptr)) return r;
-        }
+        // The number of queued leaves stays on the device: the forward pass is launched for the largest batch the queues
+        // can hold (capped by max_batch; the compaction kernel flags an overflow, reported as TAK_ERR_CAPACITY by the
+        // next mcts_check_errors) and every kernel of it reads the live count -- no stream synchronisation between
+        // queueing leaves and backing them up (Player::rollout, mcts_devirtualize).
+        const int bound = int(std::min<long long>(e->max_batch, (long long)e->max_games * m.kcap));
+        if (int r = net_forward(e, m.leaf_states.as<uint8_t>(), m.eval_index.as<int>(), bound, nullptr, 0,
+                                m.eval_count.as<int>()))
+            return r;
         ps.logits = ns.logits.as<float>();
         ps.stats = ns.stats.as<float2>();
         ps.values = ns.values.as<float>();
@@ -258,7 +259,8 @@ int mcts_check_errors(tak_engine* e) {
         return TAK_ERR_CAPACITY;
     }
     if (flags & MERR_PENDING_FULL) {
-        set_error("more than %d leaves queued for one game", m.kcap);
+        set_error("more leaves queued than one game's queue (%d) or one network batch (max_batch %d) holds", m.kcap,
+                  e->max_batch);
         return TAK_ERR_CAPACITY;
     }
     if (flags & MERR_DEPTH) {

@@ -21,7 +21,9 @@ struct MctsState {
 int mcts_ensure(tak_engine* e, int k);
 // d_ids == nullptr => games [0, n)
 int mcts_launch_rollout(tak_engine* e, const int* d_ids, int n, int k, const uint8_t* d_enable = nullptr);
-int mcts_launch_compact(tak_engine* e);                 // fills eval_index / eval_slot / eval_count (device)
+// fills eval_index / eval_slot / eval_count (device); clamp_to_batch: the count is capped at one network batch and an
+// overflow raises the device error flag (the evaluation path reads the count on the device)
+int mcts_launch_compact(tak_engine* e, bool clamp_to_batch = false);
 int mcts_read_eval_count(tak_engine* e, int* out);      // syncs the stream
 int mcts_launch_backup(tak_engine* e, const PriorSource& ps);
 int mcts_eval_and_backup(tak_engine* e);                // compact -> network -> backup (syncs once for the count)

@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(GAME_THREADS)
 // flat pending slot (gid*kcap + j) <-> compact evaluation index; single block
 static __global__ void __launch_bounds__(1024)
     k_mcts_compact(const int* pend_cnt, int n_games, int kcap, const int* limits, int* eval_index, int* eval_slot,
-                   int* eval_count) {
+                   int* eval_count, int max_eval, int* err) {
     __shared__ int s_warp[32];
     __shared__ int s_carry;
     if (threadIdx.x == 0) s_carry = 0;
@@ -251,14 +251,19 @@ static __global__ void __launch_bounds__(1024)
         const int warp_off = (threadIdx.x >> 5) ? s_warp[(threadIdx.x >> 5) - 1] : 0;
         const int excl = s_carry + warp_off + inc - c;
         for (int j = 0; j < c; ++j) {
-            eval_index[excl + j] = g * kcap + j;
             eval_slot[g * kcap + j] = excl + j;
+            if (excl + j < max_eval) eval_index[excl + j] = g * kcap + j;   // beyond one network batch: flagged below
         }
         __syncthreads();
         if (threadIdx.x == blockDim.x - 1) s_carry = excl + c;
         __syncthreads();
     }
-    if (threadIdx.x == 0) *eval_count = s_carry;
+    if (threadIdx.x == 0) {
+        // the evaluation is launched for at most max_eval leaves and reads this count on the device; more queued leaves
+        // than one network batch holds is an error the caller reports (TAK_ERR_CAPACITY)
+        if (s_carry > max_eval) atomicOr(err, MERR_PENDING_FULL);
+        *eval_count = min(s_carry, max_eval);
+    }
 }
 
 

@@ -225,19 +225,21 @@ static int launch_tower(tak_engine* e, int boards, const int* d_count) {
 
 template <int N>
 static int forward_t(tak_engine* e, const uint8_t* d_states, const int* d_index, int boards, float* d_policy_out,
-                     int raw_logits) {
+                     int raw_logits, const int* d_count) {
     NetState& ns = *e->net;
     if (int r = net_ensure_capacity(e, boards)) return r;
     const int S = ns.cap_S;
     const int wblocks = (boards + 7) / 8;
-    k_encode<N><<<wblocks, 256, 0, e->stream>>>(d_states, d_index, boards, ns.act_in.as<__nv_bfloat16>(), S);
+    // d_count: the number of boards lives on the device (the search counts its queued leaves there) and `boards` only
+    // sizes the launches -- no host round trip between queueing leaves and evaluating them
+    k_encode<N><<<wblocks, 256, 0, e->stream>>>(d_states, d_index, boards, ns.act_in.as<__nv_bfloat16>(), S, d_count);
     e->launches++;
     TB_CUDA(cudaGetLastError());
-    if (int r = launch_tower<N>(e, boards, nullptr)) return r;
+    if (int r = launch_tower<N>(e, boards, d_count)) return r;
     // heads
     if (ns.arch == 6) {
         k_policy_stats_conv<N, INFER_PF><<<wblocks, 256, 0, e->stream>>>(ns.partials.as<float2>(), S, ns.policy_groups * 4, boards,
-                                                               ns.stats.as<float2>());
+                                                                         ns.stats.as<float2>(), d_count);
         if (d_policy_out) {
             e->launches++;
             k_policy_full_conv<N><<<boards, 256, 0, e->stream>>>(ns.logits.as<float>(), S, ns.policy_ch,
@@ -245,12 +247,12 @@ static int forward_t(tak_engine* e, const uint8_t* d_states, const int* d_index,
         }
     } else {
         k_policy_stats_dense<<<boards, 256, 0, e->stream>>>(ns.logits.as<float>(), ns.policy_out,
-                                                            ns.stats.as<float2>(), d_policy_out, raw_logits);
+                                                            ns.stats.as<float2>(), d_policy_out, raw_logits, d_count);
     }
     e->launches++;
     TB_CUDA(cudaGetLastError());
     k_value<N><<<wblocks, 256, 0, e->stream>>>(ns.trunk_out, S, ns.value_w.as<float>(), ns.value_bias, boards,
-                                               ns.values.as<float>());
+                                               ns.values.as<float>(), d_count);
     e->launches++;
     TB_CUDA(cudaGetLastError());
     return TAK_OK;
@@ -298,15 +300,15 @@ int net_fast_views(tak_engine* e, int max_boards, FastEval& fe, PriorSource& ps)
 }
 
 int net_forward(tak_engine* e, const uint8_t* d_states, const int* d_index, int boards, float* d_policy_out,
-                int raw_logits) {
+                int raw_logits, const int* d_count) {
     TB_CHECK(e->net, TAK_ERR_NO_NETWORK, "no network: call net_create first");
     NetState& ns = *e->net;
     TB_CHECK(ns.arch != 0, TAK_ERR_BAD_ARG, "internal: forward on the DummyNet");
     TB_CHECK(ns.loaded, TAK_ERR_NO_NETWORK, "network weights not loaded");
     if (boards == 0) return TAK_OK;
     int r = TAK_ERR_BAD_ARG;
-    if (e->n == 5) r = forward_t<5>(e, d_states, d_index, boards, d_policy_out, raw_logits);
-    if (e->n == 6) r = forward_t<6>(e, d_states, d_index, boards, d_policy_out, raw_logits);
+    if (e->n == 5) r = forward_t<5>(e, d_states, d_index, boards, d_policy_out, raw_logits, d_count);
+    if (e->n == 6) r = forward_t<6>(e, d_states, d_index, boards, d_policy_out, raw_logits, d_count);
     return r;
 }
 

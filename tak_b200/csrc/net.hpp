@@ -51,8 +51,9 @@ struct NetState {
 
 // Evaluate `boards` packed states (d_states[index[i]] or d_states[i] if index == nullptr) on the engine stream.
 // Leaves logits / stats / values on device; optionally writes the full softmax policy [boards][policy_out].
+// d_count != nullptr: `boards` sizes the launches, the live number of boards is read from device memory
 int net_forward(tak_engine* e, const uint8_t* d_states, const int* d_index, int boards, float* d_policy_out,
-                int raw_logits = 0);
+                int raw_logits = 0, const int* d_count = nullptr);
 int net_ensure_capacity(tak_engine* e, int boards);
 // fused search loop (mcts.cu): tower over the planes the rollout warps wrote, board count read on the device
 int net_tower_fast(tak_engine* e, int max_boards, const int* d_count);

@@ -93,9 +93,10 @@ __device__ __forceinline__ void encode_board(const WarpGame<N>& g, int w, __nv_b
 // CTA of the OTHER engine replica leaves free on an SM -- at 42 the encode of one replica waited for the other's tower)
 template <int N>
 __global__ void __launch_bounds__(256, 6)
-    k_encode(const uint8_t* states, const int* index, int n_boards, __nv_bfloat16* planes, int S) {
+    k_encode(const uint8_t* states, const int* index, int n_boards, __nv_bfloat16* planes, int S,
+             const int* n_dev = nullptr) {
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (w >= n_boards) return;
+    if (w >= n_boards || (n_dev && w >= *n_dev)) return;   // n_dev: the live count, on the device (launch sized for n_boards)
     WarpGame<N> g;
     g.load(states + size_t(index ? index[w] : w) * StateLayout<N>::S);
     encode_board<N>(g, w, planes, S);
@@ -177,9 +178,10 @@ __device__ __forceinline__ float2 warp_policy_stats(const float2* partials, int 
 // (PF: which strip layout the partials are in -- the training path uses the padded one, the default)
 template <int N, bool PF = false>
 __global__ void __launch_bounds__(256)
-    k_policy_stats_conv(const float2* partials, int S, int groups, int n_boards, float2* stats) {
+    k_policy_stats_conv(const float2* partials, int S, int groups, int n_boards, float2* stats,
+                        const int* n_dev = nullptr) {
     const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (b >= n_boards) return;
+    if (b >= n_boards || (n_dev && b >= *n_dev)) return;
     const float2 st = warp_policy_stats<N, PF>(partials, S, groups, b);
     if ((threadIdx.x & 31) == 0) stats[b] = st;
 }
@@ -201,9 +203,11 @@ __global__ void __launch_bounds__(256)
 
 // softmax statistics / full policy over a dense logits row [b][n_out]
 static __global__ void __launch_bounds__(256)
-    k_policy_stats_dense(const float* logits, int n_out, float2* stats, float* policy_out, int raw) {
+    k_policy_stats_dense(const float* logits, int n_out, float2* stats, float* policy_out, int raw,
+                         const int* n_dev = nullptr) {
     __shared__ float s_tmp[8];
     const int b = blockIdx.x;
+    if (n_dev && b >= *n_dev) return;
     const float* row = logits + size_t(b) * n_out;
     float mx = -INFINITY;
     for (int j = threadIdx.x; j < n_out; j += blockDim.x) mx = fmaxf(mx, row[j]);
@@ -243,9 +247,10 @@ __device__ __forceinline__ float warp_value(const __nv_bfloat16* act, int S, con
 }
 template <int N>
 __global__ void __launch_bounds__(256)
-    k_value(const __nv_bfloat16* act, int S, const float* wv /*[128*NSQ]*/, float bv, int n_boards, float* out) {
+    k_value(const __nv_bfloat16* act, int S, const float* wv /*[128*NSQ]*/, float bv, int n_boards, float* out,
+            const int* n_dev = nullptr) {
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (w >= n_boards) return;
+    if (w >= n_boards || (n_dev && w >= *n_dev)) return;
     const float val = warp_value<N, INFER_PF>(act, S, wv, bv, w);
     if ((threadIdx.x & 31) == 0) out[w] = val;
 }
