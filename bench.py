@@ -381,7 +381,7 @@ def late_game_rate(local, blob, steps):
     more pieces on the board, taller stacks, wider move lists, terminal rollouts that need no evaluation."""
     import tak_b200 as tb
     bpt = tb.boards_per_tile(6)
-    G = 148 * (5 if bpt == 7 else 6) * bpt
+    G = 148 * (4 if bpt == 7 else 6) * bpt
     eng = tb.Engine(6, G, device=local, nodes_per_game=1 << 18, max_batch=G)
     eng.net_create(6)
     eng.net_load_weights(blob)
@@ -605,10 +605,12 @@ def run_b200(args):
     # Games never interact, so a GPU's games are split over `replicas` independent engines (own stream, search trees and
     # network replica) driven by one host thread each.
     E = max(1, args.replicas)
-    # games per GPU and replica: a whole number of conv tiles per SM -- 148 SMs x 5 tiles x 7 boards = 5 180 on the pad-free
-    # strip (148 x 6 x 6 = 5 328 on the padded one); the node pools of two replicas then take ~130 GB of the 180 GB
+    # games per GPU and replica: a whole number of conv tiles per SM -- 148 SMs x 4 tiles x 7 boards = 4 144 on the pad-free
+    # strip (148 x 6 x 6 = 5 328 on the padded one).  Measured on one box, games per GPU -> moves/s: 4 144 -> 3 890,
+    # 6 216 -> 3 859, 8 288 -> 3 875-3 882, 10 360 -> 3 821, 12 432 -> 3 824: flat within 2 %, the smaller node pools
+    # (104 GB for 8 288 games) cost a little less HBM traffic and power
     bpt = tb.boards_per_tile(6)
-    per_replica = 148 * (5 if bpt == 7 else 6) * bpt
+    per_replica = 148 * (4 if bpt == 7 else 6) * bpt
     G = args.games if args.games else per_replica * E
     Gr = G // E
     G = Gr * E
@@ -898,7 +900,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--games", type=int, default=0,
-                    help="concurrent games per GPU (default per replica: 148 SMs x 5 conv tiles x 7 boards = 5180)")
+                    help="concurrent games per GPU (default per replica: 148 SMs x 4 conv tiles x 7 boards = 4144)")
     ap.add_argument("--replicas", type=int, default=2, help="independent engine replicas per GPU (host thread each)")
     ap.add_argument("--rollouts", type=int, default=800)
     ap.add_argument("--nodes-per-game", type=int, default=1 << 18)
