@@ -148,6 +148,14 @@ struct ConvParams {
     int bw;                     // N + 1 (padded strip) or N (pad-free strip)
     int bpt;                    // boards per tile
     int pitch;                  // bpt * bw
+    // Training build, one-layer CONV_LINEAR launches that are a dgrad (train.cu): when bnb_y is set, the conv's output is
+    // the gradient w.r.t. the post-ReLU output of the BatchNorm layer below, and the epilogue fuses the first pass of
+    // that layer's BatchNorm backward: out = g' = (conv + bias + res) * (bnb_z > 0), and stats[c] += sum g',
+    // stats[128 + c] += sum g' * xhat with xhat = (bnb_y - mean) * rstd  (what k_bn_bwd_reduce computes from HBM).
+    const __nv_bfloat16* bnb_z;  // the layer's post-ReLU output (the ReLU mask)
+    const __nv_bfloat16* bnb_y;  // the layer's raw conv output (pre-BN)
+    const float* bnb_mean;       // [128] batch mean / 1/sqrt(var + eps) saved by k_bn_apply
+    const float* bnb_rstd;
 };
 
 // barrier slots
@@ -441,9 +449,14 @@ static __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc3_kernel(const
                             valid_mask |= 1u << idx;
                     // bias of this layer -> shared (double buffered by accumulator stage; the named barrier keeps the
                     // 256 epilogue threads within one work item of each other)
-                    float* bias_s = s_bias + as * 128;
-                    if (etid < 128) bias_s[etid] = ld.bias[etid];
-                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    // (training build: a launch is one layer, so the bias is staged once per group of tiles and the
+                    // per-tile rendezvous of the eight warps is gone)
+                    float* bias_s = s_bias + (TRAIN ? 0 : as * 128);
+                    if (!TRAIN || jj == 0) {
+                        if (TRAIN) asm volatile("bar.sync 1, 256;" ::: "memory");   // nobody still reads the previous bias
+                        if (etid < 128) bias_s[etid] = ld.bias[etid];
+                        asm volatile("bar.sync 1, 256;" ::: "memory");
+                    }
                     // the residual does not depend on the MMAs: the first chunk's 4 x 16 B are fetched before waiting for
                     // the accumulator, the next chunk's while the current one is processed (registers: a 352-thread CTA
                     // is allocated as 12 warps, i.e. 168 registers per thread at most).
@@ -460,14 +473,31 @@ static __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc3_kernel(const
                                     ld.res + (static_cast<size_t>(chunk) * p.S + slot0 + 32 * cc + 8 * i) * 8);
                         }
                     };
-                    uint4 res[2][4];
+                    uint4 res[TRAIN ? 1 : 2][4];   // training build: single-buffered (registers), fetched one chunk ahead
                     const bool has_res = mode == CONV_RES_RELU || (TRAIN && mode == CONV_LINEAR && ld.res != nullptr);
                     const bool relu = !(TRAIN && mode == CONV_LINEAR);
                     const bool want_stats = TRAIN && mode == CONV_LINEAR && ld.stats != nullptr;
+                    // fused BatchNorm-backward reduction (see ConvParams::bnb_y): the mask and the raw conv output of the
+                    // layer below are fetched one 32-slot chunk ahead (single-buffered: issued when the previous chunk's
+                    // values have been consumed)
+                    const bool bnb = TRAIN && mode == CONV_LINEAR && p.bnb_y != nullptr;
+                    uint4 bz[4], by[4];
+                    auto load_zy = [&](int cc) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            bz[i] = by[i] = make_uint4(0, 0, 0, 0);
+                            if ((valid_mask >> (cc * 4 + i)) & 1) {
+                                const size_t off = (static_cast<size_t>(chunk) * p.S + slot0 + 32 * cc + 8 * i) * 8;
+                                bz[i] = __ldg(reinterpret_cast<const uint4*>(p.bnb_z + off));
+                                by[i] = __ldg(reinterpret_cast<const uint4*>(p.bnb_y + off));
+                            }
+                        }
+                    };
                     float st_sum[8], st_sq[8];
                     if (TRAIN) {
 #pragma unroll
                         for (int b = 0; b < 8; ++b) st_sum[b] = st_sq[b] = 0.f;
+                        if (bnb) load_zy(0);
                     }
                     if (has_res) load_res(0, res[0]);
                     float bias8[8];
@@ -485,10 +515,12 @@ static __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc3_kernel(const
 #endif
                     const uint32_t taddr = tmem_base + as * 256 + 128 * h + (static_cast<uint32_t>(q * 32) << 16);
                     uint32_t x[32];
-#pragma unroll
+                    // training build: the chunk loop stays rolled (single-buffered operands, no register array indexed by
+                    // cc) -- a quarter of the epilogue's code, which a one-layer launch runs through only 4-5 times
+#pragma unroll(TRAIN ? 1 : 4)
                     for (int cc = 0; cc < 4; ++cc) {
                         tmem_ld32(taddr + cc * 32, x);   // 8 epilogue warps hide each other's TMEM latency
-                        if (has_res && cc < 3) load_res(cc + 1, res[(cc + 1) & 1]);
+                        if (!TRAIN && has_res && cc < 3) load_res(cc + 1, res[TRAIN ? 0 : ((cc + 1) & 1)]);
                         tmem_ld_wait();
                         if (cc == 3) {
                             // the accumulator is in registers now: hand it back to the MMA issuer BEFORE the stores of
@@ -498,7 +530,7 @@ static __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc3_kernel(const
                             __syncwarp();
                             if (lane == 0) mbar_arrive(BAR(C3B_ACC_EMPTY + as));
                         }
-                        if (mode == CONV_LOGITS_F32) {
+                        if (!TRAIN && mode == CONV_LOGITS_F32) {
                             // logits straight from the un-transposed registers: one channel, 32 consecutive slots
                             const int ch = 32 * q + lane;
                             const bool ch_ok = ch < ld.out_ch_valid;
@@ -529,7 +561,7 @@ static __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc3_kernel(const
                         transpose8_stage<2>(x, j);
                         transpose8_stage<1>(x, j);
 #endif
-                        if (mode == CONV_LOGITS_F32) {
+                        if (!TRAIN && mode == CONV_LOGITS_F32) {
                             // per-slot softmax partial over this warp's 32 channels: 8 in-thread, then the 4 lane groups
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {
@@ -558,12 +590,23 @@ static __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc3_kernel(const
 #pragma unroll
                                 for (int b = 0; b < 8; ++b) v[b] = __uint_as_float(x[8 * i + b]) + bias8[b];
                                 if (has_res) {
-                                    const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&res[cc & 1][i]);
+                                    const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&res[TRAIN ? 0 : (cc & 1)][i]);
 #pragma unroll
                                     for (int b = 0; b < 4; ++b) {
                                         float2 f = __bfloat1622float2(rb[b]);
                                         v[2 * b] += f.x;
                                         v[2 * b + 1] += f.y;
+                                    }
+                                }
+                                if (TRAIN) {
+                                    if (bnb) {   // ReLU mask of the layer below: the gradient passes where its output was > 0
+                                        const __nv_bfloat162* zb = reinterpret_cast<const __nv_bfloat162*>(&bz[i]);
+#pragma unroll
+                                        for (int b = 0; b < 4; ++b) {
+                                            const float2 zf = __bfloat1622float2(zb[b]);
+                                            if (!(zf.x > 0.f)) v[2 * b] = 0.f;
+                                            if (!(zf.y > 0.f)) v[2 * b + 1] = 0.f;
+                                        }
                                     }
                                 }
                                 uint4 ov;
@@ -575,11 +618,27 @@ static __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc3_kernel(const
                                     ob[b] = __floats2bfloat162_rn(lo, hi);
                                 }
                                 if (TRAIN) {
-                                    if (want_stats && valid) {
+                                    if (bnb) {
+                                        // sums over the bf16 values the BatchNorm-backward apply pass will read back;
+                                        // the second sum is sum g' * y here: centred and scaled (xhat = (y - mean) * rstd)
+                                        // in double at the CTA's flush
+                                        if (valid) {
+                                            const __nv_bfloat162* yb = reinterpret_cast<const __nv_bfloat162*>(&by[i]);
+#pragma unroll
+                                            for (int b = 0; b < 4; ++b) {
+                                                const float2 gf = __bfloat1622float2(ob[b]);
+                                                const float2 yf = __bfloat1622float2(yb[b]);
+                                                st_sum[2 * b] += gf.x;
+                                                st_sum[2 * b + 1] += gf.y;
+                                                st_sq[2 * b] = __fmaf_rn(gf.x, yf.x, st_sq[2 * b]);   // (the library is built -fmad=false)
+                                                st_sq[2 * b + 1] = __fmaf_rn(gf.y, yf.y, st_sq[2 * b + 1]);
+                                            }
+                                        }
+                                    } else if (want_stats && valid) {
 #pragma unroll
                                         for (int b = 0; b < 8; ++b) {
                                             st_sum[b] += v[b];
-                                            st_sq[b] += v[b] * v[b];
+                                            st_sq[b] = __fmaf_rn(v[b], v[b], st_sq[b]);
                                         }
                                     }
                                 }
@@ -588,10 +647,14 @@ static __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc3_kernel(const
 #endif
                                 *reinterpret_cast<uint4*>(ld.out + (static_cast<size_t>(chunk) * p.S + slot0 + 32 * cc + 8 * i) * 8) = ov;
                             }
+                            if (TRAIN) {
+                                if (has_res && cc < 3) load_res(cc + 1, res[0]);
+                                if (bnb && cc < 3) load_zy(cc + 1);
+                            }
                         }
                     }
                     if (TRAIN) {
-                        if (want_stats) {   // the 8 lanes of a channel chunk hold different slots of the same 8 channels
+                        if (want_stats || bnb) {   // the 8 lanes of a channel chunk hold different slots of the same 8 channels
 #pragma unroll
                             for (int b = 0; b < 8; ++b) {
 #pragma unroll
@@ -704,7 +767,7 @@ static __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc3_kernel(const
         }
     }
 
-    else if (warp == 10) {
+    else if (warp == 10 && !TRAIN) {
         // ===================== janitor =====================
         // Dead activations: once the epilogue of a work item is done (READY), the tile's input (fully consumed by the
         // MMAs) and / or residual are never read again before they are rewritten, so their L2 lines are dropped instead
@@ -741,7 +804,14 @@ static __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc3_kernel(const
         // one flush of this CTA's batch statistics per launch (a training launch is ONE layer: the next layer's
         // BatchNorm needs the statistics of the whole batch first)
         double* gs = p.layers[p.n_layers - 1].stats;
-        if (gs != nullptr && threadIdx.x < 256) atomicAdd(&gs[threadIdx.x], double(s_stats[threadIdx.x]));
+        if (gs != nullptr && threadIdx.x < 256) {
+            double v = double(s_stats[threadIdx.x]);
+            if (p.bnb_y != nullptr && threadIdx.x >= 128) {   // sum g' * xhat = rstd * (sum g' * y - mean * sum g')
+                const int c = threadIdx.x - 128;
+                v = double(p.bnb_rstd[c]) * (v - double(p.bnb_mean[c]) * double(s_stats[c]));
+            }
+            atomicAdd(&gs[threadIdx.x], v);
+        }
     }
 }
 

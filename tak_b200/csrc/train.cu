@@ -8,6 +8,7 @@
 //   BN / ReLU / heads / Adam : train_kernels.cuh (HBM-bound passes)
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "conv_tc3.cuh"
 #include "fc_tc.cuh"
@@ -189,13 +190,24 @@ static int train_chunk_t(tak_engine* e, TrainState& t, const float* d_in, const 
     const double count = double(B) * N * N;
     const int ew_blocks = int((size_t(16) * S + 255) / 256);
     using bf = __nv_bfloat16;
-    auto conv_lin = [&](const bf* in, const bf* w, const float* bias, const bf* res, bf* out, double* stats, int slabs) -> int {
+    // bnb_layer >= 0 (dgrad launches): `out` is the gradient w.r.t. the post-ReLU output of trunk layer bnb_layer; the
+    // epilogue applies that layer's ReLU mask and accumulates its BatchNorm-backward sums (ConvParams::bnb_y), so the
+    // separate reduction pass over g, z and y is gone and the apply pass reads the masked gradient only
+    auto conv_lin = [&](const bf* in, const bf* w, const float* bias, const bf* res, bf* out, double* stats, int slabs,
+                        int bnb_layer = -1) -> int {
         ConvParams p{};
         conv_params_set_layout(p, N);
         p.S = S; p.tile_begin = 0; p.tile_end = tiles; p.n_boards = B; p.n_layers = 1;
         ConvLayerDesc& d = p.layers[0];
         d.in = in; d.res = res; d.out = out; d.w = w; d.bias = bias; d.slabs = slabs; d.mode = CONV_LINEAR;
         d.out_ch_valid = 128; d.stats = stats;
+        if (bnb_layer >= 0) {
+            p.bnb_z = t.layers[bnb_layer].z.as<bf>();
+            p.bnb_y = t.layers[bnb_layer].y.as<bf>();
+            p.bnb_mean = t.bn_mean.as<float>() + bnb_layer * 128;
+            p.bnb_rstd = t.bn_rstd.as<float>() + bnb_layer * 128;
+            d.stats = t.bwd_sums.as<double>() + size_t(bnb_layer) * 256;
+        }
         TB_CUDA(conv3x3_tc3_launch<true>(p, e->num_sms, e->stream));
         t.launches++;
         return TAK_OK;
@@ -221,6 +233,9 @@ static int train_chunk_t(tak_engine* e, TrainState& t, const float* d_in, const 
     k_nchw_to_planes<N><<<ew_blocks, 256, 0, e->stream>>>(d_in, B, t.c_in, t.x0.as<bf>(), S);
     t.launches++;
     TB_CUDA(cudaMemsetAsync(t.bn_sums.p, 0, size_t(nl) * 256 * 8, e->stream));
+    TB_CUDA(cudaMemsetAsync(t.bwd_sums.p, 0, size_t(nl) * 256 * 8, e->stream));
+    // TAK_TRAIN_BNB=0: the two-pass BatchNorm backward everywhere (A/B and fallback)
+    static const bool fuse_bnb = [] { const char* v = getenv("TAK_TRAIN_BNB"); return !v || atoi(v) != 0; }();
     for (int l = 0; l < nl; ++l) {
         TrainLayer& L = t.layers[l];
         const bf* in = l == 0 ? t.x0.as<bf>() : t.layers[l - 1].z.as<bf>();
@@ -242,6 +257,7 @@ static int train_chunk_t(tak_engine* e, TrainState& t, const float* d_in, const 
     bf* g = t.g[0].as<bf>();
     bf* g_alt = t.g[1].as<bf>();
     const int wblocks = (B + 7) / 8;
+    bool top_premasked = false;   // the top gradient arrives masked, with the top layer's sums (Net6, fused)
     if constexpr (N == 5) {
         // ---- Net5 heads: FC policy (net5.rs:106-108) + value; loss; head gradients -- three GEMMs on fc_tc_kernel ----
         const int J = t.policy_out, K = 128 * N * N, P = (J + 127) / 128, b_pad = t.fc_bpad, k_pad = t.fc_kpad;
@@ -332,45 +348,61 @@ static int train_chunk_t(tak_engine* e, TrainState& t, const float* d_in, const 
     if (int r = wgrad(dl0, trunk, 128, t.pw_off, 0, 128, 0)) return r;
     if (int r = wgrad(dl1, trunk, 128, t.pw_off, 128, t.policy_ch - 128, 1)) return r;
     if (int r = conv_lin(dl0, t.pol_w_dgrad[0].as<bf>(), t.zero_bias.as<float>(), g, g_alt, nullptr, C3_MAX_SLABS)) return r;
-    if (int r = conv_lin(dl1, t.pol_w_dgrad[1].as<bf>(), t.zero_bias.as<float>(), g_alt, g, nullptr, C3_MAX_SLABS)) return r;
+    if (int r = conv_lin(dl1, t.pol_w_dgrad[1].as<bf>(), t.zero_bias.as<float>(), g_alt, g, nullptr, C3_MAX_SLABS,
+                         fuse_bnb ? nl - 1 : -1))
+        return r;
+    top_premasked = true;
     }   // N == 6 heads
     // ------------------------------------------------ trunk backward --------------------------------------------------
-    // bn_backward(l, upstream gradient w.r.t. the layer's post-ReLU output) -> dy (gradient w.r.t. the raw conv output);
-    // optionally the ReLU-masked upstream gradient (the residual connection's share)
-    auto bn_backward = [&](int l, const bf* gin, bf* dy_out, bf* gmasked) -> int {
+    // BatchNorm backward of layer l.  `gm` is the gradient w.r.t. the layer's post-ReLU output ALREADY masked by that
+    // ReLU, and bwd_sums[l] holds sum g' / sum g' * xhat: both come out of the epilogue of the dgrad launch that produced
+    // gm (conv_lin(..., bnb_layer = l)).  One pass is left: dy = gamma * rstd * (g' - c1 - xhat * c2), reading g' and y.
+    // premasked == false (Net5's top layer, whose upstream gradient comes from the FC head's kernels): the two-pass
+    // route, k_bn_bwd_reduce + masking apply, with the masked gradient written to `gmasked`.
+    auto bn_backward = [&](int l, const bf* gin, bf* dy_out, bool premasked, bf* gmasked) -> int {
         TrainLayer& L = t.layers[l];
         const float* mean = t.bn_mean.as<float>() + l * 128;
         const float* rstd = t.bn_rstd.as<float>() + l * 128;
-        TB_CUDA(cudaMemsetAsync(t.bwd_sums.p, 0, 256 * 8, e->stream));
-        k_bn_bwd_reduce<<<dim3(BNR_SPLIT, 16), 256, 0, e->stream>>>(gin, L.z.as<bf>(), L.y.as<bf>(), mean, rstd, S,
-                                                                    t.bwd_sums.as<double>());
-        k_bn_bwd_apply<N><<<ew_grid(S), 256, 0, e->stream>>>(gin, L.z.as<bf>(), L.y.as<bf>(), mean, rstd,
-                                                            master + L.gamma_off, t.bwd_sums.as<double>(), count,
-                                                            grad + L.gamma_off, grad + L.beta_off, B, S, dy_out, gmasked);
-        t.launches += 2;
+        double* sums = t.bwd_sums.as<double>() + size_t(l) * 256;
+        const bf* zmask = premasked ? nullptr : L.z.as<bf>();
+        if (!premasked) {
+            k_bn_bwd_reduce<<<dim3(BNR_SPLIT, 16), 256, 0, e->stream>>>(gin, zmask, L.y.as<bf>(), mean, rstd, S, sums);
+            t.launches++;
+        }
+        k_bn_bwd_apply<N><<<ew_grid(S), 256, 0, e->stream>>>(gin, zmask, L.y.as<bf>(), mean, rstd, master + L.gamma_off,
+                                                            sums, count, grad + L.gamma_off, grad + L.beta_off, B, S,
+                                                            dy_out, premasked ? nullptr : gmasked);
+        t.launches++;
         return TAK_OK;
     };
+    const bool fuse = fuse_bnb;
+    auto bnb = [&](int l) { return fuse ? l : -1; };
+    bool premasked = fuse && top_premasked;
     for (int blk = t.blocks - 1; blk >= 0; --blk) {
         const int l1 = 1 + 2 * blk, l2 = 2 + 2 * blk;
         const bf* xin = t.layers[l1 - 1].z.as<bf>();
-        // out = relu(bn2(conv2(t)) + x): g2 = g * (out > 0) goes to both branches
+        // out = relu(bn2(conv2(t)) + x): the masked gradient g' = g * (out > 0) goes to both branches
         if (int r = reuse_dy(0)) return r;
-        if (int r = bn_backward(l2, g, t.dy.as<bf>(), t.g2.as<bf>())) return r;
+        if (int r = bn_backward(l2, g, t.dy.as<bf>(), premasked, t.g2.as<bf>())) return r;
+        const bf* gres = premasked ? g : t.g2.as<bf>();
         if (int r = wgrad(t.dy.as<bf>(), t.layers[l1].z.as<bf>(), 128, t.layers[l2].w_off, 0, 128, 0)) return r;
+        // dt = gradient w.r.t. conv1's post-ReLU output (fused: masked, with bn1's sums)
         if (int r = conv_lin(t.dy.as<bf>(), t.layers[l2].w_dgrad.as<bf>(), t.zero_bias.as<float>(), nullptr, t.dt.as<bf>(),
-                             nullptr, C3_MAX_SLABS))
+                             nullptr, C3_MAX_SLABS, bnb(l1)))
             return r;
         if (int r = reuse_dy(1)) return r;
-        if (int r = bn_backward(l1, t.dt.as<bf>(), t.dy2.as<bf>(), nullptr)) return r;
+        if (int r = bn_backward(l1, t.dt.as<bf>(), t.dy2.as<bf>(), fuse, nullptr)) return r;
         if (int r = wgrad(t.dy2.as<bf>(), xin, 128, t.layers[l1].w_off, 0, 128, 1)) return r;
-        // gradient w.r.t. the block input = dgrad(conv1) + the residual share
-        if (int r = conv_lin(t.dy2.as<bf>(), t.layers[l1].w_dgrad.as<bf>(), t.zero_bias.as<float>(), t.g2.as<bf>(), g_alt,
-                             nullptr, C3_MAX_SLABS))
+        // gradient w.r.t. the block input = dgrad(conv1) + the residual share (fused: masked by the ReLU of the layer
+        // that produced the block input -- the previous block's conv2, or the initial conv -- with that layer's sums)
+        if (int r = conv_lin(t.dy2.as<bf>(), t.layers[l1].w_dgrad.as<bf>(), t.zero_bias.as<float>(), gres, g_alt, nullptr,
+                             C3_MAX_SLABS, bnb(l1 - 1)))
             return r;
         std::swap(g, g_alt);
+        premasked = fuse;
     }
     if (int r = reuse_dy(0)) return r;
-    if (int r = bn_backward(0, g, t.dy.as<bf>(), nullptr)) return r;
+    if (int r = bn_backward(0, g, t.dy.as<bf>(), premasked, nullptr)) return r;
     if (int r = wgrad(t.dy.as<bf>(), t.x0.as<bf>(), t.c_in, t.layers[0].w_off, 0, 128, 0)) return r;
     // join: the chunk is complete on the main stream only when the last wgrads are
     TB_CUDA(cudaEventRecord(t.ev_join, t.wstream));
@@ -461,7 +493,7 @@ int32_t net_train_begin(tak_engine_t* e, int32_t max_boards) {
     const size_t nl = t->layers.size();
     TB_CUDA(t->bn_sums.ensure(nl * 256 * 8));
     for (DevBuf* b : {&t->bn_mean, &t->bn_rstd}) TB_CUDA(b->ensure(nl * 128 * 4));
-    TB_CUDA(t->bwd_sums.ensure(256 * 8));
+    TB_CUDA(t->bwd_sums.ensure(nl * 256 * 8));
     TB_CUDA(t->loss.ensure(16));
     TB_CUDA(t->wg_scratch.ensure(wgrad_scratch_elems(e->num_sms) * 4));
     TB_CUDA(cudaEventCreate(&t->ev0));

@@ -36,3 +36,4 @@ eng.train_step()
 flop = 3 * (368_197_632 if arch == 6 else 132_198_400) * boards
 print({"arch": arch, "boards": boards, "ms_per_chunk": float(np.mean(ms)), "positions_per_s": boards / (np.mean(ms) * 1e-3),
        "tflops_fwd_bwd": flop / (np.mean(ms) * 1e-3) / 1e12, "loss": loss})
+eng.train_end()
