@@ -295,7 +295,11 @@ static __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc3_kernel(const
                             const uint32_t dst = smem_u32(stage_buf + sb * STAGE_BYTES) + C3_HALO * 16;
                             if (PF) {
                                 mbar_expect_tx(BAR(C3B_AFULL + sb), PF_COPIES_LOADED * 2 * C3_TILE_M * 16);
+#if defined(CONV_EXP) && (CONV_EXP & 4096)
+                                mbar_expect_tx(BAR(C3B_FULL + sb), cnt < STAGES ? C3_W_SLAB_BYTES : 0);
+#else
                                 mbar_expect_tx(BAR(C3B_FULL + sb), C3_W_SLAB_BYTES);
+#endif
                                 if (k > 0) {
 #pragma unroll
                                     for (int c = 0; c < PF_COPIES_LOADED; ++c) {
@@ -306,9 +310,18 @@ static __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc3_kernel(const
                                     }
                                 }
                             } else {
+#if defined(CONV_EXP) && (CONV_EXP & 4096)
+                                mbar_expect_tx(BAR(C3B_FULL + sb), 2 * C3_TILE_M * 16 + (cnt < STAGES ? C3_W_SLAB_BYTES : 0));
+#else
                                 mbar_expect_tx(BAR(C3B_FULL + sb), 2 * C3_TILE_M * 16 + C3_W_SLAB_BYTES);
+#endif
                             }
                             // weights never depend on anything computed here: at k == 0 they go out first
+#if defined(CONV_EXP) && (CONV_EXP & 4096)
+                            // experiment (wrong results, timing only): weight slabs are fetched for the first ring
+                            // revolution only -- the ceiling of what sharing weight traffic between CTAs could buy
+                            if (cnt < STAGES)
+#endif
                             bulk_g2s(smem_u32(stage_buf + sb * STAGE_BYTES + W_OFF),
                                      reinterpret_cast<const uint8_t*>(ld.w) + static_cast<size_t>(k) * C3_W_SLAB_BYTES,
                                      C3_W_SLAB_BYTES, BAR(C3B_FULL + sb));
