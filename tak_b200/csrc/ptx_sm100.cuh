@@ -63,6 +63,17 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
                  : "memory");
 }
 
+// Tiled TMA load (tensor map in kernel-parameter space, `const __grid_constant__ CUtensorMap`): one instruction moves a
+// 4-D box global -> shared, out-of-bounds elements arrive as zeros, completion on an mbarrier (SASS: UTMALDG)
+__device__ __forceinline__ void tma_load_4d(uint32_t dst_smem, const void* tensor_map, int c0, int c1, int c2, int c3,
+                                            uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
+            dst_smem),
+        "l"(tensor_map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+        : "memory");
+}
+
 // The 128-byte line at `p` will not be read again before it is overwritten: L2 may drop the dirty data instead of
 // writing it back to HBM (a hint; reads after it return indeterminate data).
 __device__ __forceinline__ void l2_discard_128(const void* p) {

@@ -369,9 +369,14 @@ static int train_chunk_t(tak_engine* e, TrainState& t, const float* d_in, const 
             k_bn_bwd_reduce<<<dim3(BNR_SPLIT, 16), 256, 0, e->stream>>>(gin, zmask, L.y.as<bf>(), mean, rstd, S, sums);
             t.launches++;
         }
-        k_bn_bwd_apply<N><<<ew_grid(S), 256, 0, e->stream>>>(gin, zmask, L.y.as<bf>(), mean, rstd, master + L.gamma_off,
-                                                            sums, count, grad + L.gamma_off, grad + L.beta_off, B, S,
-                                                            dy_out, premasked ? nullptr : gmasked);
+        if (premasked)
+            k_bn_bwd_apply<N, false><<<ew_grid(S), 256, 0, e->stream>>>(gin, nullptr, L.y.as<bf>(), mean, rstd,
+                                                                       master + L.gamma_off, sums, count, grad + L.gamma_off,
+                                                                       grad + L.beta_off, B, S, dy_out, nullptr);
+        else
+            k_bn_bwd_apply<N, true><<<ew_grid(S), 256, 0, e->stream>>>(gin, zmask, L.y.as<bf>(), mean, rstd,
+                                                                      master + L.gamma_off, sums, count, grad + L.gamma_off,
+                                                                      grad + L.beta_off, B, S, dy_out, gmasked);
         t.launches++;
         return TAK_OK;
     };

@@ -105,7 +105,7 @@ constexpr int EW_UNROLL = 4;
 inline dim3 ew_grid(int S) { return dim3(unsigned((S + 256 * EW_UNROLL - 1) / (256 * EW_UNROLL)), 16); }
 
 template <int N>
-__global__ void __launch_bounds__(256) k_bn_apply(const __nv_bfloat16* y, const __nv_bfloat16* res, const double* sums,
+__global__ void __launch_bounds__(256, 4) k_bn_apply(const __nv_bfloat16* y, const __nv_bfloat16* res, const double* sums,
                                                   double count, const float* gamma, const float* beta,
                                                   float* running_mean, float* running_var, float* mean_out,
                                                   float* rstd_out, int n_boards, int S, __nv_bfloat16* z) {
@@ -237,8 +237,11 @@ static __global__ void __launch_bounds__(256) k_bn_bwd_reduce(const __nv_bfloat1
 // flows into the residual connection, res_block.rs:21)
 // (the sums of pass 1 are finalised here: c1 = sum g' / n, c2 = sum g'*xhat / n per block, and the first block of every
 // chunk accumulates dgamma += sum g'*xhat, dbeta += sum g')
-template <int N>
-__global__ void __launch_bounds__(256) k_bn_bwd_apply(const __nv_bfloat16* g, const __nv_bfloat16* zout,
+// MASK = false: `g` is already the masked gradient g' (it came out of the dgrad epilogue with the sums, conv_tc3.cuh
+// ConvParams::bnb_y): two loads and one store per slot, half the registers -- 4 blocks per SM instead of 2 (124
+// registers with the mask operand: the pass ran at 3.6 TB/s against 4.9 for k_bn_apply on the same bytes).
+template <int N, bool MASK>
+__global__ void __launch_bounds__(256, MASK ? 2 : 4) k_bn_bwd_apply(const __nv_bfloat16* g, const __nv_bfloat16* zout,
                                                       const __nv_bfloat16* y, const float* mean, const float* rstd,
                                                       const float* gamma, const double* sums, double count,
                                                       float* grad_gamma, float* grad_beta,
@@ -258,18 +261,19 @@ __global__ void __launch_bounds__(256) k_bn_bwd_apply(const __nv_bfloat16* g, co
         }
     }
     const int s0 = blockIdx.x * (256 * EW_UNROLL) + threadIdx.x;
-    uint4 gq[EW_UNROLL], yq[EW_UNROLL], zq[EW_UNROLL];
+    uint4 gq[EW_UNROLL], yq[EW_UNROLL], zq[MASK ? EW_UNROLL : 1];
     bool ok[EW_UNROLL];
 #pragma unroll
     for (int u = 0; u < EW_UNROLL; ++u) {
         const int slot = s0 + 256 * u;
         ok[u] = slot < S && slot_valid<N>(size_t(slot), n_boards);
-        gq[u] = yq[u] = zq[u] = make_uint4(0, 0, 0, 0);
+        gq[u] = yq[u] = make_uint4(0, 0, 0, 0);
+        if (MASK) zq[u] = make_uint4(0, 0, 0, 0);
         if (ok[u]) {
             const size_t idx = size_t(chunk) * S + slot;
             gq[u] = *reinterpret_cast<const uint4*>(g + idx * 8);
             yq[u] = *reinterpret_cast<const uint4*>(y + idx * 8);
-            if (zout) zq[u] = *reinterpret_cast<const uint4*>(zout + idx * 8);
+            if (MASK) zq[u] = *reinterpret_cast<const uint4*>(zout + idx * 8);
         }
     }
     __syncthreads();
@@ -282,10 +286,10 @@ __global__ void __launch_bounds__(256) k_bn_bwd_apply(const __nv_bfloat16* g, co
             float gv[8], yv[8], zv[8];
             unpack8(gq[u], gv);
             unpack8(yq[u], yv);
-            unpack8(zq[u], zv);
+            if (MASK) unpack8(zq[u], zv);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const float gg = (!zout || zv[j] > 0.f) ? gv[j] : 0.f;
+                const float gg = (!MASK || zv[j] > 0.f) ? gv[j] : 0.f;
                 const float xhat = (yv[j] - s_m[j]) * s_r[j];
                 gm[j] = gg;
                 o[j] = s_gr[j] * (gg - c1[j] - xhat * c2[j]);
@@ -293,7 +297,7 @@ __global__ void __launch_bounds__(256) k_bn_bwd_apply(const __nv_bfloat16* g, co
         }
         const size_t idx = size_t(chunk) * S + slot;
         *reinterpret_cast<uint4*>(dy + idx * 8) = pack8(o);
-        if (gmasked) *reinterpret_cast<uint4*>(gmasked + idx * 8) = pack8(gm);
+        if (MASK && gmasked) *reinterpret_cast<uint4*>(gmasked + idx * 8) = pack8(gm);
     }
 }
 

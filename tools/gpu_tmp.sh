@@ -1,13 +1,7 @@
 set -x
 mkdir -p gpurun_out
-rm -f gpurun_out/probe_wexp.log
-cp tak_b200/lib/libtaknative.so /tmp/A.so
-for rep in 1 2; do
-for v in A E; do
-  if [ $v = A ]; then cp /tmp/A.so tak_b200/lib/libtaknative.so; else cp build/dev/libtaknative_exp.so tak_b200/lib/libtaknative.so; fi
-  echo "== variant $v (E: weight slabs fetched for the first ring revolution only; wrong results, timing only)" >> gpurun_out/probe_wexp.log
-  timeout 200 python tools/probe_selfplay.py 6 4144 800 3 2>&1 | cut -c1-200 >> gpurun_out/probe_wexp.log
-done
-done
-cp /tmp/A.so tak_b200/lib/libtaknative.so
-cat gpurun_out/probe_wexp.log
+timeout 200 python tools/probe_train.py 4000 10 2>&1 | cut -c1-110
+timeout 200 python tools/probe_train.py 4000 10 5 2>&1 | cut -c1-110
+timeout 600 python -m pytest tests/test_train_gpu.py -x -q 2>&1 | tail -3
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -s 330 -c 420 --csv --log-file gpurun_out/launches_train.csv python tools/probe_train.py 4000 2 > /dev/null 2>&1
+python tools/launch_summary.py gpurun_out/launches_train.csv > gpurun_out/launch_summary_train.txt 2>&1; head -8 gpurun_out/launch_summary_train.txt
