@@ -30,7 +30,9 @@
 // (First version: a CTA per 32 input channels x 9 taps, N = 32 instructions: 104 us per layer at 4000 positions -- an
 // M=128,N=32,K=16 instruction costs ~73 cycles, the 4 KiB A-operand fetch, for 32 cycles of math.)
 //
-// Warp roles (192 threads): warp 0 producer (cp.async.bulk), warp 1 TMEM alloc + MMA issuer, warps 2-5 epilogue.
+// Warp roles (320 threads): warp 0 producer (TMA), warp 1 TMEM alloc + MMA issuer, warps 2-9 epilogue (two per TMEM lane
+// quarter, alternating 32-column blocks: the partial is 12 dependent tcgen05.ld + store rounds per quarter, exposed at
+// the end of every launch).
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -47,7 +49,7 @@
 
 namespace tb {
 
-constexpr int WG_THREADS = 192;
+constexpr int WG_THREADS = 320;
 constexpr int WG_PARTS = 2;                                 // parts of a tile (one pipeline stage holds one part)
 constexpr int WG_STAGES = 3;                                // ring depth
 constexpr int WG_HALF = C3_TILE_M / WG_PARTS;               // 128 slots per pipeline stage
@@ -151,14 +153,17 @@ wgrad_tc_kernel(const __grid_constant__ WgradParams p, const __grid_constant__ C
     } else {
         // epilogue: warp w reads TMEM lane quarter w % 4 (a warp may only touch lanes 32*(warpid % 4) ..)
         const int lq = warp & 3;
+        const int half = (warp - 2) >> 2;
         const int co = 32 * lq + lane;
         float* dst = p.scratch + (size_t(blockIdx.x) * 128 + co) * WG_COLS;
         if (n_my > 0) {
             mbar_wait(ACC, 0);
             tc_fence_after();
         }
+        int blk = 0;
         for (int kx = 0; kx < 3; ++kx)
             for (int c0 = 0; c0 < N; c0 += 32) {
+                if ((blk++ & 1) != half) continue;
                 uint32_t v[32];
                 if (n_my > 0) {
                     tmem_ld32(tmem_base + kx * 128 + c0 + (uint32_t(lq * 32) << 16), v);

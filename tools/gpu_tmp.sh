@@ -1,7 +1,13 @@
 set -x
 mkdir -p gpurun_out
-timeout 200 python tools/probe_train.py 4000 10 2>&1 | cut -c1-110
+timeout 120 ./build/wgrad_selftest 667 128 42 2>&1 | tail -3
+timeout 120 ./build/wgrad_selftest 37 96 48 2>&1 | tail -3
+for rep in 1 2; do
+for pf in 1 0; do
+echo "== TAK_TRAIN_PREFETCH=$pf"
+TAK_TRAIN_PREFETCH=$pf timeout 200 python tools/probe_train.py 4000 10 2>&1 | cut -c1-110
+done
+done
 timeout 200 python tools/probe_train.py 4000 10 5 2>&1 | cut -c1-110
-timeout 600 python -m pytest tests/test_train_gpu.py -x -q 2>&1 | tail -3
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -s 330 -c 420 --csv --log-file gpurun_out/launches_train.csv python tools/probe_train.py 4000 2 > /dev/null 2>&1
-python tools/launch_summary.py gpurun_out/launches_train.csv > gpurun_out/launch_summary_train.txt 2>&1; head -8 gpurun_out/launch_summary_train.txt
+timeout 600 python -m pytest tests/test_train_gpu.py tests/test_net_gpu.py -x -q 2>&1 | tail -3
+timeout 300 ./build/conv_selftest 5180 6 8 1 2>&1 | tail -4
