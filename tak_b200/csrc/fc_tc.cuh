@@ -36,13 +36,22 @@ constexpr int FC_SMEM_BYTES = FC_STAGES * FC_STAGE_BYTES + 1024;
 
 struct FcParams {
     const __nv_bfloat16* wp;   // [jt][pos][slab 8][kc 2][128][8]
-    const __nv_bfloat16* x;    // [pos][chunk 16][b_pad][8]
+    const __nv_bfloat16* x;    // [pos][board tile of FC_NT][chunk 16][FC_NT boards][8]: one stage's B operand is ONE
+                               // contiguous 64 KiB block (fc_x_offset)
     const float* bias;         // [n_out]
     float* logits;             // [boards][n_out]
     int n_out, boards, b_pad, n_pos, j_tiles, n_tiles;
 };
 
-// trunk output strip planes -> X[pos][chunk][board][8]; boards >= n_boards (padding up to b_pad) are written as zero
+// Element offset (in units of 8 channels = 16 B) of (position p, channel chunk, column n) in an X image of n_pad
+// columns: [p][n / FC_NT][chunk][n % FC_NT].  A GEMM stage (one position, one tile of FC_NT columns, all 16 chunks) is
+// contiguous, so the producer fetches it with ONE bulk copy -- as [p][chunk][n_pad] it took 16 copies of 4 KiB, and the
+// copy engine's per-copy cost (~70 ns, measured on the wgrad kernel) exceeded the stage's 8 MMAs.
+__host__ __device__ inline size_t fc_x_offset(int p, int chunk, int n, int n_pad) {
+    return ((size_t(p) * (n_pad / FC_NT) + n / FC_NT) * 16 + chunk) * FC_NT + n % FC_NT;
+}
+
+// trunk output strip planes -> X image (fc_x_offset); boards >= n_boards (padding up to b_pad) are written as zero
 template <int N, bool PF = false>
 __global__ void __launch_bounds__(256) k_fc_repack(const __nv_bfloat16* act, int S, int n_boards, int b_pad,
                                                    __nv_bfloat16* x) {
@@ -53,7 +62,7 @@ __global__ void __launch_bounds__(256) k_fc_repack(const __nv_bfloat16* act, int
     uint4 v = make_uint4(0, 0, 0, 0);
     if (b < n_boards)
         v = *reinterpret_cast<const uint4*>(act + (size_t(chunk) * S + SlotMap<N, PF>::slot(b, pos / N, pos % N)) * 8);
-    *reinterpret_cast<uint4*>(x + idx * 8) = v;
+    *reinterpret_cast<uint4*>(x + fc_x_offset(pos, chunk, b, b_pad) * 8) = v;
 }
 
 static __global__ void __launch_bounds__(FC_THREADS, 1) fc_tc_kernel(const __grid_constant__ FcParams p) {
@@ -97,11 +106,8 @@ static __global__ void __launch_bounds__(FC_THREADS, 1) fc_tc_kernel(const __gri
                     const uint32_t dst = smem_u32(smem + sb * FC_STAGE_BYTES);
                     bulk_g2s(dst, reinterpret_cast<const uint8_t*>(p.wp) + (size_t(jt) * p.n_pos + pos) * FC_W_POS_BYTES,
                              FC_W_POS_BYTES, FULL_(sb));
-                    const uint8_t* xs = reinterpret_cast<const uint8_t*>(p.x) +
-                                        (size_t(pos) * 16 * p.b_pad + size_t(nt) * FC_NT) * 16;
-                    for (int c = 0; c < 16; ++c)
-                        bulk_g2s(dst + FC_W_POS_BYTES + c * (FC_NT * 16), xs + size_t(c) * p.b_pad * 16, FC_NT * 16,
-                                 FULL_(sb));
+                    bulk_g2s(dst + FC_W_POS_BYTES, reinterpret_cast<const uint8_t*>(p.x) + fc_x_offset(pos, 0, nt * FC_NT, p.b_pad) * 16,
+                             16 * FC_NT * 16, FULL_(sb));
                 }
             }
         }

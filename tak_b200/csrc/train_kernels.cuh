@@ -526,7 +526,7 @@ __device__ __forceinline__ size_t fc_a_index(int m, int kk, int P) {      // ele
 }
 __device__ __forceinline__ size_t fc_x_index(int n, int kk, int n_pad) {  // element (kk, n) of an X image
     const int p = kk >> 7, c = kk & 127;
-    return ((size_t(p) * 16 + (c >> 3)) * n_pad + n) * 8 + (c & 7);
+    return fc_x_offset(p, c >> 3, n, n_pad) * 8 + (c & 7);
 }
 
 // forward / dgrad operand images of the fp32 master W[J][K] (K = 128*NSQ, column k = c*NSQ + pos)
