@@ -5,6 +5,7 @@
 
 #include <climits>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 
 #include "game_kernels.cuh"
@@ -174,11 +175,11 @@ int mcts_eval_and_backup(tak_engine* e) {
 static int launch_step(tak_engine* e, const int* d_ids, int n, const uint8_t* d_enable, const FastEval& fe,
                        const PriorSource& ps, int do_backup, int do_rollout, int reps) {
     MctsState& m = *e->mcts;
-    // With a network, the search of one engine replica should run BESIDE the other replica's conv tower: a tower CTA
-    // (352 threads x 168 registers) leaves 6 400 registers free on its SM, so the step kernel is built with a 64-register
-    // cap (32 bytes of spills) and launched in 64-thread blocks = 4 096 registers.  Measured on one box, 2 replicas x
-    // 5 328 games: 3 707 moves/s against 3 623 with the uncapped 132-register build, whose blocks do not fit
-    // (TAK_STEP_REGS=128 selects it; the DummyNet loop has no tower to hide under and always uses it).
+    // The 64-register / 64-thread build was meant to run BESIDE the other engine replica's conv tower.  It does not: a
+    // tower CTA (11 warps x 168 registers, allocated in units of 4 warps = 64 512 registers) leaves 1 024 registers on its
+    // SM, and no block shape / register cap / stream priority made the step co-resident (profiles/r02_step_overlap.md);
+    // the capped build is kept because it costs nothing measurable (3 858-3 920 moves/s for every variant).
+    // TAK_STEP_REGS=128 selects the uncapped build; the DummyNet loop always uses it.
     static const int regs = [] {
         const char* s = std::getenv("TAK_STEP_REGS");
         return s ? std::atoi(s) : 64;
@@ -188,7 +189,7 @@ static int launch_step(tak_engine* e, const int* d_ids, int n, const uint8_t* d_
         const char* s = std::getenv("TAK_STEP_WARPS");
         return s ? std::atoi(s) : 2;
     }();
-    if (capped && e->n == 6 && cwarps == 3) {      // 3 warps x 64 registers = 6 144 of the 6 400 a tower CTA leaves free
+    if (capped && e->n == 6 && cwarps == 3) {      // 3 warps x 64 registers (A/B variant)
         k_mcts_step<6, 96, 10><<<(n + 2) / 3, 96, 0, e->stream>>>(m.view(), e->states.as<uint8_t>(), d_ids, n, d_enable, fe,
                                                                   ps, do_backup, do_rollout, reps);
     } else if (capped && e->n == 6) {
@@ -228,6 +229,14 @@ int mcts_fast_rollouts(tak_engine* e, const int* d_ids, int n, int reps, const u
     int* cnt = m.eval_count.as<int>() + 2;   // [2], [3]: the two phases of the loop ([0] belongs to the compaction path)
     TB_CUDA(cudaMemsetAsync(cnt, 0, 8, e->stream));
     fe.eval_slot = m.eval_slot.as<int>();
+    // TAK_STEP_TIMING=1 (profiling aid, tools/probe_overlap.py): CUDA events around the step kernel in the middle of the loop
+    static const bool timing = [] { const char* v = std::getenv("TAK_STEP_TIMING"); return v && std::atoi(v) != 0; }();
+    cudaEvent_t tev[2] = {nullptr, nullptr};
+    const bool timed_one = timing && reps >= 4;
+    if (timed_one) {
+        TB_CUDA(cudaEventCreate(&tev[0]));
+        TB_CUDA(cudaEventCreate(&tev[1]));
+    }
     int phase = 0;
     fe.eval_count = cnt + phase;
     fe.eval_count_reset = cnt + (phase ^ 1);
@@ -237,12 +246,23 @@ int mcts_fast_rollouts(tak_engine* e, const int* d_ids, int n, int reps, const u
         phase ^= 1;
         fe.eval_count = cnt + phase;
         fe.eval_count_reset = cnt + (phase ^ 1);
+        if (timed_one && i == reps / 2) TB_CUDA(cudaEventRecord(tev[0], e->stream));
         if (int r = launch_step(e, d_ids, n, d_enable, fe, ps, 1, 1, 1)) return r;
+        if (timed_one && i == reps / 2) TB_CUDA(cudaEventRecord(tev[1], e->stream));
     }
     if (int r = net_tower_fast(e, n, cnt + phase)) return r;
     fe.eval_count = nullptr;
     fe.eval_count_reset = nullptr;
     if (int r = launch_step(e, d_ids, n, nullptr, fe, ps, 1, 0, 1)) return r;
+    if (timed_one) {   // event to event: includes the time the kernel waits for SMs held by another replica's tower
+        TB_CUDA(cudaEventSynchronize(tev[1]));
+        float ms = 0;
+        TB_CUDA(cudaEventElapsedTime(&ms, tev[0], tev[1]));
+        fprintf(stderr, "[step timing] engine %p: k_mcts_step of iteration %d of %d took %.1f us (n = %d)\n", (void*)e,
+                reps / 2, reps, ms * 1e3, n);
+        cudaEventDestroy(tev[0]);
+        cudaEventDestroy(tev[1]);
+    }
     m.queued = false;
     return TAK_OK;
 }
