@@ -199,8 +199,15 @@ struct TowerWalk {
     __device__ int group_size(int g) const { return base + (g < rem ? 1 : 0); }
 };
 
+// TAK_TOWER_LOWREG=1: the pad-free inference build is compiled for at most 128 registers per thread (a 512-thread launch
+// bound; it is still launched with 352), so that 12 allocated warps x 4 096 registers leave 16 384 on the SM: room for
+// eight warps of the other engine replica's search step beside a resident tower CTA (profiles/r02_step_overlap.md).
+#ifndef TAK_TOWER_LOWREG
+#define TAK_TOWER_LOWREG 0
+#endif
 template <bool TRAIN, bool PF = false>
-static __global__ void __launch_bounds__(C3_THREADS, 1) conv3x3_tc3_kernel(const __grid_constant__ ConvParams p) {
+static __global__ void __launch_bounds__((TAK_TOWER_LOWREG && PF && !TRAIN) ? 512 : C3_THREADS, 1)
+conv3x3_tc3_kernel(const __grid_constant__ ConvParams p) {
     static_assert(!(TRAIN && PF), "the training build keeps the padded strip");
     constexpr int STAGES = PF ? C3_PF_STAGES : C3_STAGES;
     constexpr int STAGE_BYTES = PF ? C3_PF_STAGE_BYTES : C3_STAGE_BYTES;
