@@ -74,6 +74,9 @@ __device__ __forceinline__ void encode_board(const WarpGame<N>& g, int w, __nv_b
         const int kind = ((g.walls >> o) & 1) ? 1 : ((g.caps >> o) & 1) ? 2 : 0;
         const int x = o / N, y = o % N;
         const size_t slot = SlotMap<N, PF>::slot(w, y, x);
+        // unrolled: with the channel a compile-time constant repr_plane folds to a compare or a bit test per value (rolled,
+        // its chain of range checks was a fifth of the search step's instructions, profiles/r02_mcts_step_ncu_full_g4144.txt)
+#pragma unroll
         for (int chunk = 0; chunk < 16; ++chunk) {
             uint4 v;
             __nv_bfloat162* vb = reinterpret_cast<__nv_bfloat162*>(&v);
