@@ -365,8 +365,8 @@ __global__ void __launch_bounds__(GAME_THREADS)
 // only this game's tree, so they need no grid-wide ordering and live in one launch: the loop is {k_mcts_step; tower} x R.
 // With the DummyNet (arch 0: prior 1, eval 0 -- nothing to evaluate) the whole loop of `reps` rollouts is ONE launch.
 // MINB = minimum resident blocks per SM the compiler must allow for (register cap = 65536 / (MAXT * MINB)): the default
-// build lets the kernel have its 128 registers; the capped builds (TAK_STEP_REGS) exist to measure whether a block that
-// fits beside a resident conv-tower CTA buys overlap.
+// build lets the kernel have its 128 registers; the capped builds (TAK_STEP_REGS) were made to measure whether a smaller
+// block runs beside a resident conv-tower CTA (it does not: profiles/r02_step_overlap.md).
 template <int N, int MAXT = 128, int MINB = 1>
 __global__ void __launch_bounds__(MAXT, MINB)
     k_mcts_step(MctsView v, const uint8_t* states, const int* ids, int n, const uint8_t* enable, FastEval fe,

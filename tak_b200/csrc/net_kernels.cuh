@@ -92,8 +92,8 @@ __device__ __forceinline__ void encode_board(const WarpGame<N>& g, int w, __nv_b
 }
 
 // one warp per board; `states` = packed records of the boards to encode (index list optional).
-// (launch bounds: at most 40 registers per thread, so that a block fits in the 11 776 registers a resident conv-tower
-// CTA of the OTHER engine replica leaves free on an SM -- at 42 the encode of one replica waited for the other's tower)
+// (launch bounds: at most 40 registers per thread.  The cap dates from the attempt to run this kernel beside the other
+// engine replica's conv tower; nothing fits beside a tower CTA -- profiles/r02_step_overlap.md -- but the cap costs nothing)
 template <int N>
 __global__ void __launch_bounds__(256, 6)
     k_encode(const uint8_t* states, const int* index, int n_boards, __nv_bfloat16* planes, int S,
